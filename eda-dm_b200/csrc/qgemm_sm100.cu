@@ -1,0 +1,450 @@
+// W4A8 / W8A8 QuantModule GEMM for sm_100a (replaces qdiff/quant_layer.py:434
+// F.conv2d / F.conv1d / F.linear on fake-quant operands).
+//
+//   D[m][n] = sum_k  Aq[m][k] * Wq[n][k]          (u8 x s8 -> s32, exact)
+//   out     = dA * dW[n] * (D + cw[n]*rowsum[m] - zA * wsum_eff[n]) + bias[n]   (+ SiLU) (+ prev out)
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer   : A tile (128 pixels x 128 B of channels, one filter tap per K step) through a
+//                                rank-4 tiled tensor map over the halo-padded NHWC code tensor -- the implicit
+//                                GEMM needs no im2col buffer, out-of-range channels are zero-filled by TMA;
+//                                B tile (BLOCK_N out-channels x 128 B) through a rank-3 map over [Np][taps][Cp].
+//   warp 1      MMA issuer     : tcgen05.mma.cta_group::1.kind::i8, M=128, N=BLOCK_N (multiple of 16, <=256),
+//                                K=32 per instruction, accumulators in TMEM (2 stages x 256 columns).
+//   warps 2..5  epilogue       : tcgen05.ld 32x32b -> zero-point fold, per-channel dequant, bias, SiLU ->
+//                                coalesced NCHW stores (TMEM lane == output pixel == consecutive address).
+// Shared memory: 4 pipeline stages x (16 KB A + 32 KB B), 128B-swizzled K-major operands.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace edadm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 128;        // bytes == int8 elements per K step (one 128B swizzle atom)
+constexpr int MAX_BLOCK_N = 256;
+constexpr int STAGES = 4;
+constexpr int UMMA_K = 32;          // kind::i8: 32 bytes of K per instruction
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K;
+constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = 512;
+constexpr int GEMM_THREADS = 192;
+constexpr uint64_t SPIN_LIMIT_CYCLES = 4000000000ull;  // ~2 s: a wedged pipeline traps instead of hanging the box
+
+struct GemmParams {
+  // problem
+  int M, N, taps, S;        // M output rows, N out channels, taps = R*S filter taps, S = filter width
+  int k_chunks;             // ceil(Cp_range / 128) K steps per tap
+  int k_last_mmas;          // MMAs (of 32 B) in the last chunk of each tap
+  int a_c_offset;           // first channel of this K range inside the activation tensor (split shortcut)
+  // tile -> coordinate mapping of the activation tensor map (dims: C, W, H, B)
+  int Wo, HoWo;             // output row length and pixels per image (2-D GEMM: Wo = HoWo = 2^30)
+  int block_n, n_tiles, m_tiles;
+  // epilogue
+  int out_hw;               // pixels per image of the OUTPUT layout (1 => row-major [M][N])
+  int accumulate, silu;
+  const float* delta_a;     // device scalars (nn.Parameter storage): no host sync on the path
+  const float* zp_a;
+  const float* delta_w;     // [N]
+  const int32_t* wsum_eff;  // [N]  sum_k Wq + Kreal*cw
+  const int32_t* cw;        // [N] or null
+  const int32_t* rowsum;    // [M] or null (required when cw != null)
+  const float* bias;        // [N] or null
+  float* out;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if ((uint64_t)(clock64() - t0) > SPIN_LIMIT_CYCLES) {
+      printf("edadm qgemm: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+// (descriptor fields: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout=SWIZZLE_128B(2) [61,64))
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor: D=s32, A=u8, B=s8, both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t make_idesc_i8(int n, int a_signed, int b_signed) {
+  return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct __align__(8) PipeBarriers {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tmem_full[ACC_STAGES];
+  uint64_t tmem_empty[ACC_STAGES];
+  uint32_t tmem_base;
+};
+
+constexpr int EPI_VEC_BYTES = MAX_BLOCK_N * 4 * 4;  // scale, zterm, cw, bias per column
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_VEC_BYTES + 256;
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  float* epi_scale = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  int* epi_zterm = reinterpret_cast<int*>(epi_scale + MAX_BLOCK_N);
+  int* epi_cw = epi_zterm + MAX_BLOCK_N;
+  float* epi_bias = reinterpret_cast<float*>(epi_cw + MAX_BLOCK_N);
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(epi_bias + MAX_BLOCK_N);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int k_iters = p.taps * p.k_chunks;
+  const uint32_t stage_tx = A_STAGE_BYTES + (uint32_t)p.block_n * BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 4); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+        const int m0 = m_blk * BLOCK_M;
+        const int b0 = m0 / p.HoWo;
+        const int rem = m0 - b0 * p.HoWo;
+        const int oh0 = rem / p.Wo, ow0 = rem - oh0 * p.Wo;
+        const int n0 = n_blk * p.block_n;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int kh = tap / p.S, kw = tap - kh * p.S;
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(&bars->empty[stage], phase ^ 1);
+            mbar_expect_tx(&bars->full[stage], stage_tx);
+            tma_load_4d(smem_a + stage * A_STAGE_BYTES, &map_a, &bars->full[stage], p.a_c_offset + kc * BLOCK_K, ow0 + kw, oh0 + kh, b0);
+            tma_load_3d(smem_b + stage * B_STAGE_BYTES, &map_b, &bars->full[stage], kc * BLOCK_K, tap, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_i8(p.block_n, /*A u8*/ 0, /*B s8*/ 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BLOCK_N;
+        for (int it = 0; it < k_iters; ++it) {
+          const int kc = it % p.k_chunks;
+          const int nmma = (kc == p.k_chunks - 1) ? p.k_last_mmas : BLOCK_K / UMMA_K;
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+          for (int k = 0; k < nmma; ++k)
+            umma_i8(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)), idesc, (it | k) ? 1u : 0u);
+          umma_commit(&bars->empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&bars->tmem_full[acc]);
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    const int row_in_tile = quarter * 32 + lane;
+    const int et = threadIdx.x - 64;              // 0..127
+    const float da = __ldg(p.delta_a);
+    const int za = (int)__ldg(p.zp_a);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+      const int n0 = n_blk * p.block_n;
+      // stage per-column vectors
+      for (int j = et; j < p.block_n; j += 128) {
+        const int n = n0 + j;
+        const bool ok = n < p.N;
+        epi_scale[j] = ok ? da * __ldg(p.delta_w + n) : 0.f;
+        epi_zterm[j] = ok ? -za * __ldg(p.wsum_eff + n) : 0;
+        epi_cw[j] = (ok && p.cw) ? __ldg(p.cw + n) : 0;
+        epi_bias[j] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int m = m_blk * BLOCK_M + row_in_tile;
+      const bool row_ok = m < p.M;
+      const int rs = (row_ok && p.rowsum) ? __ldg(p.rowsum + m) : 0;
+      const long long img = row_ok ? m / p.out_hw : 0;
+      const long long pix = row_ok ? m - img * p.out_hw : 0;
+      float* out_row = p.out + img * (long long)p.N * p.out_hw + pix;
+
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BLOCK_N;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < p.N) {
+              // zero-point fold in int32 (exact: |terms| < 2^30), one rounding when converting to fp32
+              const float iv = (float)((int)r[j] + epi_cw[c0 + j] * rs + epi_zterm[c0 + j]);
+              float v = iv * epi_scale[c0 + j] + epi_bias[c0 + j];
+              float* dst = out_row + (long long)n * p.out_hw;
+              if (p.accumulate) v += *dst;
+              if (p.silu) v = v / (1.f + __expf(-v));
+              *dst = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // epi_* vectors are rewritten next tile
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(EDADM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EDADM_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return EDADM_OK;
+}
+
+// choose the N tile: the multiple of 16 (<=256) that covers N in the fewest tiles with the least padding
+static int pick_block_n(int N) {
+  const int tiles = (N + MAX_BLOCK_N - 1) / MAX_BLOCK_N;
+  int bn = (N + tiles - 1) / tiles;
+  bn = (bn + 15) & ~15;
+  if (bn < 16) bn = 16;
+  return bn;
+}
+
+}  // namespace edadm
+
+using namespace edadm;
+
+// Activation codes q: [B][Hp][Wp][Cp_act] u8 (halo included), filter R x S, stride 1:  Ho = Hp-R+1, Wo = Wp-S+1.
+// A 2-D GEMM ([M][Kp] rows) is the special case B=1, Hp=1, Wp=M, R=S=1.
+// Weights wq: [Np][R*S][Cp_w] s8 with Np >= round_up(N, block_n) rows allocated (pack_weight pads with zeros).
+extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const int8_t* wq,
+                              int N, int Np, int R, int S, int Cp_w, const float* delta_a, const float* zp_a,
+                              const float* delta_w, const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum,
+                              const float* bias, float* out, int out_hw, int accumulate, int silu, void* stream) {
+  if (!q || !wq || !delta_a || !zp_a || !delta_w || !wsum_eff || !out) return fail(EDADM_ERR_ARG, "qgemm_i8: null pointer");
+  if (cw && !rowsum) return fail(EDADM_ERR_ARG, "qgemm_i8: cw given without rowsum");
+  if (B < 1 || Hp < R || Wp < S || R < 1 || S < 1 || N < 1 || (Cp_act & 15) || (Cp_w & 15) || Cp_w < 16 || a_c_offset < 0 ||
+      a_c_offset + 16 > Cp_act + 15)
+    return fail(EDADM_ERR_ARG, "qgemm_i8: bad geometry B=%d Hp=%d Wp=%d Cp_act=%d Cp_w=%d R=%d S=%d N=%d", B, Hp, Wp, Cp_act, Cp_w, R, S, N);
+  if ((((uintptr_t)q) & 15) || (((uintptr_t)wq) & 15)) return fail(EDADM_ERR_ARG, "qgemm_i8: operands must be 16-byte aligned");
+  const int Ho = Hp - R + 1, Wo = Wp - S + 1;
+  const long long M = (long long)B * Ho * Wo;
+  if (M > 0x7fffffffLL) return fail(EDADM_ERR_UNSUPPORTED, "qgemm_i8: M too large");
+  if (out_hw < 1 || (M % out_hw) != 0) return fail(EDADM_ERR_ARG, "qgemm_i8: out_hw=%d does not divide M=%lld", out_hw, M);
+
+  // tile box over (W, H, B): 128 consecutive output pixels
+  int box_w, box_h, box_b;
+  const bool flat = (Ho == 1 && B == 1);
+  if (flat) {
+    box_w = BLOCK_M; box_h = 1; box_b = 1;
+  } else if (Wo >= BLOCK_M) {
+    if (Wo % BLOCK_M) return fail(EDADM_ERR_UNSUPPORTED, "qgemm_i8: output width %d not a multiple of 128", Wo);
+    box_w = BLOCK_M; box_h = 1; box_b = 1;
+  } else {
+    if (BLOCK_M % Wo) return fail(EDADM_ERR_UNSUPPORTED, "qgemm_i8: output width %d does not divide 128 (use the im2col route)", Wo);
+    box_w = Wo;
+    const int rows = BLOCK_M / Wo;
+    if (rows <= Ho) {
+      if (Ho % rows) return fail(EDADM_ERR_UNSUPPORTED, "qgemm_i8: output height %d not a multiple of %d rows per tile", Ho, rows);
+      box_h = rows; box_b = 1;
+    } else {
+      if (rows % Ho) return fail(EDADM_ERR_UNSUPPORTED, "qgemm_i8: %d rows per tile not a multiple of output height %d", rows, Ho);
+      box_h = Ho; box_b = rows / Ho;
+    }
+  }
+
+  const int block_n = pick_block_n(N);
+  const int n_tiles = (N + block_n - 1) / block_n;
+  if (Np < n_tiles * block_n) return fail(EDADM_ERR_ARG, "qgemm_i8: weight rows Np=%d < %d needed by the N tiling", Np, n_tiles * block_n);
+
+  CUtensorMap map_a, map_b;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)Cp_act, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cp_act, (cuuint64_t)Wp * Cp_act, (cuuint64_t)Hp * Wp * Cp_act};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_b};
+    int rc = encode_map(&map_a, q, 4, dims, strides, box, "activations");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Cp_w, (cuuint64_t)(R * S), (cuuint64_t)Np};
+    cuuint64_t strides[2] = {(cuuint64_t)Cp_w, (cuuint64_t)R * S * Cp_w};
+    cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, 1u, (cuuint32_t)block_n};
+    int rc = encode_map(&map_b, wq, 3, dims, strides, box, "weights");
+    if (rc) return rc;
+  }
+
+  GemmParams p;
+  p.M = (int)M; p.N = N; p.taps = R * S; p.S = S;
+  p.k_chunks = (Cp_w + BLOCK_K - 1) / BLOCK_K;
+  const int last_bytes = Cp_w - (p.k_chunks - 1) * BLOCK_K;
+  p.k_last_mmas = (last_bytes + UMMA_K - 1) / UMMA_K;
+  p.a_c_offset = a_c_offset;
+  p.Wo = flat ? (1 << 30) : Wo;
+  p.HoWo = flat ? (1 << 30) : Ho * Wo;
+  p.block_n = block_n; p.n_tiles = n_tiles; p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  p.out_hw = out_hw; p.accumulate = accumulate; p.silu = silu;
+  p.delta_a = delta_a; p.zp_a = zp_a; p.delta_w = delta_w; p.wsum_eff = wsum_eff; p.cw = cw; p.rowsum = rowsum;
+  p.bias = bias; p.out = out;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(qgemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return fail(EDADM_ERR_CUDA, "qgemm_i8: cannot opt in to %d B shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  qgemm_i8_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_b, p);
+  return check_launch("qgemm_i8");
+}

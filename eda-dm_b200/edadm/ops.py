@@ -1,0 +1,386 @@
+"""Torch-facing wrappers around the C ABI (include/edadm.h).
+
+Every function takes CUDA fp32 tensors, enqueues kernels on the current torch stream and returns
+torch tensors; autograd.Function classes wire the hand-written backward kernels in.  Nothing here
+computes on the CPU: non-CUDA inputs raise.
+"""
+import math
+from typing import Optional
+
+import torch
+
+from .native import lib, EdadmError
+
+_partials_cache = {}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise EdadmError("edadm ops need CUDA tensors (no CPU fallback for the quantized path)")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _partials(device) -> torch.Tensor:
+    key = (device.type, device.index)
+    buf = _partials_cache.get(key)
+    if buf is None:
+        buf = torch.empty(lib.reduce_slots(), dtype=torch.float64, device=device)
+        _partials_cache[key] = buf
+    return buf
+
+
+def _chan_layout(x: torch.Tensor, delta: torch.Tensor):
+    """channels / inner of a per-tensor or per-dim-0 (weight, quant_layer.py:111-114) quantizer."""
+    nd = delta.numel()
+    if nd == 1:
+        return 1, 1
+    if nd != x.shape[0]:
+        raise EdadmError(f"delta with {nd} elements does not match dim 0 of {tuple(x.shape)}")
+    return nd, x.numel() // nd
+
+
+def _qparam(t, device) -> torch.Tensor:
+    """delta / zero_point as a contiguous fp32 device tensor (they are tensors / Parameters in qdiff)."""
+    if not torch.is_tensor(t):
+        t = torch.tensor(float(t), dtype=torch.float32, device=device)
+    t = t.detach()
+    if t.device != device or t.dtype != torch.float32:
+        t = t.to(device=device, dtype=torch.float32)
+    return t.contiguous().reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# K2  UniformAffineQuantizer
+# ------------------------------------------------------------------------------------------------
+def uaq_forward(x, delta, zero_point, n_levels, keep_mask=None, prob=1.0, seed=0, offset=0, want_codes=False):
+    _need_cuda(x)
+    x = _f32c(x)
+    d = _qparam(delta, x.device)
+    z = _qparam(zero_point, x.device)
+    channels, inner = _chan_layout(x, d)
+    if z.numel() != d.numel():
+        z = z.expand(d.numel()).contiguous() if z.numel() == 1 else z
+    y = torch.empty_like(x)
+    codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_codes else None
+    if keep_mask is not None:
+        keep_mask = keep_mask.to(torch.uint8).contiguous()
+    lib.uaq_fwd(x.data_ptr(), y.data_ptr(), _ptr(codes), d.data_ptr(), z.data_ptr(), x.numel(), channels, inner,
+                int(n_levels), _ptr(keep_mask), float(prob), int(seed), int(offset), _stream())
+    return (y, codes) if want_codes else y
+
+
+class UAQFunction(torch.autograd.Function):
+    """Fake-quant with straight-through gradient (quant_layer.py:19-23, 267-274) as one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, x, delta, zero_point, n_levels, keep_mask, prob, seed, offset):
+        xc = _f32c(x)
+        y = uaq_forward(xc, delta, zero_point, n_levels, keep_mask, prob, seed, offset)
+        ctx.save_for_backward(xc, delta, zero_point, keep_mask if keep_mask is not None else torch.empty(0))
+        ctx.meta = (int(n_levels), float(prob), int(seed), int(offset), keep_mask is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, delta, zero_point, keep_mask = ctx.saved_tensors
+        n_levels, prob, seed, offset, has_mask = ctx.meta
+        gy = _f32c(gy)
+        d = _qparam(delta, x.device)
+        z = _qparam(zero_point, x.device)
+        channels, inner = _chan_layout(x, d)
+        gx = torch.empty_like(x)
+        want_gd = ctx.needs_input_grad[1] and channels == 1
+        gd = torch.zeros(1, dtype=torch.float32, device=x.device) if want_gd else None
+        mask = keep_mask.to(torch.uint8).contiguous() if has_mask else None
+        lib.uaq_bwd(gy.data_ptr(), x.data_ptr(), d.data_ptr(), z.data_ptr(), x.numel(), channels, inner, n_levels,
+                    _ptr(mask), prob, seed, offset, gx.data_ptr(), _ptr(gd), 0,
+                    _partials(x.device).data_ptr() if want_gd else None, _stream())
+        gdelta = gd.reshape(delta.shape) if want_gd else None
+        return gx, gdelta, None, None, None, None, None, None
+
+
+def uaq_fake_quant(x, delta, zero_point, n_levels, keep_mask=None, prob=1.0, seed=0, offset=0):
+    return UAQFunction.apply(x, delta, zero_point, n_levels, keep_mask, prob, seed, offset)
+
+
+# ------------------------------------------------------------------------------------------------
+# K3  AdaRound
+# ------------------------------------------------------------------------------------------------
+def adaround_init_alpha(w, delta):
+    _need_cuda(w)
+    w = _f32c(w)
+    d = _qparam(delta, w.device)
+    channels, inner = _chan_layout(w, d)
+    alpha = torch.empty_like(w)
+    lib.adaround_init_alpha(w.data_ptr(), d.data_ptr(), w.numel(), channels, inner, alpha.data_ptr(), _stream())
+    return alpha
+
+
+def adaround_forward(w, alpha, delta, zero_point, n_levels, soft, want_codes=False):
+    _need_cuda(w, alpha)
+    w = _f32c(w)
+    a = _f32c(alpha.detach())
+    d = _qparam(delta, w.device)
+    z = _qparam(zero_point, w.device)
+    channels, inner = _chan_layout(w, d)
+    out = torch.empty_like(w)
+    codes = torch.empty(w.shape, dtype=torch.uint8, device=w.device) if want_codes else None
+    lib.adaround_fwd(w.data_ptr(), a.data_ptr(), d.data_ptr(), z.data_ptr(), w.numel(), channels, inner,
+                     int(n_levels), 1 if soft else 0, out.data_ptr(), _ptr(codes), _stream())
+    return (out, codes) if want_codes else out
+
+
+class AdaRoundFunction(torch.autograd.Function):
+    """W~ = (clamp(floor(W/d) + h(alpha) + zp) - zp) * d with d W~ / d alpha (adaptive_rounding.py:49-64)."""
+
+    @staticmethod
+    def forward(ctx, w, alpha, delta, zero_point, n_levels, soft):
+        out = adaround_forward(w, alpha, delta, zero_point, n_levels, soft)
+        ctx.save_for_backward(w, alpha, delta, zero_point)
+        ctx.meta = (int(n_levels), bool(soft))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        w, alpha, delta, zero_point = ctx.saved_tensors
+        n_levels, soft = ctx.meta
+        if not soft or not ctx.needs_input_grad[1]:
+            return None, None, None, None, None, None
+        gout = _f32c(gout)
+        wc = _f32c(w)
+        a = _f32c(alpha.detach())
+        d = _qparam(delta, w.device)
+        z = _qparam(zero_point, w.device)
+        channels, inner = _chan_layout(wc, d)
+        ga = torch.empty_like(a)
+        lib.adaround_bwd(gout.data_ptr(), wc.data_ptr(), a.data_ptr(), d.data_ptr(), z.data_ptr(), wc.numel(), channels,
+                         inner, n_levels, ga.data_ptr(), 0, _stream())
+        return None, ga, None, None, None, None
+
+
+def adaround_fake_quant(w, alpha, delta, zero_point, n_levels, soft):
+    return AdaRoundFunction.apply(w, alpha, delta, zero_point, n_levels, soft)
+
+
+class RoundRegFunction(torch.autograd.Function):
+    """weight * sum(1 - |2 h(alpha) - 1|^b)  (block_recon.py:286-291)."""
+
+    @staticmethod
+    def forward(ctx, alpha, b, weight):
+        a = _f32c(alpha.detach())
+        loss = torch.zeros(1, dtype=torch.float32, device=a.device)
+        lib.round_reg(a.data_ptr(), a.numel(), float(b), float(weight), _partials(a.device).data_ptr(), loss.data_ptr(),
+                      0, None, _stream())
+        ctx.save_for_backward(a)
+        ctx.meta = (float(b), float(weight))
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (a,) = ctx.saved_tensors
+        b, weight = ctx.meta
+        ga = torch.zeros_like(a)
+        scratch = torch.zeros(1, dtype=torch.float32, device=a.device)
+        lib.round_reg(a.data_ptr(), a.numel(), b, weight, _partials(a.device).data_ptr(), scratch.data_ptr(), 0,
+                      ga.data_ptr(), _stream())
+        return ga * g, None, None
+
+
+def round_reg(alpha, b, weight):
+    return RoundRegFunction.apply(alpha, b, weight)
+
+
+# ------------------------------------------------------------------------------------------------
+# K4  L_p loss
+# ------------------------------------------------------------------------------------------------
+class LpLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, tgt, p, per_dim1):
+        _need_cuda(pred, tgt)
+        pc, tc = _f32c(pred), _f32c(tgt.detach())
+        n = pc.numel()
+        if per_dim1:  # .sum(1).mean()
+            inv_rest = pc.shape[1] / n if n else 0.0
+        else:         # .mean()
+            inv_rest = 1.0 / n if n else 0.0
+        loss = torch.empty(1, dtype=torch.float32, device=pc.device)
+        lib.lp_loss_fwd(pc.data_ptr(), tc.data_ptr(), n, float(p), float(inv_rest), _partials(pc.device).data_ptr(),
+                        loss.data_ptr(), _stream())
+        ctx.save_for_backward(pc, tc)
+        ctx.meta = (float(p), float(inv_rest))
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        pc, tc = ctx.saved_tensors
+        p, inv_rest = ctx.meta
+        g = _f32c(g).reshape(1)
+        gp = torch.empty_like(pc)
+        lib.lp_loss_bwd(pc.data_ptr(), tc.data_ptr(), pc.numel(), p, inv_rest, g.data_ptr(), gp.data_ptr(), _stream())
+        return gp, None, None, None
+
+
+def lp_loss(pred, tgt, p=2.0, reduction="none"):
+    """Same meaning as qdiff.quant_layer.lp_loss (quant_layer.py:26-33)."""
+    return LpLossFunction.apply(pred, tgt, p, reduction == "none")
+
+
+# ------------------------------------------------------------------------------------------------
+# K1  integer path
+# ------------------------------------------------------------------------------------------------
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+_BLOCK_M = 128
+_MAX_BLOCK_N = 256
+
+
+def gemm_block_n(n: int) -> int:
+    tiles = (n + _MAX_BLOCK_N - 1) // _MAX_BLOCK_N
+    bn = _round_up((n + tiles - 1) // tiles, 16)
+    return max(bn, 16)
+
+
+def gemm_padded_n(n: int) -> int:
+    bn = gemm_block_n(n)
+    return bn * ((n + bn - 1) // bn)
+
+
+class PackedWeight:
+    """Integer weight codes of one QuantModule K-range in the layout the GEMM consumes."""
+
+    __slots__ = ("wq", "wsum_eff", "cw", "delta_w", "N", "Np", "R", "S", "C", "Cp", "needs_rowsum", "codes")
+
+    def nbytes(self):
+        return self.wq.numel()
+
+
+def pack_weight(w, delta, zero_point, n_levels, alpha=None, c_begin=0, c_end=None, want_codes=False) -> PackedWeight:
+    """w: [N, C, R, S] / [N, C, T] / [N, C] fp32 -> PackedWeight for channels [c_begin, c_end)."""
+    _need_cuda(w)
+    w = _f32c(w.detach())
+    N, Ctot = w.shape[0], w.shape[1]
+    if w.dim() == 4:
+        R, S = w.shape[2], w.shape[3]
+    elif w.dim() == 3:
+        R, S = 1, w.shape[2]
+    else:
+        R, S = 1, 1
+    c_end = Ctot if c_end is None else c_end
+    Cr = c_end - c_begin
+    Cp = _round_up(Cr, 16)
+    Np = gemm_padded_n(N)
+    d = _qparam(delta, w.device)
+    z = _qparam(zero_point, w.device)
+    if d.numel() == 1:
+        d = d.expand(N).contiguous()
+    if z.numel() == 1:
+        z = z.expand(N).contiguous()
+    pw = PackedWeight()
+    pw.wq = torch.empty((Np, R * S, Cp), dtype=torch.int8, device=w.device)
+    wsum = torch.empty(Np, dtype=torch.int32, device=w.device)
+    pw.cw = torch.empty(Np, dtype=torch.int32, device=w.device)
+    pw.codes = torch.empty((N, Cr, R, S), dtype=torch.uint8, device=w.device) if want_codes else None
+    a = None if alpha is None else _f32c(alpha.detach())
+    lib.pack_weight(w.data_ptr(), _ptr(a), d.data_ptr(), z.data_ptr(), N, Ctot, R, S, c_begin, c_end, Cp, Np,
+                    int(n_levels), pw.wq.data_ptr(), _ptr(pw.codes), wsum.data_ptr(), pw.cw.data_ptr(), _stream())
+    pw.wsum_eff = wsum + pw.cw * (R * S * Cr)
+    pw.needs_rowsum = n_levels > 128  # resolved without a host sync: 8-bit codes may need the cw term
+    dw = torch.zeros(Np, dtype=torch.float32, device=w.device)
+    dw[:N] = d
+    pw.delta_w = dw
+    pw.N, pw.Np, pw.R, pw.S, pw.C, pw.Cp = N, Np, R, S, Cr, Cp
+    return pw
+
+
+class ActQuant:
+    """(delta, zero_point, n_levels) of the one or two (split) activation quantizers of a QuantModule."""
+
+    __slots__ = ("delta0", "zp0", "levels0", "split", "delta1", "zp1", "levels1")
+
+    def __init__(self, delta0, zp0, levels0, split=0, delta1=None, zp1=None, levels1=0):
+        self.delta0, self.zp0, self.levels0 = delta0, zp0, int(levels0)
+        self.split, self.delta1, self.zp1, self.levels1 = int(split), delta1, zp1, int(levels1)
+
+
+def act_quant_nhwc(x, aq: ActQuant, pad: int, want_chsum=False):
+    """x fp32 [B,C,H,W] -> u8 codes [B,H+2p,W+2p,Cp] (halo = zero-point code)."""
+    _need_cuda(x)
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    Cp = _round_up(C, 16)
+    q = torch.empty((B, H + 2 * pad, W + 2 * pad, Cp), dtype=torch.uint8, device=x.device)
+    chsum = torch.empty((B, H + 2 * pad, W + 2 * pad), dtype=torch.int32, device=x.device) if want_chsum else None
+    dev = x.device
+    d0, z0 = _qparam(aq.delta0, dev), _qparam(aq.zp0, dev)
+    d1 = _qparam(aq.delta1, dev) if aq.split else None
+    z1 = _qparam(aq.zp1, dev) if aq.split else None
+    lib.act_quant_nhwc(x.data_ptr(), q.data_ptr(), _ptr(chsum), B, C, H, W, Cp, pad, d0.data_ptr(), z0.data_ptr(),
+                       aq.levels0, aq.split, _ptr(d1), _ptr(z1), aq.levels1, _stream())
+    return q, chsum
+
+
+def act_quant_rows(x2d, aq: ActQuant, want_rowsum=False):
+    """x fp32 [M,K] -> u8 codes [M,Kp]."""
+    _need_cuda(x2d)
+    x2d = _f32c(x2d)
+    M, K = x2d.shape
+    Kp = _round_up(K, 16)
+    q = torch.empty((M, Kp), dtype=torch.uint8, device=x2d.device)
+    rowsum = torch.empty(M, dtype=torch.int32, device=x2d.device) if want_rowsum else None
+    dev = x2d.device
+    d0, z0 = _qparam(aq.delta0, dev), _qparam(aq.zp0, dev)
+    d1 = _qparam(aq.delta1, dev) if aq.split else None
+    z1 = _qparam(aq.zp1, dev) if aq.split else None
+    lib.act_quant_rows(x2d.data_ptr(), q.data_ptr(), _ptr(rowsum), M, K, Kp, d0.data_ptr(), z0.data_ptr(), aq.levels0,
+                       aq.split, _ptr(d1), _ptr(z1), aq.levels1, _stream())
+    return q, rowsum
+
+
+def im2col_u8(q, Ho, Wo, R, S, stride):
+    B, Hp, Wp, Cp = q.shape
+    a = torch.empty((B * Ho * Wo, R * S * Cp), dtype=torch.uint8, device=q.device)
+    lib.im2col_u8(q.data_ptr(), a.data_ptr(), B, Hp, Wp, Cp, Ho, Wo, R, S, stride, _stream())
+    return a
+
+
+def conv_rowsum(chsum, Ho, Wo, R, S, stride):
+    B, Hp, Wp = chsum.shape
+    rs = torch.empty(B * Ho * Wo, dtype=torch.int32, device=chsum.device)
+    lib.conv_rowsum(chsum.data_ptr(), rs.data_ptr(), B, Hp, Wp, Ho, Wo, R, S, stride, _stream())
+    return rs
+
+
+def qgemm_i8(q, pw: PackedWeight, delta_a, zp_a, out, out_hw, bias=None, rowsum=None, a_c_offset=0,
+             accumulate=False, silu=False, filter_rs=None):
+    """Launch the tcgen05 GEMM.  q: [B,Hp,Wp,Cp] u8 codes (or [M,Kp] for a flat GEMM)."""
+    if q.dim() == 2:
+        B, Hp, Wp, Cp_act = 1, 1, q.shape[0], q.shape[1]
+    else:
+        B, Hp, Wp, Cp_act = q.shape
+    R, S = filter_rs if filter_rs is not None else (pw.R, pw.S)
+    dev = q.device
+    da, za = _qparam(delta_a, dev), _qparam(zp_a, dev)
+    if pw.needs_rowsum and rowsum is None:
+        raise EdadmError("8-bit weight codes need the activation row sums (zero-point fold); pass rowsum")
+    cw = pw.cw if pw.needs_rowsum else None
+    lib.qgemm_i8(q.data_ptr(), B, Hp, Wp, Cp_act, int(a_c_offset), pw.wq.data_ptr(), pw.N, pw.Np, R, S,
+                 pw.wq.shape[2] if filter_rs is None else pw.wq.shape[1] * pw.wq.shape[2] // (R * S),
+                 da.data_ptr(), za.data_ptr(), pw.delta_w.data_ptr(), pw.wsum_eff.data_ptr(), _ptr(cw), _ptr(rowsum),
+                 _ptr(bias), out.data_ptr(), int(out_hw), 1 if accumulate else 0, 1 if silu else 0, _stream())
+    return out

@@ -1,0 +1,367 @@
+"""Latent-diffusion UNet family (LSUN-Church / LSUN-Bedroom / ImageNet / Stable-Diffusion shapes).
+
+FP structure only -- the L0 layer under the quantized path -- written from scratch with the public
+ADM / latent-diffusion checkpoint naming (`time_embed`, `input_blocks.N.M`, `middle_block`,
+`output_blocks`, `out`; `in_layers/emb_layers/out_layers/skip_connection`; `attn1/attn2/ff`), which is the
+layout ldm/modules/diffusionmodules/openaimodel.py:447-783 and ldm/modules/attention.py of the reference
+load, so reference state_dicts map 1:1.  The two attention matmuls are separate modules (QKMatMul /
+SMVMatMul) because that is the seam the quantized path swaps (reference openaimodel.py:350-371).
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def timestep_embedding(t, dim, max_period=10000):
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    args = t[:, None].float() * freqs[None]
+    emb = torch.cat([args.cos(), args.sin()], dim=-1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+    return emb
+
+
+class GroupNorm32(nn.GroupNorm):
+    def forward(self, x):
+        return super().forward(x.float()).type(x.dtype)
+
+
+def _zero(m):
+    for p in m.parameters():
+        p.detach().zero_()
+    return m
+
+
+class TimestepBlock(nn.Module):
+    """Marker: forward(x, emb, split=0)."""
+
+
+class Upsample(nn.Module):
+    def __init__(self, channels, use_conv, out_channels=None, padding=1):
+        super().__init__()
+        self.channels, self.out_channels, self.use_conv = channels, out_channels or channels, use_conv
+        if use_conv:
+            self.conv = nn.Conv2d(channels, self.out_channels, 3, padding=padding)
+
+    def forward(self, x):
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+        return self.conv(x) if self.use_conv else x
+
+
+class Downsample(nn.Module):
+    def __init__(self, channels, use_conv, out_channels=None, padding=1):
+        super().__init__()
+        self.channels, self.out_channels, self.use_conv = channels, out_channels or channels, use_conv
+        self.op = nn.Conv2d(channels, self.out_channels, 3, stride=2, padding=padding) if use_conv else nn.AvgPool2d(2, 2)
+
+    def forward(self, x):
+        return self.op(x)
+
+
+class ResBlock(TimestepBlock):
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=False, use_scale_shift_norm=False,
+                 use_checkpoint=False, up=False, down=False):
+        super().__init__()
+        self.channels, self.emb_channels, self.dropout = channels, emb_channels, dropout
+        self.out_channels = out_channels or channels
+        self.use_conv, self.use_checkpoint, self.use_scale_shift_norm = use_conv, use_checkpoint, use_scale_shift_norm
+        self.in_layers = nn.Sequential(GroupNorm32(32, channels), nn.SiLU(), nn.Conv2d(channels, self.out_channels, 3, padding=1))
+        self.updown = up or down
+        if up:
+            self.h_upd, self.x_upd = Upsample(channels, False), Upsample(channels, False)
+        elif down:
+            self.h_upd, self.x_upd = Downsample(channels, False), Downsample(channels, False)
+        else:
+            self.h_upd = self.x_upd = nn.Identity()
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, 2 * self.out_channels if use_scale_shift_norm else self.out_channels))
+        self.out_layers = nn.Sequential(GroupNorm32(32, self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        _zero(nn.Conv2d(self.out_channels, self.out_channels, 3, padding=1)))
+        if self.out_channels == channels:
+            self.skip_connection = nn.Identity()
+        elif use_conv:
+            self.skip_connection = nn.Conv2d(channels, self.out_channels, 3, padding=1)
+        else:
+            self.skip_connection = nn.Conv2d(channels, self.out_channels, 1)
+
+    def forward(self, x, emb, split=0):
+        return resblock_forward(self, x, emb, split)
+
+
+def resblock_forward(blk, x, emb, split=0):
+    """Shared by ResBlock and its quantized wrapper (same dataflow as reference quant_block.py:86-116)."""
+    if blk.updown:
+        h = blk.in_layers[:-1](x)
+        h, x = blk.h_upd(h), blk.x_upd(x)
+        h = blk.in_layers[-1](h)
+    else:
+        h = blk.in_layers(x)
+    emb_out = blk.emb_layers(emb).type(h.dtype)
+    while emb_out.dim() < h.dim():
+        emb_out = emb_out[..., None]
+    if blk.use_scale_shift_norm:
+        scale, shift = torch.chunk(emb_out, 2, dim=1)
+        h = blk.out_layers[0](h) * (1 + scale) + shift
+        h = blk.out_layers[1:](h)
+    else:
+        h = blk.out_layers(h + emb_out)
+    if split:
+        return blk.skip_connection(x, split=split) + h
+    return blk.skip_connection(x) + h
+
+
+class QKMatMul(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.scale = None
+
+    def forward(self, q, k):
+        return torch.einsum("bct,bcs->bts", q * self.scale, k * self.scale)
+
+
+class SMVMatMul(nn.Module):
+    def forward(self, weight, v):
+        return torch.einsum("bts,bcs->bct", weight, v)
+
+
+class QKVAttentionLegacy(nn.Module):
+    def __init__(self, n_heads):
+        super().__init__()
+        self.n_heads = n_heads
+        self.qkv_matmul = QKMatMul()
+        self.smv_matmul = SMVMatMul()
+
+    def forward(self, qkv):
+        bs, width, length = qkv.shape
+        ch = width // (3 * self.n_heads)
+        q, k, v = qkv.reshape(bs * self.n_heads, ch * 3, length).split(ch, dim=1)
+        self.qkv_matmul.scale = 1 / math.sqrt(math.sqrt(ch))
+        weight = self.qkv_matmul(q, k)
+        weight = torch.softmax(weight.float(), dim=-1).type(weight.dtype)
+        return self.smv_matmul(weight, v).reshape(bs, -1, length)
+
+
+class AttentionBlock(nn.Module):
+    def __init__(self, channels, num_heads=1, num_head_channels=-1, use_checkpoint=False):
+        super().__init__()
+        self.channels = channels
+        self.num_heads = num_heads if num_head_channels == -1 else channels // num_head_channels
+        self.use_checkpoint = use_checkpoint
+        self.norm = GroupNorm32(32, channels)
+        self.qkv = nn.Conv1d(channels, channels * 3, 1)
+        self.attention = QKVAttentionLegacy(self.num_heads)
+        self.proj_out = _zero(nn.Conv1d(channels, channels, 1))
+
+    def forward(self, x):
+        b, c, *spatial = x.shape
+        x = x.reshape(b, c, -1)
+        h = self.proj_out(self.attention(self.qkv(self.norm(x))))
+        return (x + h).reshape(b, c, *spatial)
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        x, gate = self.proj(x).chunk(2, dim=-1)
+        return x * F.gelu(gate)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, mult=4, glu=True, dropout=0.0):
+        super().__init__()
+        inner = int(dim * mult)
+        first = GEGLU(dim, inner) if glu else nn.Sequential(nn.Linear(dim, inner), nn.GELU())
+        self.net = nn.Sequential(first, nn.Dropout(dropout), nn.Linear(inner, dim))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+def _heads_split(t, h):
+    b, n, hd = t.shape
+    return t.reshape(b, n, h, hd // h).permute(0, 2, 1, 3).reshape(b * h, n, hd // h)
+
+
+def _heads_merge(t, h):
+    bh, n, d = t.shape
+    return t.reshape(bh // h, h, n, d).permute(0, 2, 1, 3).reshape(bh // h, n, h * d)
+
+
+class CrossAttention(nn.Module):
+    def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64, dropout=0.0):
+        super().__init__()
+        inner = dim_head * heads
+        context_dim = context_dim or query_dim
+        self.scale, self.heads = dim_head ** -0.5, heads
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(context_dim, inner, bias=False)
+        self.to_v = nn.Linear(context_dim, inner, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner, query_dim), nn.Dropout(dropout))
+
+    def forward(self, x, context=None, mask=None):
+        context = x if context is None else context
+        q, k, v = (_heads_split(t, self.heads) for t in (self.to_q(x), self.to_k(context), self.to_v(context)))
+        attn = (torch.einsum("bid,bjd->bij", q, k) * self.scale).softmax(dim=-1)
+        return self.to_out(_heads_merge(torch.einsum("bij,bjd->bid", attn, v), self.heads))
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim, n_heads, d_head, dropout=0.0, context_dim=None, gated_ff=True, checkpoint=True):
+        super().__init__()
+        self.attn1 = CrossAttention(dim, heads=n_heads, dim_head=d_head, dropout=dropout)
+        self.ff = FeedForward(dim, dropout=dropout, glu=gated_ff)
+        self.attn2 = CrossAttention(dim, context_dim=context_dim, heads=n_heads, dim_head=d_head, dropout=dropout)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
+        self.checkpoint = checkpoint
+
+    def forward(self, x, context=None):
+        x = self.attn1(self.norm1(x)) + x
+        x = self.attn2(self.norm2(x), context=context) + x
+        return self.ff(self.norm3(x)) + x
+
+
+class SpatialTransformer(nn.Module):
+    def __init__(self, in_channels, n_heads, d_head, depth=1, dropout=0.0, context_dim=None):
+        super().__init__()
+        self.in_channels = in_channels
+        inner = n_heads * d_head
+        self.norm = nn.GroupNorm(32, in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Conv2d(in_channels, inner, 1)
+        self.transformer_blocks = nn.ModuleList(
+            [BasicTransformerBlock(inner, n_heads, d_head, dropout=dropout, context_dim=context_dim) for _ in range(depth)])
+        self.proj_out = _zero(nn.Conv2d(inner, in_channels, 1))
+
+    def forward(self, x, context=None):
+        b, c, h, w = x.shape
+        y = self.proj_in(self.norm(x)).reshape(b, -1, h * w).permute(0, 2, 1)
+        for blk in self.transformer_blocks:
+            y = blk(y, context)
+        y = y.permute(0, 2, 1).reshape(b, -1, h, w)
+        return self.proj_out(y) + x
+
+
+class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
+    def forward(self, x, emb, context=None, split=0):
+        for layer in self:
+            if isinstance(layer, TimestepBlock) or getattr(layer, "takes_emb", False):
+                x = layer(x, emb, split=split)
+            elif isinstance(layer, SpatialTransformer):
+                x = layer(x, context)
+            else:
+                x = layer(x)
+        return x
+
+
+class UNetModel(nn.Module):
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, num_classes=None, use_checkpoint=False,
+                 num_heads=-1, num_head_channels=-1, use_scale_shift_norm=False, resblock_updown=False,
+                 use_spatial_transformer=False, transformer_depth=1, context_dim=None, legacy=True, **_ignored):
+        super().__init__()
+        self.image_size, self.in_channels, self.model_channels, self.out_channels = image_size, in_channels, model_channels, out_channels
+        self.num_classes = num_classes
+        self.split_shortcut = False
+        ted = model_channels * 4
+        self.time_embed = nn.Sequential(nn.Linear(model_channels, ted), nn.SiLU(), nn.Linear(ted, ted))
+        if num_classes is not None:
+            self.label_emb = nn.Embedding(num_classes, ted)
+
+        def res(cin, cout, **kw):
+            return ResBlock(cin, ted, dropout, out_channels=cout, use_checkpoint=use_checkpoint,
+                            use_scale_shift_norm=use_scale_shift_norm, **kw)
+
+        def attn(ch):
+            if num_head_channels == -1:
+                heads, dim_head = num_heads, ch // num_heads
+            else:
+                heads, dim_head = ch // num_head_channels, num_head_channels
+            if legacy:
+                dim_head = ch // heads if use_spatial_transformer else num_head_channels
+            if use_spatial_transformer:
+                return SpatialTransformer(ch, heads, dim_head, depth=transformer_depth, context_dim=context_dim)
+            return AttentionBlock(ch, use_checkpoint=use_checkpoint, num_heads=heads, num_head_channels=dim_head)
+
+        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(nn.Conv2d(in_channels, model_channels, 3, padding=1))])
+        chans, ch, ds = [model_channels], model_channels, 1
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [res(ch, mult * model_channels)]
+                ch = mult * model_channels
+                if ds in attention_resolutions:
+                    layers.append(attn(ch))
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                chans.append(ch)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(
+                    res(ch, ch, down=True) if resblock_updown else Downsample(ch, conv_resample, out_channels=ch)))
+                chans.append(ch)
+                ds *= 2
+        self.middle_block = TimestepEmbedSequential(res(ch, ch), attn(ch), res(ch, ch))
+        self.output_blocks = nn.ModuleList()
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                layers = [res(ch + chans.pop(), model_channels * mult)]
+                ch = model_channels * mult
+                if ds in attention_resolutions:
+                    layers.append(attn(ch))
+                if level and i == num_res_blocks:
+                    layers.append(res(ch, ch, up=True) if resblock_updown else Upsample(ch, conv_resample, out_channels=ch))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+        self.out = nn.Sequential(GroupNorm32(32, ch), nn.SiLU(), _zero(nn.Conv2d(model_channels, out_channels, 3, padding=1)))
+
+    def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
+        emb = self.time_embed(timestep_embedding(timesteps, self.model_channels))
+        if self.num_classes is not None:
+            emb = emb + self.label_emb(y)
+        hs, h = [], x
+        for module in self.input_blocks:
+            h = module(h, emb, context)
+            hs.append(h)
+        h = self.middle_block(h, emb, context)
+        for module in self.output_blocks:
+            split = h.shape[1] if self.split_shortcut else 0
+            h = module(torch.cat([h, hs.pop()], dim=1), emb, context, split=split)
+        return self.out(h)
+
+
+def reinit_zero_modules(model: nn.Module, std: float = 0.02, seed: int = 0):
+    """The public init zeroes some convs (`zero_module`); synthetic benchmarks re-draw them so that no GEMM
+    is trivially zero."""
+    g = torch.Generator().manual_seed(seed)
+    for p in model.parameters():
+        if p.dim() > 1 and float(p.detach().abs().max()) == 0.0:
+            p.data.copy_(torch.randn(p.shape, generator=g) * std)
+    return model
+
+
+# unet_config.params of the reference's model configs (file:line in each docstring)
+def lsun_church_unet():
+    """models/ldm/lsun_churches256/config.yaml:32-53 (LDM-8, latent 32x32x4, 295.0 M params)."""
+    return UNetModel(image_size=32, in_channels=4, out_channels=4, model_channels=192, attention_resolutions=[1, 2, 4, 8],
+                     num_res_blocks=2, channel_mult=[1, 2, 2, 4, 4], num_heads=8, use_scale_shift_norm=True, resblock_updown=True)
+
+
+def lsun_bedroom_unet():
+    """models/ldm/lsun_beds256/config.yaml:17-34 (LDM-4, latent 64x64x3, 274.1 M params)."""
+    return UNetModel(image_size=64, in_channels=3, out_channels=3, model_channels=224, attention_resolutions=[8, 4, 2],
+                     num_res_blocks=2, channel_mult=[1, 2, 3, 4], num_head_channels=32)
+
+
+def imagenet_unet():
+    """configs/latent-diffusion/cin256-v2.yaml:19-39 (LDM-4 class-conditional, 400.9 M params)."""
+    return UNetModel(image_size=64, in_channels=3, out_channels=3, model_channels=192, attention_resolutions=[8, 4, 2],
+                     num_res_blocks=2, channel_mult=[1, 2, 3, 5], num_heads=1, use_spatial_transformer=True,
+                     transformer_depth=1, context_dim=512)
+
+
+def stable_diffusion_unet():
+    """configs/stable-diffusion/v1-inference.yaml:29-44 (SD v1.4, 859.5 M params)."""
+    return UNetModel(image_size=32, in_channels=4, out_channels=4, model_channels=320, attention_resolutions=[4, 2, 1],
+                     num_res_blocks=2, channel_mult=[1, 2, 4, 4], num_heads=8, use_spatial_transformer=True,
+                     transformer_depth=1, context_dim=768, use_checkpoint=False, legacy=False)

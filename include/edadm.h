@@ -1,0 +1,113 @@
+/* libedadm.so -- C ABI of the B200-native quantized-UNet hot path of EDA-DM's `qdiff`.
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers and sizes (no torch types), enqueues
+ * on the given cudaStream_t (passed as void*) and returns 0 on success or a negative EDADM_ERR_* code;
+ * edadm_last_error() returns the message of the calling thread's last failure.  There is no CPU
+ * fallback: a call either runs the sm_100a kernel or fails.
+ *
+ * "Replaces" cites the reference (BienLuky/EDA-DM) call site a binding would swap out; the Python
+ * (ctypes) binding the reference side needs is shown in INTEGRATION.md.
+ *
+ * Scalars that the reference keeps as tensors / nn.Parameters (activation delta, zero_point) are
+ * passed as DEVICE pointers so the path never synchronises with the host.
+ */
+#ifndef EDADM_H
+#define EDADM_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDADM_OK 0
+#define EDADM_ERR_ARG (-1)
+#define EDADM_ERR_CUDA (-2)
+#define EDADM_ERR_UNSUPPORTED (-3)
+
+const char* edadm_last_error(void);
+int edadm_abi_version(void);
+/* number of double slots a `partials` workspace must hold for the two-stage reductions below */
+int edadm_reduce_slots(void);
+
+/* ---- K2: UniformAffineQuantizer fake-quant ------------------------------------------------------
+ * Replaces qdiff/quant_layer.py:267-274 (UniformAffineQuantizer.forward body, incl. the QDrop
+ * `torch.where(rand_like(x) < prob, x_dequant, x)`), and its autograd graph (round_ste :19-23).
+ *   y = keep ? (clamp(rint(x/delta)+zp, 0, n_levels-1) - zp) * delta : x
+ * delta/zero_point: 1 element (channels==1) or `channels` elements; channel of element i is
+ * (i / inner) % channels.  keep_mask (u8, nullable) is an explicit QDrop mask; when null and
+ * qdrop_prob < 1 a Philox4x32-10 stream keyed by (seed, offset) draws the mask (same draw in bwd).
+ * codes (nullable) receives the integer codes as u8.                                             */
+int edadm_uaq_fwd(const float* x, float* y, uint8_t* codes, const float* delta, const float* zero_point,
+                  int64_t n, int64_t channels, int64_t inner, int n_levels, const uint8_t* keep_mask,
+                  float qdrop_prob, uint64_t seed, uint64_t offset, void* stream);
+/* gx = straight-through gradient; gdelta (nullable, per-tensor only) = LSQ step-size gradient,
+ * reduced in fp64 through `partials` (edadm_reduce_slots() doubles).                              */
+int edadm_uaq_bwd(const float* gy, const float* x, const float* delta, const float* zero_point, int64_t n,
+                  int64_t channels, int64_t inner, int n_levels, const uint8_t* keep_mask, float qdrop_prob,
+                  uint64_t seed, uint64_t offset, float* gx, float* gdelta, int accumulate_gdelta,
+                  double* partials, void* stream);
+
+/* ---- K3: AdaRoundQuantizer -----------------------------------------------------------------------
+ * Replaces qdiff/adaptive_rounding.py:49-59 (forward, 'learned_hard_sigmoid'), :63-64
+ * (get_soft_targets), :66-72 (init_alpha) and the autograd graph of alpha.                        */
+int edadm_adaround_fwd(const float* w, const float* alpha, const float* delta, const float* zero_point,
+                       int64_t n, int64_t channels, int64_t inner, int n_levels, int soft, float* out,
+                       uint8_t* codes, void* stream);
+int edadm_adaround_bwd(const float* gout, const float* w, const float* alpha, const float* delta,
+                       const float* zero_point, int64_t n, int64_t channels, int64_t inner, int n_levels,
+                       float* galpha, int accumulate, void* stream);
+int edadm_adaround_init_alpha(const float* w, const float* delta, int64_t n, int64_t channels, int64_t inner,
+                              float* alpha, void* stream);
+/* Replaces the 'relaxation' branch of LossFunction.__call__, qdiff/block_recon.py:286-291:
+ * loss (+)= weight * sum(1 - |2h(alpha)-1|^b); galpha (nullable) += d loss / d alpha.             */
+int edadm_round_reg(const float* alpha, int64_t n, float b, float weight, double* partials, float* loss,
+                    int accumulate_loss, float* galpha, void* stream);
+
+/* ---- K4: reconstruction loss ----------------------------------------------------------------------
+ * Replaces lp_loss, qdiff/quant_layer.py:26-33 as used by LossFunction (block_recon.py:271-272) and
+ * the FBR per-layer terms (block_recon.py:188-191): loss = sum|pred-tgt|^p * inv_rest with
+ * inv_rest = size(1)/numel  (".sum(1).mean()").                                                   */
+int edadm_lp_loss_fwd(const float* pred, const float* tgt, int64_t n, float p, float inv_rest, double* partials,
+                      float* loss, void* stream);
+int edadm_lp_loss_bwd(const float* pred, const float* tgt, int64_t n, float p, float inv_rest, const float* gloss,
+                      float* gpred, void* stream);
+
+/* ---- K1 prologue: integer-code producers ----------------------------------------------------------
+ * Activation codes are exactly clamp(rint(x/delta)+zp, 0, L-1) (quant_layer.py:267-268) stored as u8.
+ * act_quant_nhwc: x fp32 [B][C][H][W] -> q [B][H+2pad][W+2pad][Cp]; halo pixels hold the zero-point
+ * code (zero padding of F.conv2d on dequantised values == code zp), padded channels hold 0.
+ * split != 0: channels >= split use the second quantizer (quant_layer.py:415-419).
+ * chsum (nullable): int32 [B][H+2pad][W+2pad] per-pixel sum of codes (for 8-bit weight zero-points). */
+int edadm_act_quant_nhwc(const float* x, uint8_t* q, int32_t* chsum, int B, int C, int H, int W, int Cp, int pad,
+                         const float* delta0, const float* zp0, int n_levels0, int split, const float* delta1,
+                         const float* zp1, int n_levels1, void* stream);
+int edadm_act_quant_rows(const float* x, uint8_t* q, int32_t* rowsum, int64_t M, int K, int Kp, const float* delta0,
+                         const float* zp0, int n_levels0, int split, const float* delta1, const float* zp1,
+                         int n_levels1, void* stream);
+int edadm_im2col_u8(const uint8_t* q, uint8_t* a, int B, int Hp, int Wp, int Cp, int Ho, int Wo, int R, int S,
+                    int stride, void* stream);
+int edadm_conv_rowsum(const int32_t* chsum, int32_t* rowsum, int B, int Hp, int Wp, int Ho, int Wo, int R, int S,
+                      int stride, void* stream);
+/* Weight codes: nearest (UniformAffineQuantizer, quant_layer.py:267-268) or, with alpha, hard AdaRound
+ * (adaptive_rounding.py:50-58).  w fp32 [N][Ctot][R][S], channel range [c_begin,c_end) ->
+ * wq s8 [Np][R*S][Cp] = code - zoff (zoff = zp[n] for <=7 bit, 128 for 8 bit), wsum[n] = sum wq,
+ * cw[n] = zoff - zp[n]; codes (nullable) u8 [N][c_end-c_begin][R][S].                              */
+int edadm_pack_weight(const float* w, const float* alpha, const float* delta, const float* zp, int N, int Ctot, int R,
+                      int S, int c_begin, int c_end, int Cp, int Np, int n_levels, int8_t* wq, uint8_t* codes,
+                      int32_t* wsum, int32_t* cw, void* stream);
+
+/* ---- K1: QuantModule conv2d / conv1d / linear on integer codes (tcgen05 kind::i8) ------------------
+ * Replaces `self.fwd_func(input, weight, bias, **self.fwd_kwargs)` at qdiff/quant_layer.py:434 when
+ * use_weight_quant and use_act_quant are on.  Stride-1 implicit GEMM over the halo-padded NHWC codes
+ * (Ho = Hp-R+1, Wo = Wp-S+1); a 2-D GEMM is B=1,Hp=1,Wp=M,R=S=1; strided convs go through
+ * edadm_im2col_u8 first.  out fp32 is written as [M/out_hw][N][out_hw] (NCHW; out_hw=1 => [M][N]):
+ *   out = delta_a*delta_w[n]*(acc + cw[n]*rowsum[m] - zp_a*wsum_eff[n]) + bias[n]  (+= out if accumulate) */
+int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const int8_t* wq, int N, int Np,
+                   int R, int S, int Cp_w, const float* delta_a, const float* zp_a, const float* delta_w,
+                   const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum, const float* bias, float* out,
+                   int out_hw, int accumulate, int silu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDADM_H */

@@ -1,0 +1,273 @@
+"""-m gpu parity tests of the CUDA kernels (through the C ABI) against the CPU oracle.
+
+Integer codes: bit-exact.  Floating-point outputs: tolerance stated at each assert.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import qdiff_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _act_params(x, n_bits=8):
+    d, z, _ = O.init_scale(x.cpu(), n_bits, channel_wise=False, sym=True)
+    return d.reshape(1), z.reshape(1)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(4, 64, 16, 16), (3, 5, 7), (1,), (2, 320, 33)])
+@pytest.mark.parametrize("zp", [128.0, 127.0, 0.0])
+def test_uaq_fwd_codes_bit_exact(cuda, shape, zp):
+    from edadm import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(shape, generator=g) * 2.0
+    delta = torch.tensor([0.0173])
+    z = torch.tensor([zp])
+    y, codes = ops.uaq_forward(x.to(cuda), delta.to(cuda), z.to(cuda), 256, want_codes=True)
+    ref_codes = O.uaq_codes(x, delta, z, 256)
+    ref_y = O.uaq_forward(x, delta, z, 256)
+    assert torch.equal(codes.cpu().float(), ref_codes)
+    assert torch.equal(y.cpu(), ref_y)  # same fp32 ops in the same order -> bit-exact
+
+
+def test_uaq_fwd_channelwise_weights(cuda):
+    from edadm import ops
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(48, 32, 3, 3, generator=g) * 0.1
+    d, z, _ = O.init_scale(w, 4, channel_wise=True)
+    y, codes = ops.uaq_forward(w.to(cuda), d.to(cuda), z.to(cuda), 16, want_codes=True)
+    assert torch.equal(codes.cpu().float(), O.uaq_codes(w, d, z, 16))
+    assert torch.equal(y.cpu(), O.uaq_forward(w, d, z, 16))
+
+
+@pytest.mark.parametrize("prob", [1.0, 0.5])
+def test_uaq_bwd_matches_autograd(cuda, prob):
+    from edadm import ops
+    g = torch.Generator().manual_seed(2)
+    x = (torch.randn(8, 32, 16, 16, generator=g) * 3.0)
+    delta = torch.tensor(0.02)
+    z = torch.tensor(128.0)
+    keep = (torch.rand(x.shape, generator=g) < prob) if prob < 1 else None
+    gy = torch.randn(x.shape, generator=g)
+    # oracle: autograd through the restated forward
+    xr = x.clone().requires_grad_(True)
+    dr = delta.clone().requires_grad_(True)
+    O.uaq_forward(xr, dr, z, 256, keep).backward(gy)
+    xc = x.to(cuda).requires_grad_(True)
+    dc = delta.to(cuda).requires_grad_(True)
+    y = ops.uaq_fake_quant(xc, dc, z.to(cuda), 256, keep.to(cuda) if keep is not None else None)
+    y.backward(gy.to(cuda))
+    assert torch.equal(xc.grad.cpu(), xr.grad)  # pass-through / zero: exact
+    # step-size gradient: fp64-accumulated sum of ~65k fp32 terms vs torch's fp32 reduction: rel 1e-4
+    assert abs(dc.grad.item() - dr.grad.item()) <= 1e-4 * max(1.0, abs(dr.grad.item()))
+
+
+def test_uaq_philox_mask_consistent_and_rate(cuda):
+    from edadm import ops
+    x = torch.randn(1 << 20, device=cuda)
+    d = torch.tensor([0.05], device=cuda)
+    z = torch.tensor([128.0], device=cuda)
+    xq = ops.uaq_forward(x, d, z, 256)
+    y1 = ops.uaq_forward(x, d, z, 256, prob=0.5, seed=7, offset=0)
+    y2 = ops.uaq_forward(x, d, z, 256, prob=0.5, seed=7, offset=0)
+    assert torch.equal(y1, y2)
+    kept = (y1 == xq) & (xq != x)
+    dropped = (y1 == x) & (xq != x)
+    frac = kept.sum().item() / max(1, (kept | dropped).sum().item())
+    assert abs(frac - 0.5) < 0.01
+    # backward draws the same mask
+    xg = x.clone().requires_grad_(True)
+    ops.uaq_fake_quant(xg, d, z, 256, None, 0.5, 7, 0).sum().backward()
+    inr = (torch.round(x / d) + z).clamp(0, 255) == (torch.round(x / d) + z)
+    expect = torch.where(y1 == x, torch.ones_like(x), inr.float())
+    same = (xg.grad == expect) | (xq == x)
+    assert bool(same.all())
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("soft", [True, False])
+def test_adaround_fwd_bwd(cuda, soft):
+    from edadm import ops
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(64, 48, 3, 3, generator=g) * 0.05
+    d, z, _ = O.init_scale(w, 4, channel_wise=True)
+    alpha = O.adaround_init_alpha(w, d) + 0.3 * torch.randn(w.shape, generator=g)
+    a_gpu = ops.adaround_init_alpha(w.to(cuda), d.to(cuda))
+    # alpha init: logf/div ulp differences between libm and CUDA: abs 1e-4 on values of O(1..10)
+    assert torch.allclose(a_gpu.cpu(), O.adaround_init_alpha(w, d), atol=1e-4, rtol=1e-5)
+    ar = alpha.clone().requires_grad_(True)
+    ref = O.adaround_forward(w, ar, d, z, 16, soft)
+    ac = alpha.to(cuda).requires_grad_(True)
+    out = ops.adaround_fake_quant(w.to(cuda), ac, d.to(cuda), z.to(cuda), 16, soft)
+    if soft:
+        # sigmoid via expf: 1-2 ulp vs torch CPU; values are O(delta*8): atol 1e-6
+        assert torch.allclose(out.cpu(), ref, atol=1e-6, rtol=1e-5)
+        gy = torch.randn(w.shape, generator=g)
+        ref.backward(gy)
+        out.backward(gy.to(cuda))
+        assert torch.allclose(ac.grad.cpu(), ar.grad, atol=1e-7, rtol=1e-4)
+    else:
+        assert torch.equal(out.detach().cpu(), ref.detach())
+        _, codes = ops.adaround_forward(w.to(cuda), alpha.to(cuda), d.to(cuda), z.to(cuda), 16, False, want_codes=True)
+        assert torch.equal(codes.cpu().float(), O.adaround_codes(w, alpha, d, z, 16))
+
+
+def test_round_reg(cuda):
+    from edadm import ops
+    g = torch.Generator().manual_seed(4)
+    alpha = torch.randn(20000, generator=g) * 2
+    ar = alpha.clone().requires_grad_(True)
+    ref = O.round_reg(ar, 8.0, 0.01)
+    ref.backward()
+    ac = alpha.to(cuda).requires_grad_(True)
+    out = ops.round_reg(ac, 8.0, 0.01)
+    out.backward()
+    assert abs(out.item() - ref.item()) <= 1e-4 * abs(ref.item())
+    assert torch.allclose(ac.grad.cpu(), ar.grad, atol=1e-6, rtol=1e-3)
+
+
+@pytest.mark.parametrize("p", [2.0, 2.4])
+@pytest.mark.parametrize("shape", [(32, 64, 16, 16), (4, 77, 320), (2, 3)])
+def test_lp_loss(cuda, p, shape):
+    from edadm import ops
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(shape, generator=g)
+    b = torch.randn(shape, generator=g)
+    ar = a.clone().requires_grad_(True)
+    ref = O.lp_loss(ar, b, p)
+    ref.backward()
+    ac = a.to(cuda).requires_grad_(True)
+    out = ops.lp_loss(ac, b.to(cuda), p)
+    out.backward()
+    # fp64 accumulation on the GPU vs fp32 pairwise sum in torch: rel 1e-5
+    assert abs(out.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert torch.allclose(ac.grad.cpu(), ar.grad, rtol=1e-5, atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------------
+def _ref_int_conv(codes_a, za, wcodes, zw, stride=1, padding=0):
+    """exact integer convolution of (qa - za) with (qw - zw[n]) in float64"""
+    a = codes_a.double() - za
+    w = wcodes.double() - zw.reshape(-1, 1, 1, 1).double()
+    return F.conv2d(a, w, None, stride=stride, padding=padding)
+
+
+@pytest.mark.parametrize("B,C,H,W,pad", [(2, 64, 16, 16, 1), (3, 20, 8, 8, 1), (1, 3, 32, 32, 1), (2, 130, 4, 4, 0)])
+def test_act_quant_nhwc_codes(cuda, B, C, H, W, pad):
+    from edadm import ops
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(B, C, H, W, generator=g) * 1.5
+    d, z = _act_params(x)
+    aq = ops.ActQuant(d.to(cuda), z.to(cuda), 256)
+    q, chsum = ops.act_quant_nhwc(x.to(cuda), aq, pad, want_chsum=True)
+    ref = O.uaq_codes(x, d, z, 256).permute(0, 2, 3, 1)
+    q = q.cpu()
+    assert torch.equal(q[:, pad:pad + H, pad:pad + W, :C].float(), ref)
+    assert int(q[..., C:].sum()) == 0
+    if pad:
+        assert bool((q[:, 0, :, :C] == int(z.item())).all()) and bool((q[:, :, -1, :C] == int(z.item())).all())
+    assert torch.equal(chsum.cpu().long(), q.long().sum(-1))
+
+
+@pytest.mark.parametrize("M,K", [(200, 128), (64, 77), (4096, 320), (1, 512)])
+def test_act_quant_rows_codes(cuda, M, K):
+    from edadm import ops
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(M, K, generator=g)
+    d, z = _act_params(x)
+    q, rs = ops.act_quant_rows(x.to(cuda), ops.ActQuant(d.to(cuda), z.to(cuda), 256), want_rowsum=True)
+    ref = O.uaq_codes(x, d, z, 256)
+    assert torch.equal(q.cpu()[:, :K].float(), ref)
+    assert torch.equal(rs.cpu().long(), ref.long().sum(1))
+
+
+@pytest.mark.parametrize("n_bits", [4, 8])
+def test_pack_weight_codes(cuda, n_bits):
+    from edadm import ops
+    g = torch.Generator().manual_seed(8)
+    w = torch.randn(40, 24, 3, 3, generator=g) * 0.07
+    d, z, _ = O.init_scale(w, n_bits, channel_wise=True)
+    L = 2 ** n_bits
+    pw = ops.pack_weight(w.to(cuda), d.to(cuda), z.to(cuda), L, want_codes=True)
+    ref = O.uaq_codes(w, d, z, L)
+    assert torch.equal(pw.codes.cpu().float(), ref)
+    zoff = z.reshape(-1) if L <= 128 else torch.full((40,), 128.0)
+    wq = pw.wq.cpu()[:40].reshape(40, 3, 3, -1)[..., :24].permute(0, 3, 1, 2).float()
+    assert torch.equal(wq, ref - zoff.reshape(-1, 1, 1, 1))
+    # alpha path (hard AdaRound codes)
+    alpha = O.adaround_init_alpha(w, d) + 0.5 * torch.randn(w.shape, generator=g)
+    pw2 = ops.pack_weight(w.to(cuda), d.to(cuda), z.to(cuda), L, alpha=alpha.to(cuda), want_codes=True)
+    assert torch.equal(pw2.codes.cpu().float(), O.adaround_codes(w, alpha, d, z, L))
+
+
+# ------------------------------------------------------------------------------------------------
+def _run_qconv(cuda, x, w, bias, n_bits_w, pad, kind="conv"):
+    """full integer path: quantize activations, pack weights, tcgen05 GEMM"""
+    from edadm import ops
+    d_a, z_a = _act_params(x)
+    d_w, z_w, _ = O.init_scale(w, n_bits_w, channel_wise=True)
+    Lw = 2 ** n_bits_w
+    pw = ops.pack_weight(w.to(cuda), d_w.to(cuda), z_w.to(cuda), Lw)
+    aq = ops.ActQuant(d_a.to(cuda), z_a.to(cuda), 256)
+    if kind == "conv":
+        B, C, H, W = x.shape
+        q, chsum = ops.act_quant_nhwc(x.to(cuda), aq, pad, want_chsum=pw.needs_rowsum)
+        R, S = w.shape[2], w.shape[3]
+        Ho, Wo = H + 2 * pad - R + 1, W + 2 * pad - S + 1
+        rs = ops.conv_rowsum(chsum, Ho, Wo, R, S, 1) if pw.needs_rowsum else None
+        out = torch.empty(B, w.shape[0], Ho, Wo, device=cuda)
+        ops.qgemm_i8(q, pw, aq.delta0, aq.zp0, out, Ho * Wo, bias=None if bias is None else bias.to(cuda), rowsum=rs)
+    else:
+        q, rs = ops.act_quant_rows(x.to(cuda), aq, want_rowsum=pw.needs_rowsum)
+        out = torch.empty(x.shape[0], w.shape[0], device=cuda)
+        ops.qgemm_i8(q, pw, aq.delta0, aq.zp0, out, 1, bias=None if bias is None else bias.to(cuda), rowsum=rs)
+    torch.cuda.synchronize()
+    # oracle: reference fake-quant forward (quant_layer.py:406-437) in fp32 on CPU
+    act_q = [dict(delta=d_a, zero_point=z_a, n_levels=256)]
+    w_q = [dict(delta=d_w, zero_point=z_w, n_levels=Lw)]
+    if kind == "conv":
+        ref = O.quant_module_forward(x, w, bias, "conv2d", dict(stride=1, padding=pad), act_q, w_q)
+        exact = _ref_int_conv(O.uaq_codes(x, d_a, z_a, 256), z_a.item(), O.uaq_codes(w, d_w, z_w, Lw), z_w.reshape(-1), 1, pad)
+        exact = exact * (d_a.double() * d_w.reshape(1, -1, 1, 1).double())
+        if bias is not None:
+            exact = exact + bias.reshape(1, -1, 1, 1).double()
+    else:
+        ref = O.quant_module_forward(x, w, bias, "linear", {}, act_q, w_q)
+        exact = (O.uaq_codes(x, d_a, z_a, 256).double() - z_a.item()) @ (O.uaq_codes(w, d_w, z_w, Lw).double() - z_w.reshape(-1, 1).double()).t()
+        exact = exact * (d_a.double() * d_w.reshape(1, -1).double())
+        if bias is not None:
+            exact = exact + bias.reshape(1, -1).double()
+    return out.cpu(), ref, exact.float()
+
+
+def _rel_l2(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("M,K,N,bits", [(256, 128, 64, 4), (300, 320, 320, 4), (128, 512, 1280, 4), (77, 768, 96, 8),
+                                        (1000, 96, 24, 8), (4096, 384, 3072, 4)])
+def test_qgemm_linear(cuda, M, K, N, bits):
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) * 0.05
+    bias = torch.randn(N, generator=g)
+    out, ref, exact = _run_qconv(cuda, x, w, bias, bits, 0, kind="linear")
+    # integer accumulation is exact; the only rounding is the final fp32 scale+bias: 1e-6 of the exact value
+    assert _rel_l2(out, exact) < 1e-6
+    # vs the reference fp32 fake-quant forward (north_star tolerance 1e-3; fp32 summation order only)
+    assert _rel_l2(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,H,N,k,bits", [(2, 128, 16, 128, 3, 4), (1, 224, 64, 224, 3, 4), (4, 64, 8, 96, 3, 4),
+                                            (8, 256, 4, 256, 3, 4), (2, 3, 32, 128, 3, 8), (2, 128, 32, 3, 3, 8),
+                                            (2, 192, 16, 384, 1, 4), (32, 32, 2, 48, 3, 4)])
+def test_qgemm_conv(cuda, B, C, H, N, k, bits):
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(B, C, H, H, generator=g)
+    w = torch.randn(N, C, k, k, generator=g) * 0.05
+    bias = torch.randn(N, generator=g)
+    out, ref, exact = _run_qconv(cuda, x, w, bias, bits, k // 2, kind="conv")
+    assert _rel_l2(out, exact) < 1e-6
+    assert _rel_l2(out, ref) < 1e-5
