@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- W4A8 QuantModel UNet steps/s (+ block-reconstruction iters/s) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload church|cifar|bedroom|imagenet] [--impl reference]
+
+One JSON line on stdout (rank 0).  A "step" is one `QuantModel.forward` over the workload's image batch with
+the whole network on the integer tcgen05 path (W4A8, first/last weight quantizers 8 bit, split shortcuts);
+`value` is images x UNet-forwards per second with inputs resident in HBM, `e2e` is the same through
+`QuantModel.forward` from pinned HOST buffers (H2D of x, t[, context], D2H of the prediction inside the timed
+region).  Sampling shards the image batch across ranks with no communication ("weak": fixed batch per GPU).
+`recon` reports block_reconstruction iterations/s on one representative unit (data parallel, one all-reduce of
+the flat alpha/delta gradient bucket per iteration).
+
+`--impl reference` times the CPU oracle (oracle/model_oracle.py: the reference's fake-quant QuantModel restated
+in plain torch fp32) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "eda-dm_b200")]
+
+import torch  # noqa: E402
+
+WQ = {'n_bits': 4, 'symmetric': True, 'channel_wise': True, 'scale_method': 'mse'}
+AQ = {'n_bits': 8, 'symmetric': True, 'channel_wise': False, 'scale_method': 'mse', 'leaf_param': True, 'prob': 0.5}
+
+# name -> (constructor, sampling batch per GPU, latent shape, context shape or None, GEMM GFLOP/sample)
+WORKLOADS = {
+    "cifar": ("ddpm", 256, (3, 32, 32), None, 12.11),
+    "church": ("church", 100, (4, 32, 32), None, 37.28),
+    "bedroom": ("bedroom", 32, (3, 64, 64), None, 192.04),
+    "imagenet": ("imagenet", 128, (3, 64, 64), (1, 512), 199.54),
+}
+
+
+def build_fp_unet(kind):
+    from unet_zoo import ddpm_unet, ldm_unet
+    torch.manual_seed(0)
+    if kind == "ddpm":
+        m = ddpm_unet.cifar10_unet(dropout=0.0)
+    else:
+        m = {"church": ldm_unet.lsun_church_unet, "bedroom": ldm_unet.lsun_bedroom_unet,
+             "imagenet": ldm_unet.imagenet_unet}[kind]()
+        ldm_unet.reinit_zero_modules(m)
+    return m.eval()
+
+
+def synth_inputs(shape, ctx, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, *shape, generator=g)
+    t = torch.randint(0, 1000, (n,), generator=g)
+    out = [x, t]
+    if ctx is not None:
+        out.append(torch.randn(n, *ctx, generator=g))
+    return out
+
+
+def set_split(model, kind):
+    if kind == "ddpm":
+        model.config.split_shortcut = True
+    else:
+        model.split_shortcut = True
+
+
+def total_gemm_flops(qnn, args):
+    """2*M*N*K over every QuantModule call of one forward (counted with hooks; the algorithmic work of a step)."""
+    from qdiff.quant_layer import QuantModule
+    total = [0]
+    hooks = []
+
+    def hook(m, inp, out):
+        w = m.weight
+        k = w[0].numel()
+        total[0] += 2 * (out.numel() // w.shape[0]) * w.shape[0] * k
+    for m in qnn.modules():
+        if isinstance(m, QuantModule):
+            hooks.append(m.register_forward_hook(hook))
+    with torch.no_grad():
+        qnn(*args)
+    for h in hooks:
+        h.remove()
+    return total[0]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(kind, shape, ctx, sample_batch, reps, threads):
+    """The reference's fake-quant QuantModel forward restated on the CPU (oracle), timed on a bounded sample."""
+    from oracle.model_oracle import OracleQuantUNet
+    torch.set_num_threads(threads)
+    fp = build_fp_unet(kind)
+    om = OracleQuantUNet(fp, WQ, AQ, sm_abit=8)
+    om.set_first_last_layer_to_8bit()
+    om.disable_network_output_quantization()
+    set_split(fp, kind)
+    args = synth_inputs(shape, ctx, sample_batch, seed=1234)
+    om.cheap_calibrate(*args)     # ranges only; the arithmetic timed below does not depend on their values
+    om.set_quant_state(True, True)
+    times = []
+    with torch.no_grad():
+        om(*args)                 # warm-up
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            om(*args)
+            times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": sample_batch / med, "unit": "img-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{reps} x QuantModel.forward on {sample_batch} images (oracle/model_oracle.py, fp32 fake-quant, "
+                      f"max-abs ranges), median {med:.3f} s"}, med
+
+
+def run_reference(args, kind, batch, shape, ctx):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = max(1, min(batch, 8))
+    t_start = time.perf_counter()
+    cb, med = cpu_baseline(kind, shape, ctx, sample, max(1, args.steps), threads)
+    line = {"impl": "reference", "metric": "W4A8 QuantModel UNet img-steps/s", "value": cb["value"], "unit": "img-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32 fake-quant (CPU)",
+            "data": "synthetic", "config": {"workload": args.workload, "sample_batch": sample},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "img-steps/s", "h2d_bytes_per_step": 0,
+                                        "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_start}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="church", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the workload's sampling batch)")
+    ap.add_argument("--impl", default="edadm", choices=["edadm", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the UNet forward in a CUDA graph")
+    ap.add_argument("--no-recon", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--recon-iters", type=int, default=12)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    kind, batch, shape, ctx, gflop_per_sample = WORKLOADS[args.workload]
+    batch = args.batch or batch
+
+    if args.impl == "reference":
+        return run_reference(args, kind, batch, shape, ctx)
+
+    import torch.distributed as dist
+    from edadm import ops, native
+    from qdiff import QuantModel, set_weight_quantize_params, set_act_quantize_params
+    from qdiff.block_recon import block_reconstruction
+    from qdiff.quant_block import BaseQuantBlock
+
+    native.load_library()                      # fail loudly if the CUDA extension is missing
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the quantized path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    t_wall0 = time.perf_counter()
+    # ---- model + scales (outside the timed region) ------------------------------------------------------------
+    fp = build_fp_unet(kind).to(dev)
+    qnn = QuantModel(fp, WQ, AQ, sm_abit=8).to(dev).eval()
+    qnn.set_first_last_layer_to_8bit()
+    qnn.disable_network_output_quantization()
+    set_split(qnn.model, kind)
+    cali = [c.to(dev) for c in synth_inputs(shape, ctx, 64, seed=1234)]
+    set_weight_quantize_params(qnn, cali)
+    set_act_quantize_params(qnn, cali, batch_size=32, all_attention=True)
+    qnn.set_quant_state(True, True)
+
+    host_in = [c.pin_memory() for c in synth_inputs(shape, ctx, batch, seed=100 + rank)]
+    dev_in = [c.to(dev) for c in host_in]
+    flops_step = total_gemm_flops(qnn, dev_in)
+    paths = qnn.path_report()
+    n_int8 = sum(1 for v in paths.values() if v == "int8")
+
+    # kernel launches of one forward (my kernels only), counted on an eager pass
+    with torch.no_grad():
+        native.launch_counter["kernels"] = 0
+        qnn(*dev_in)
+        launches_per_step = native.launch_counter["kernels"]
+
+    # ---- CUDA graph of the forward ----------------------------------------------------------------------------
+    static_in = [c.clone() for c in dev_in]
+    graph = None
+    with torch.no_grad():
+        if not args.no_graph:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    qnn(*static_in)
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = qnn(*static_in)
+
+        def step_resident():
+            if graph is not None:
+                graph.replay()
+                return static_out
+            return qnn(*static_in)
+
+        host_out = torch.empty((batch, *shape), dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            for s_in, h in zip(static_in, host_in):
+                s_in.copy_(h, non_blocking=True)
+            out = step_resident()
+            host_out.copy_(out, non_blocking=True)
+
+        def timed(fn, k, w):
+            for _ in range(w):
+                fn()
+            barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(k):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(); barrier()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                tt = torch.tensor([ms], device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ms = float(tt.item())
+            return ms / k
+
+        with ClockSampler(local) as clk:
+            ms_step = timed(step_resident, args.steps, args.warmup)
+        clocks = clk.summary()
+        ms_e2e = timed(step_e2e, args.steps, args.warmup)
+
+        # ---- dominant kernel: per-launch CUDA events around every tcgen05 GEMM of eager steps -------------------
+        for _ in range(2):
+            qnn(*static_in)
+        ops.gemm_profile = []
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_prof = 3
+        e0.record()
+        for _ in range(n_prof):
+            qnn(*static_in)
+        e1.record()
+        torch.cuda.synchronize()
+        prof, ops.gemm_profile = ops.gemm_profile, None
+        gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof) / n_prof
+        gemm_macs = sum(m for _, _, m in prof) / n_prof
+        eager_ms = e0.elapsed_time(e1) / n_prof
+        n_gemm = len(prof) // n_prof
+
+    peaks, peak_src = measured_peaks()
+    int8_peak = 2.0 * peaks["bf16_tflops"]      # dense int8 = 2x bf16 on B200; no int8 entry in MEASURED_PEAKS.json
+    achieved = 2.0 * gemm_macs / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "qgemm_i8_kernel (tcgen05 kind::i8)", "achieved": achieved, "peak": int8_peak,
+                "unit": "TOP/s", "frac": achieved / int8_peak, "traffic": None,
+                "peak_source": f"2 x bf16 burst {peaks['bf16_tflops']} TF/s, {peak_src}",
+                "launches_per_step": n_gemm, "avg_launch_us": 1e3 * gemm_ms / max(1, n_gemm),
+                "share_of_eager_step": gemm_ms / eager_ms if eager_ms else None,
+                "algorithmic_gflop_per_step": 2.0 * gemm_macs / 1e9}
+
+    # ---- block reconstruction iterations/s on a representative unit --------------------------------------------
+    recon = None
+    if not args.no_recon:
+        units = [m for m in qnn.model.modules() if isinstance(m, BaseQuantBlock) and type(m).__name__ in ("QuantResBlock", "QuantResnetBlock")]
+        unit = units[len(units) // 4]
+        rb = 32
+        cali_r = [c.to(dev) for c in synth_inputs(shape, ctx, 64 * world, seed=4321)]
+        timing = {"warmup": 3}
+        kw = dict(cali_data=cali_r, iters=args.recon_iters + 3, batch_size=rb, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2,
+                  act_quant=True, opt_mode='mse', lr_a=4e-4, lr_w=1e-2, p=2.0, input_prob=0.5, keep_gpu=True, recon_w=True,
+                  recon_a=True, add_loss=0.8, timing=timing)
+        native.launch_counter["kernels"] = 0
+        block_reconstruction(qnn, unit, **kw)
+        ms_it = timing["ms_per_iter"]
+        if world > 1:
+            tt = torch.tensor([ms_it], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_it = float(tt.item())
+        recon = {"unit": type(unit).__name__, "iters_per_s": 1e3 / ms_it, "samples_per_s": world * rb * 1e3 / ms_it,
+                 "ms_per_iter": ms_it, "batch_per_gpu": rb, "global_batch": rb * world, "scaling": "weak",
+                 "allreduce_bytes_per_iter": timing.get("bucket_bytes", 0) if world > 1 else 0,
+                 "semantics": "reference loop: quant fwd + FP fwd + quant fwd (FBR) + backward, QDrop 0.5"}
+        qnn.set_quant_state(True, True)
+
+    if rank == 0:
+        cb = None
+        if not args.no_cpu_baseline and world == 1:
+            cb, _ = cpu_baseline(kind, shape, ctx, min(batch, 4), 3, os.cpu_count() or 1)
+        in_bytes = sum(c.numel() * c.element_size() for c in host_in)
+        out_bytes = host_out.numel() * 4
+        value = world * batch * 1e3 / ms_step
+        line = {
+            "metric": "W4A8 QuantModel UNet img-steps/s", "value": value, "unit": "img-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8 x s8 -> s32 (W4A8 codes; W8 first/last)", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {kind} UNet, latent {list(shape)}, batch {batch}/GPU, W4A8, split shortcuts",
+                       "quant_modules": len(paths), "on_int8_tcgen05_path": n_int8, "cuda_graph": graph is not None,
+                       "l2": "weights + activations of one forward exceed the 126 MB L2 (no flush needed)",
+                       "unet_steps_per_s": world * 1e3 / ms_step, "gemm_gflop_per_sample": flops_step / batch / 1e9,
+                       "attention": "fake-quant kernels + library bmm (fused kernel: next round)"},
+            "e2e": {"value": world * batch * 1e3 / ms_e2e, "unit": "img-steps/s", "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cb, "recon": recon,
+            "effective_int8_tops": flops_step / (ms_step * 1e-3) / 1e12,
+            "wall_s": time.perf_counter() - t_wall0,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,12 @@ _SIGNATURES = {
 
 _lib = None
 
+# kernels each entry point launches (for bench.py's gpu_launches accounting)
+KERNELS_PER_CALL = {"uaq_fwd": 1, "uaq_bwd": 1, "adaround_fwd": 1, "adaround_bwd": 1, "adaround_init_alpha": 1,
+                    "round_reg": 2, "lp_loss_fwd": 2, "lp_loss_bwd": 1, "act_quant_nhwc": 2, "act_quant_rows": 1,
+                    "im2col_u8": 1, "conv_rowsum": 1, "pack_weight": 1, "qgemm_i8": 1, "qattn_fwd": 1}
+launch_counter = {"kernels": 0, "calls": {}}
+
 
 def exported_symbols():
     """Names every build of the library must export (checked by the CPU test-suite)."""
@@ -74,7 +80,11 @@ class _Lib:
         if fn.restype is not c_int or name in ("abi_version", "reduce_slots"):
             return fn
 
+        n_kernels = KERNELS_PER_CALL.get(name, 1)
+
         def call(*args):
+            launch_counter["kernels"] += n_kernels
+            launch_counter["calls"][name] = launch_counter["calls"].get(name, 0) + 1
             rc = fn(*args)
             if rc != 0:
                 msg = handle.edadm_last_error()

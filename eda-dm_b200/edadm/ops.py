@@ -366,6 +366,9 @@ def conv_rowsum(chsum, Ho, Wo, R, S, stride):
     return rs
 
 
+gemm_profile = None   # bench.py sets this to a list to get (start_event, end_event, macs) per GEMM launch
+
+
 def qgemm_i8(q, pw: PackedWeight, delta_a, zp_a, out, out_hw, bias=None, rowsum=None, a_c_offset=0,
              accumulate=False, silu=False, filter_rs=None):
     """Launch the tcgen05 GEMM.  q: [B,Hp,Wp,Cp] u8 codes (or [M,Kp] for a flat GEMM)."""
@@ -379,8 +382,16 @@ def qgemm_i8(q, pw: PackedWeight, delta_a, zp_a, out, out_hw, bias=None, rowsum=
     if pw.needs_rowsum and rowsum is None:
         raise EdadmError("8-bit weight codes need the activation row sums (zero-point fold); pass rowsum")
     cw = pw.cw if pw.needs_rowsum else None
+    prof = gemm_profile
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     lib.qgemm_i8(q.data_ptr(), B, Hp, Wp, Cp_act, int(a_c_offset), pw.wq.data_ptr(), pw.N, pw.Np, R, S,
                  pw.wq.shape[2] if filter_rs is None else pw.wq.shape[1] * pw.wq.shape[2] // (R * S),
                  da.data_ptr(), za.data_ptr(), pw.delta_w.data_ptr(), pw.wsum_eff.data_ptr(), _ptr(cw), _ptr(rowsum),
                  _ptr(bias), out.data_ptr(), int(out_hw), 1 if accumulate else 0, 1 if silu else 0, _stream())
+    if prof is not None:
+        ev1.record()
+        m = B * (Hp - R + 1) * (Wp - S + 1)
+        prof.append((ev0, ev1, m * pw.N * pw.C * pw.R * pw.S))
     return out

@@ -1,0 +1,256 @@
+"""Reconstruction loop shared by block_reconstruction / layer_reconstruction (and their CFG twins).
+
+Same optimisation problem, parameter set, optimiser, schedules and loss as the reference loop
+(qdiff/block_recon.py:39-232, qdiff/layer_recon.py:39-129): AdaRound alphas of every QuantModule in the unit
+(Adam, lr_w) and activation step sizes (Adam, lr_a), both cosine-annealed to 0; loss = L_p(block output,
+FP output) + add_loss * sum of per-layer L2 terms between a quantized and an FP pass (FBR).
+
+What is different on B200:
+  * all quantizer arithmetic, its gradients and the loss reductions are the fused kernels of libedadm.so;
+  * nothing in the loop synchronises with the host (losses stay on the device; the reference calls .cpu()
+    on the loss every iteration, block_recon.py:186,194);
+  * gradients live in one flat bucket (dist.GradBucket) and, when a process group is up, are averaged with a
+    single all-reduce per step -- data parallel over the calibration rows of the unit;
+  * the cache builder shards the calibration set by rank.
+"""
+import random
+
+import torch
+
+from .quant_layer import QuantModule, lp_loss
+from .quant_block import (BaseQuantBlock, QuantAttnBlock, QuantAttentionBlock, QuantBasicTransformerBlock)
+from .adaptive_rounding import AdaRoundQuantizer
+from .utils import AttentionMap
+from edadm import ops
+from . import dist as qdist
+
+
+class LinearTempDecay:
+    """Temperature b of the rounding regulariser (reference block_recon.py:305-323)."""
+
+    def __init__(self, t_max: int, rel_start_decay: float = 0.2, start_b: int = 10, end_b: int = 2):
+        self.t_max = t_max
+        self.start_decay = rel_start_decay * t_max
+        self.start_b, self.end_b = start_b, end_b
+
+    def __call__(self, t):
+        if t < self.start_decay:
+            return self.start_b
+        rel_t = (t - self.start_decay) / (self.t_max - self.start_decay)
+        return self.end_b + (self.start_b - self.end_b) * max(0.0, (1 - rel_t))
+
+
+class LossFunction:
+    """Reconstruction loss + optional rounding regulariser (reference block_recon.py:235-302).  Every caller in
+    the reference passes round_loss='none'; 'relaxation' is kept and runs the fused regulariser kernel."""
+
+    def __init__(self, block, round_loss: str = 'relaxation', weight: float = 1., rec_loss: str = 'mse',
+                 max_count: int = 2000, b_range: tuple = (10, 2), decay_start: float = 0.0, warmup: float = 0.0,
+                 p: float = 2.):
+        self.block, self.round_loss, self.weight, self.rec_loss = block, round_loss, weight, rec_loss
+        self.loss_start = max_count * warmup
+        self.p, self.iters = p, max_count
+        self.temp_decay = LinearTempDecay(max_count, rel_start_decay=warmup + (1 - warmup) * decay_start,
+                                          start_b=b_range[0], end_b=b_range[1])
+        self.count = 0
+
+    def __call__(self, pred, tgt, grad=None):
+        self.count += 1
+        if self.rec_loss == 'mse':
+            rec_loss = lp_loss(pred, tgt, p=self.p)
+        elif self.rec_loss == 'fisher_diag':
+            rec_loss = ((pred - tgt).pow(2) * grad.pow(2)).sum(1).mean()
+        elif self.rec_loss == 'fisher_full':
+            a, g = (pred - tgt).abs(), grad.abs()
+            rec_loss = (torch.sum(a * g, (1, 2, 3)).view(-1, 1, 1, 1) * a * g).mean() / 100
+        else:
+            raise ValueError('Not supported reconstruction loss function: {}'.format(self.rec_loss))
+        b = self.temp_decay(self.count)
+        if self.count < self.loss_start or self.round_loss == 'none':
+            return rec_loss
+        if self.round_loss != 'relaxation':
+            raise NotImplementedError
+        round_loss = 0
+        modules = [self.block] if isinstance(self.block, QuantModule) else self.block.modules()
+        for module in modules:
+            if isinstance(module, QuantModule):
+                round_loss = round_loss + ops.round_reg(module.weight_quantizer.alpha, b, self.weight)
+        return rec_loss + round_loss
+
+
+def _as_param(q):
+    q.delta = torch.nn.Parameter(q.delta.detach().clone())
+    return q.delta
+
+
+def _install_adaround(module: QuantModule, recon_w: bool, w_para: list, split_aware: bool = True):
+    mode = 'learned_hard_sigmoid'
+    if module.split == 0 or not split_aware:
+        module.weight_quantizer = AdaRoundQuantizer(uaq=module.weight_quantizer, round_mode=mode,
+                                                    weight_tensor=module.org_weight.data)
+        quantizers = [module.weight_quantizer]
+    else:
+        module.weight_quantizer = AdaRoundQuantizer(uaq=module.weight_quantizer, round_mode=mode,
+                                                    weight_tensor=module.org_weight.data[:, :module.split, ...].contiguous())
+        module.weight_quantizer_0 = AdaRoundQuantizer(uaq=module.weight_quantizer_0, round_mode=mode,
+                                                      weight_tensor=module.org_weight.data[:, module.split:, ...].contiguous())
+        quantizers = [module.weight_quantizer, module.weight_quantizer_0]
+    if recon_w:
+        for q in quantizers:
+            q.soft_targets = True
+            w_para.append(q.alpha)
+
+
+def _attention_quantizers(module, transformer: bool):
+    """q/k/v/w quantizers that become trainable, in the reference's order."""
+    if isinstance(module, QuantAttentionBlock) and not transformer:
+        a = module.attention
+        return [a.qkv_matmul.act_quantizer_q, a.qkv_matmul.act_quantizer_k, a.smv_matmul.act_quantizer_v,
+                a.smv_matmul.act_quantizer_w]
+    if isinstance(module, QuantAttnBlock):
+        return [module.act_quantizer_q, module.act_quantizer_k, module.act_quantizer_v, module.act_quantizer_w]
+    if isinstance(module, QuantBasicTransformerBlock) and transformer:
+        out = []
+        for attn in (module.attn1, module.attn2):
+            out += [attn.act_quantizer_q, attn.act_quantizer_k, attn.act_quantizer_v, attn.act_quantizer_w]
+        return out
+    return []
+
+
+def prepare_unit(unit, act_quant, recon_w, recon_a, transformer=False, with_hooks=True, split_aware=True,
+                 attn_only=False):
+    """Swap in AdaRound quantizers, promote step sizes to Parameters; returns (w_para, a_para, hooks, trained).
+    attn_only: only the q/k/v/w quantizers of a QuantAttnBlock are trained (reference attn_layer_recon.py:42-58)."""
+    w_para, a_para, hooks, trained = [], [], [], []
+    modules = [unit] if isinstance(unit, QuantModule) else list(unit.modules())
+    for module in modules:
+        if isinstance(module, QuantModule) and not attn_only:
+            if with_hooks:
+                hooks.append(AttentionMap(module))
+            _install_adaround(module, recon_w, w_para, split_aware)
+        if isinstance(module, (QuantModule, BaseQuantBlock)) and act_quant:
+            quantizers = list(_attention_quantizers(module, transformer))
+            if attn_only:
+                quantizers = quantizers if isinstance(module, QuantAttnBlock) else []
+            elif module.act_quantizer.delta is not None:
+                quantizers.append(module.act_quantizer)
+                if module.split != 0 and isinstance(module, QuantModule):
+                    quantizers.append(module.act_quantizer_0)
+            for q in quantizers:
+                p = _as_param(q)
+                if recon_a:
+                    a_para.append(p)
+                    q.is_training = True
+                    trained.append(q)
+    return w_para, a_para, hooks, trained
+
+
+def finish_unit(unit, trained, hooks, attn_only=False):
+    modules = [unit] if isinstance(unit, QuantModule) else list(unit.modules())
+    for module in modules:
+        if isinstance(module, QuantModule) and not attn_only:
+            module.weight_quantizer.soft_targets = False
+            module.act_quantizer.is_training = False
+            if module.split != 0:
+                if hasattr(module.weight_quantizer_0, 'soft_targets'):
+                    module.weight_quantizer_0.soft_targets = False
+                module.act_quantizer_0.is_training = False
+    for q in trained:
+        q.is_training = False
+    for hook in hooks:
+        hook.remove()
+
+
+def _take(t, idx, device):
+    out = t[idx]
+    return out if out.device == device else out.to(device, non_blocking=True)
+
+
+def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, asym, b_range, warmup, act_quant, lr_a,
+                lr_w, p, input_prob, keep_gpu, recon_w, recon_a, add_loss, cache_builder, cache_batch_size=32,
+                transformer=False, is_layer=False, split_aware=True, attn_only=False, return_losses=False, timing=None):
+    unit.set_quant_state(True, act_quant)
+    w_para, a_para, hooks, trained = prepare_unit(unit, act_quant, recon_w, recon_a, transformer,
+                                                  with_hooks=not (is_layer or attn_only), split_aware=split_aware,
+                                                  attn_only=attn_only)
+    w_opt = a_opt = w_sched = a_sched = None
+    if w_para:
+        w_opt = torch.optim.Adam(w_para, lr=lr_w)
+        w_sched = torch.optim.lr_scheduler.CosineAnnealingLR(w_opt, T_max=iters, eta_min=0.)
+    if a_para:
+        a_opt = torch.optim.Adam(a_para, lr=lr_a)
+        a_sched = torch.optim.lr_scheduler.CosineAnnealingLR(a_opt, T_max=iters, eta_min=0.)
+    loss_func = LossFunction(unit, round_loss='none', weight=weight, max_count=iters, rec_loss=opt_mode,
+                             b_range=b_range, decay_start=0, warmup=warmup, p=p)
+
+    resblock, cached_inps, cached_outs = cache_builder(model, unit, cali_data, asym, act_quant,
+                                                       batch_size=cache_batch_size, input_prob=True, keep_gpu=keep_gpu)
+    device = next(model.parameters()).device
+    sz = cached_outs.size(0)
+    model.block_count = model.block_count + 1
+    bucket = qdist.GradBucket(w_para + a_para) if (w_para or a_para) else None
+    rng = random if not qdist.is_active() else random.Random(random.getrandbits(48) + 7919 * qdist.rank())
+    losses = []
+    fbr = (not is_layer) and len(hooks) != 0 and add_loss != 0.0
+
+    for it in range(iters):
+        if timing is not None and it == timing.get('warmup', 0):
+            timing['start'], timing['end'] = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            qdist.barrier()
+            torch.cuda.synchronize()
+            timing['start'].record()
+        idx = rng.sample(range(sz), min(batch_size, sz))
+        idx_t = torch.as_tensor(idx, device=cached_outs.device)
+        cur_out = _take(cached_outs, idx_t, device)
+        if resblock:
+            cur_inp, cur_sym = _take(cached_inps[0][0], idx_t, device), _take(cached_inps[1][0], idx_t, device)
+            emb_inp, emb_sym = _take(cached_inps[0][1], idx_t, device), _take(cached_inps[1][1], idx_t, device)
+        else:
+            cur_inp, cur_sym = _take(cached_inps[0], idx_t, device), _take(cached_inps[1], idx_t, device)
+            emb_inp = emb_sym = None
+        if input_prob < 1.0:
+            cur_inp = torch.where(torch.rand_like(cur_inp) < input_prob, cur_inp, cur_sym)
+        elif not is_layer:
+            cur_inp = cur_sym
+        if bucket is not None:
+            bucket.zero()
+
+        args_q = (cur_inp, emb_inp) if resblock else (cur_inp,)
+        args_fp = (cur_sym, emb_sym) if resblock else (cur_sym,)
+        out_quant = unit(*args_q)
+        m_loss = 0.0
+        if fbr:
+            unit.set_quant_state(False, False)
+            with torch.no_grad():
+                unit(*args_fp)
+            module_r = [h.out for h in hooks]
+            unit.set_quant_state(True, act_quant)
+            unit(*args_q)
+            module_q = [h.out for h in hooks]
+            for j in range(len(module_r) - 1):      # the unit's last QuantModule is left out (reference :188)
+                m_loss = m_loss + lp_loss(module_q[j], module_r[j], p=2)
+        block_loss = loss_func(out_quant, cur_out)
+        loss = block_loss + add_loss * m_loss if fbr else block_loss
+        loss.backward()
+        if bucket is not None:
+            bucket.all_reduce_mean()
+        for step in (w_opt, a_opt, w_sched, a_sched):
+            if step is not None:
+                step.step()
+        if return_losses:
+            losses.append(block_loss.detach())
+
+    if timing is not None and 'start' in timing:
+        timing['end'].record()
+        torch.cuda.synchronize()
+        qdist.barrier()
+        timing['iters'] = iters - timing.get('warmup', 0)
+        timing['ms_per_iter'] = timing['start'].elapsed_time(timing['end']) / max(1, timing['iters'])
+        timing['bucket_bytes'] = bucket.nbytes() if bucket is not None else 0
+    finish_unit(unit, trained, hooks, attn_only)
+    if bucket is not None:
+        for prm in bucket.params:
+            prm.grad = None
+    if return_losses:
+        return torch.stack(losses) if losses else torch.empty(0)
+    return None

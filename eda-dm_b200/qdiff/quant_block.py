@@ -1,0 +1,296 @@
+"""Quantized block wrappers with the reference's names and behaviour (qdiff/quant_block.py:20-508).
+
+The wrappers keep the FP glue (GroupNorm, SiLU, embeddings, residuals) of the block they absorb and
+route (a) every Conv/Linear through QuantModule and (b) the two attention matmuls through the
+quantized-attention op.  They accept both the reference's own L0 classes (ldm.*, ddim.*, when that tree
+is importable) and the from-scratch structures in unet_zoo (same attribute names).
+"""
+import logging
+from types import MethodType
+
+import torch as th
+import torch.nn as nn
+from torch.utils.checkpoint import checkpoint as _torch_checkpoint
+
+from unet_zoo import ddpm_unet as _zoo_ddpm
+from unet_zoo import ldm_unet as _zoo_ldm
+from .quant_layer import QuantModule, UniformAffineQuantizer, StraightThrough
+from . import attention as qattn
+
+logger = logging.getLogger(__name__)
+
+
+def _optional(modname, *names):
+    try:
+        mod = __import__(modname, fromlist=list(names))
+        return [getattr(mod, n) for n in names]
+    except Exception:  # the reference tree is not on sys.path (benchmarks, GPU box)
+        return [None] * len(names)
+
+
+_ref_ResBlock, _ref_AttentionBlock, _ref_QKMatMul, _ref_SMVMatMul, _ref_TimestepBlock = _optional(
+    'ldm.modules.diffusionmodules.openaimodel', 'ResBlock', 'AttentionBlock', 'QKMatMul', 'SMVMatMul', 'TimestepBlock')
+(_ref_BasicTransformerBlock,) = _optional('ldm.modules.attention', 'BasicTransformerBlock')
+_ref_ResnetBlock, _ref_AttnBlock = _optional('ddim.models.diffusion', 'ResnetBlock', 'AttnBlock')
+
+_TimestepBases = tuple(c for c in (_zoo_ldm.TimestepBlock, _ref_TimestepBlock) if c is not None)
+
+
+def checkpoint(func, inputs, params, flag):
+    """Activation recompute when `flag` and a gradient is being recorded (reference util.py:102-148)."""
+    if flag and th.is_grad_enabled():
+        return _torch_checkpoint(func, *inputs, use_reentrant=False)
+    return func(*inputs)
+
+
+def nonlinearity(x):
+    return x * th.sigmoid(x)
+
+
+class BaseQuantBlock(nn.Module):
+    """Common state of all quantized blocks (reference quant_block.py:20-43)."""
+
+    def __init__(self, act_quant_params: dict = {}):
+        super().__init__()
+        self.use_weight_quant = False
+        self.use_act_quant = False
+        self.can_recon = True
+        self.split = 0
+        self.act_quantizer = UniformAffineQuantizer(**act_quant_params)  # present but unused, as in the reference
+        self.activation_function = StraightThrough()
+        self.ignore_reconstruction = False
+
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        self.use_weight_quant = weight_quant
+        self.use_act_quant = act_quant
+        for m in self.modules():
+            if isinstance(m, QuantModule):
+                m.set_quant_state(weight_quant, act_quant)
+
+
+# ---- LDM / ADM residual block -------------------------------------------------------------------------
+class QuantResBlock(BaseQuantBlock, *_TimestepBases):
+    takes_emb = True
+
+    def __init__(self, res, act_quant_params: dict = {}):
+        super().__init__(act_quant_params)
+        for name in ('channels', 'emb_channels', 'dropout', 'out_channels', 'use_conv', 'use_checkpoint',
+                     'use_scale_shift_norm', 'in_layers', 'updown', 'h_upd', 'x_upd', 'emb_layers', 'out_layers',
+                     'skip_connection'):
+            setattr(self, name, getattr(res, name))
+        self.split = 0
+
+    def forward(self, x, emb=None, split=0):
+        use_split = split != 0 and not isinstance(self.skip_connection, nn.Identity) and self.skip_connection.split == 0
+        args = (x, emb, split) if use_split else (x, emb)
+        return checkpoint(self._forward, args, self.parameters(), self.use_checkpoint)
+
+    def _forward(self, x, emb, split=0):
+        if emb is None:
+            assert len(x) == 2
+            x, emb = x
+        assert x.shape[2] == x.shape[3]
+        if split != 0:
+            self.split = split
+        return _zoo_ldm.resblock_forward(self, x, emb, self.split if split != 0 else 0)
+
+
+# ---- LDM attention: the two matmuls -----------------------------------------------------------------------
+class QuantQKMatMul(BaseQuantBlock):
+    def __init__(self, act_quant_params: dict = {}):
+        super().__init__(act_quant_params)
+        self.scale = None
+        self.use_act_quant = False
+        self.act_quantizer_q = UniformAffineQuantizer(**act_quant_params)
+        self.act_quantizer_k = UniformAffineQuantizer(**act_quant_params)
+
+    def forward(self, q, k):
+        if self.use_act_quant:
+            return qattn.qk_scores_bct(self.act_quantizer_q(q * self.scale), self.act_quantizer_k(k * self.scale))
+        return th.einsum("bct,bcs->bts", q * self.scale, k * self.scale)
+
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        self.use_act_quant = act_quant
+
+
+class QuantSMVMatMul(BaseQuantBlock):
+    def __init__(self, act_quant_params: dict = {}, sm_abit=8):
+        super().__init__(act_quant_params)
+        self.use_act_quant = False
+        self.act_quantizer_v = UniformAffineQuantizer(**act_quant_params)
+        params_w = act_quant_params.copy()
+        params_w['n_bits'] = sm_abit
+        params_w['symmetric'] = False
+        params_w['always_zero'] = True
+        self.act_quantizer_w = UniformAffineQuantizer(**params_w)
+
+    def forward(self, weight, v):
+        if self.use_act_quant:
+            return th.einsum("bts,bcs->bct", self.act_quantizer_w(weight), self.act_quantizer_v(v))
+        return th.einsum("bts,bcs->bct", weight, v)
+
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        self.use_act_quant = act_quant
+
+
+class QuantAttentionBlock(BaseQuantBlock):
+    def __init__(self, attn, act_quant_params: dict = {}):
+        super().__init__(act_quant_params)
+        self.channels = attn.channels
+        self.num_heads = attn.num_heads
+        self.use_checkpoint = attn.use_checkpoint
+        self.norm = attn.norm
+        self.qkv = attn.qkv
+        self.attention = attn.attention
+        self.proj_out = attn.proj_out
+
+    def forward(self, x):
+        return checkpoint(self._forward, (x,), self.parameters(), True)
+
+    def _forward(self, x):
+        b, c, *spatial = x.shape
+        x = x.reshape(b, c, -1)
+        h = self.proj_out(self.attention(self.qkv(self.norm(x))))
+        return (x + h).reshape(b, c, *spatial)
+
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        self.use_weight_quant = weight_quant
+        self.use_act_quant = act_quant
+        for m in self.modules():
+            if isinstance(m, QuantModule):
+                m.set_quant_state(weight_quant, act_quant)
+            elif isinstance(m, (QuantQKMatMul, QuantSMVMatMul)):
+                m.set_quant_state(weight_quant, act_quant)
+
+
+# ---- transformer block (ImageNet / Stable Diffusion) -------------------------------------------------------
+def cross_attn_forward(self, x, context=None, mask=None):
+    """Replacement `CrossAttention.forward` with quantized q, k, v and softmax (reference quant_block.py:204-235)."""
+    h = self.heads
+    q = self.to_q(x)
+    context = x if context is None else context
+    k, v = self.to_k(context), self.to_v(context)
+    q, k, v = (_zoo_ldm._heads_split(t, h) for t in (q, k, v))
+    if mask is not None:
+        raise NotImplementedError("attention masks are not used by any EDA-DM configuration")
+    if self.use_act_quant:
+        out = qattn.quantized_attention_bnd(q, k, v, self.scale, self.act_quantizer_q, self.act_quantizer_k,
+                                            self.act_quantizer_v, self.act_quantizer_w)
+    else:
+        attn = (th.einsum('bid,bjd->bij', q, k) * self.scale).softmax(dim=-1)
+        out = th.einsum('bij,bjd->bid', attn, v)
+    return self.to_out(_zoo_ldm._heads_merge(out, h))
+
+
+class QuantBasicTransformerBlock(BaseQuantBlock):
+    def __init__(self, tran, act_quant_params: dict = {}, sm_abit: int = 8):
+        super().__init__(act_quant_params)
+        self.attn1, self.ff, self.attn2 = tran.attn1, tran.ff, tran.attn2
+        self.norm1, self.norm2, self.norm3 = tran.norm1, tran.norm2, tran.norm3
+        self.checkpoint = tran.checkpoint
+        params_w = act_quant_params.copy()
+        params_w['n_bits'] = sm_abit
+        params_w['always_zero'] = True
+        for attn in (self.attn1, self.attn2):
+            attn.act_quantizer_q = UniformAffineQuantizer(**act_quant_params)
+            attn.act_quantizer_k = UniformAffineQuantizer(**act_quant_params)
+            attn.act_quantizer_v = UniformAffineQuantizer(**act_quant_params)
+            attn.act_quantizer_w = UniformAffineQuantizer(**params_w)
+            attn.forward = MethodType(cross_attn_forward, attn)
+            attn.use_act_quant = False
+
+    def forward(self, x, context=None):
+        return checkpoint(self._forward, (x, context), self.parameters(), self.checkpoint)
+
+    def _forward(self, x, context=None):
+        if context is None:
+            assert len(x) == 2
+            x, context = x
+        x = self.attn1(self.norm1(x)) + x
+        x = self.attn2(self.norm2(x), context=context) + x
+        return self.ff(self.norm3(x)) + x
+
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        self.attn1.use_act_quant = act_quant
+        self.attn2.use_act_quant = act_quant
+        self.use_weight_quant = weight_quant
+        self.use_act_quant = act_quant
+        for m in self.modules():
+            if isinstance(m, QuantModule):
+                m.set_quant_state(weight_quant, act_quant)
+
+
+# ---- DDIM (CIFAR) blocks ----------------------------------------------------------------------------------
+class QuantResnetBlock(BaseQuantBlock):
+    def __init__(self, res, act_quant_params: dict = {}):
+        super().__init__(act_quant_params)
+        self.in_channels, self.out_channels = res.in_channels, res.out_channels
+        self.use_conv_shortcut = res.use_conv_shortcut
+        self.norm1, self.conv1, self.temb_proj = res.norm1, res.conv1, res.temb_proj
+        self.norm2, self.dropout, self.conv2 = res.norm2, res.dropout, res.conv2
+        if self.in_channels != self.out_channels:
+            if self.use_conv_shortcut:
+                self.conv_shortcut = res.conv_shortcut
+            else:
+                self.nin_shortcut = res.nin_shortcut
+        self.split = 0
+
+    def forward(self, x, temb=None, split=0):
+        if split != 0:
+            self.split = split
+        h = self.conv1(nonlinearity(self.norm1(x)))
+        h = h + self.temb_proj(nonlinearity(temb))[:, :, None, None]
+        h = self.conv2(self.dropout(nonlinearity(self.norm2(h))))
+        if self.in_channels != self.out_channels:
+            x = self.conv_shortcut(x) if self.use_conv_shortcut else self.nin_shortcut(x, split=self.split)
+        return x + h
+
+
+class QuantAttnBlock(BaseQuantBlock):
+    def __init__(self, attn, act_quant_params: dict = {}, sm_abit=8):
+        super().__init__(act_quant_params)
+        self.in_channels = attn.in_channels
+        self.norm, self.q, self.k, self.v, self.proj_out = attn.norm, attn.q, attn.k, attn.v, attn.proj_out
+        self.act_quantizer_q = UniformAffineQuantizer(**act_quant_params)
+        self.act_quantizer_k = UniformAffineQuantizer(**act_quant_params)
+        self.act_quantizer_v = UniformAffineQuantizer(**act_quant_params)
+        params_w = act_quant_params.copy()
+        params_w['n_bits'] = sm_abit
+        self.act_quantizer_w = UniformAffineQuantizer(**params_w)
+
+    def forward(self, x):
+        h_ = self.norm(x)
+        q, k, v = self.q(h_), self.k(h_), self.v(h_)
+        b, c, h, w = q.shape
+        scale = int(c) ** (-0.5)
+        if self.use_act_quant:
+            out = qattn.quantized_attention_bct(q.reshape(b, c, h * w), k.reshape(b, c, h * w), v.reshape(b, c, h * w), scale,
+                                                self.act_quantizer_q, self.act_quantizer_k, self.act_quantizer_v,
+                                                self.act_quantizer_w)
+        else:
+            qf = q.reshape(b, c, h * w).permute(0, 2, 1)
+            w_ = th.softmax(th.bmm(qf, k.reshape(b, c, h * w)) * scale, dim=2)
+            out = th.bmm(v.reshape(b, c, h * w), w_.permute(0, 2, 1))
+        return x + self.proj_out(out.reshape(b, c, h, w))
+
+
+def get_specials(quant_act=False):
+    """block type -> quantized wrapper (reference quant_block.py:496-508); with `quant_act` (leaf_param) the LDM
+    AttentionBlock is kept and only its two matmul modules are swapped."""
+    specials = {}
+
+    def add(zoo_cls, ref_cls, wrapper):
+        specials[zoo_cls] = wrapper
+        if ref_cls is not None:
+            specials[ref_cls] = wrapper
+
+    add(_zoo_ldm.ResBlock, _ref_ResBlock, QuantResBlock)
+    add(_zoo_ldm.BasicTransformerBlock, _ref_BasicTransformerBlock, QuantBasicTransformerBlock)
+    add(_zoo_ddpm.ResnetBlock, _ref_ResnetBlock, QuantResnetBlock)
+    add(_zoo_ddpm.AttnBlock, _ref_AttnBlock, QuantAttnBlock)
+    if quant_act:
+        add(_zoo_ldm.QKMatMul, _ref_QKMatMul, QuantQKMatMul)
+        add(_zoo_ldm.SMVMatMul, _ref_SMVMatMul, QuantSMVMatMul)
+    else:
+        add(_zoo_ldm.AttentionBlock, _ref_AttentionBlock, QuantAttentionBlock)
+    return specials

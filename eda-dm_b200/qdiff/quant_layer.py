@@ -1,0 +1,460 @@
+"""QuantModule / UniformAffineQuantizer with the reference's interface (qdiff/quant_layer.py:36-446 of
+BienLuky/EDA-DM) on top of the sm_100a kernels in libedadm.so.
+
+Two execution paths, chosen per call by `QuantModule.forward`:
+
+* integer path (sampling, cache building: weight+act quantization on, no gradient wanted) --
+  activations are quantized to u8 codes, weights are packed once to s8 codes, and the conv / linear
+  runs as an exact int32 tcgen05 GEMM with the dequant in the epilogue (edadm_qgemm_i8);
+* calibration path (reconstruction, weight-only quantization, scale search) -- the fused fake-quant
+  kernels (edadm_uaq_fwd/bwd, edadm_adaround_fwd/bwd) produce fp32 operands with straight-through
+  gradients, feeding a library fp32 convolution.
+
+There is no CPU fallback: CPU tensors are only accepted on the un-quantized (FP) branch.
+"""
+import logging
+from typing import Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from edadm import ops
+from edadm.native import EdadmError
+
+logger = logging.getLogger(__name__)
+
+
+class _Backend:
+    """Process-wide knobs of the calibration path (defaults reproduce the reference's fp32 numerics)."""
+    allow_tf32 = False       # library conv/matmul of the calibration path in strict fp32
+    integer_path = True      # use the tcgen05 int8 GEMM whenever it applies
+    qdrop_seed = None        # None -> torch.initial_seed()
+    qdrop_offset = 0         # running Philox offset (one fresh sub-stream per fake-quant call)
+
+    @classmethod
+    def next_stream(cls, numel: int):
+        seed = cls.qdrop_seed if cls.qdrop_seed is not None else torch.initial_seed()
+        off = cls.qdrop_offset
+        cls.qdrop_offset += (numel + 3) // 4 * 4
+        return seed & 0xFFFFFFFFFFFFFFFF, off
+
+
+backend = _Backend
+
+
+class StraightThrough(nn.Module):
+    def __init__(self, channel_num: int = 1):
+        super().__init__()
+
+    def forward(self, input):
+        return input
+
+
+def _tdiv(t: torch.Tensor, scalar: float) -> torch.Tensor:
+    """IEEE division of a tensor by a Python scalar.  torch's CUDA kernel turns `t / python_scalar` into
+    `t * (1/scalar)`, which is 1 ulp off and flips `round(min/scale)` between 7 and 8 (or 127 and 128) during the range
+    search; dividing by a 0-dim DEVICE tensor keeps true division, i.e. the CPU semantics the oracle is pinned to."""
+    return t / torch.full((), float(scalar), dtype=t.dtype, device=t.device)
+
+
+def round_ste(x: torch.Tensor):
+    """Round with identity gradient (reference quant_layer.py:19-23)."""
+    return (x.round() - x).detach() + x
+
+
+def lp_loss(pred, tgt, p=2.0, reduction='none'):
+    """L_p loss (reference quant_layer.py:26-33); one fused reduction kernel on CUDA tensors."""
+    if pred.is_cuda:
+        return ops.lp_loss(pred, tgt, p, reduction)
+    d = (pred - tgt).abs().pow(p)
+    return d.sum(1).mean() if reduction == 'none' else d.mean()
+
+
+class UniformAffineQuantizer(nn.Module):
+    """Uniform affine fake-quantizer; same constructor, attributes and init behaviour as the reference
+    (quant_layer.py:36-358): `delta`/`zero_point` are found by an L2.4 grid search on the first
+    un-inited forward, `delta` becomes an nn.Parameter when `leaf_param`, and `inited` only changes
+    through `set_inited()`.
+    """
+
+    def __init__(self, n_bits: int = 8, symmetric: bool = False, channel_wise: bool = False, scale_method: str = 'max',
+                 leaf_param: bool = False, always_zero: bool = False, prob: float = 1.0):
+        super().__init__()
+        self.sym = symmetric
+        self.bitwidth_refactor(n_bits)
+        self.delta = None
+        self.zero_point = None
+        self.inited = False
+        self.leaf_param = leaf_param
+        self.channel_wise = channel_wise
+        self.scale_method = scale_method
+        self.running_stat = False
+        self.always_zero = always_zero
+        if self.leaf_param:
+            self.x_min, self.x_max = None, None
+        self.running_min = None
+        self.running_max = None
+        self.one_side_dist = None
+        self.num = 100
+        self.eps = torch.tensor(1e-8, dtype=torch.float32)
+        self.prob = prob
+        self.is_training = False
+
+    def set_inited(self, inited: bool = True):
+        self.inited = inited
+
+    def bitwidth_refactor(self, refactored_bit: int):
+        self.n_bits = refactored_bit
+        self.n_levels = 2 ** self.n_bits
+
+    # ---- scale search (reference quant_layer.py:79-244); init-time, plain tensor ops on the device ----
+    def update_quantize_range(self, x_min, x_max):
+        if self.running_min is None:
+            self.running_min, self.running_max = x_min, x_max
+        self.running_min = 0.1 * x_min + 0.9 * self.running_min
+        self.running_max = 0.1 * x_max + 0.9 * self.running_max
+        return self.running_min, self.running_max
+
+    def calculate_qparams(self, min_val, max_val):
+        qmax = self.n_levels - 1
+        lo = torch.clamp(min_val, max=0.0)
+        hi = torch.clamp(max_val, min=0.0)
+        scale = torch.clamp(_tdiv(hi - lo, qmax), min=1e-8)
+        zero_point = torch.clamp(0 - torch.round(lo / scale), 0, qmax)
+        return scale, zero_point
+
+    def _score_candidates(self, x_flat, new_min, new_max, rows: bool):
+        """L2.4 score of each (new_min, new_max) candidate; `rows` = per-channel candidates [C] against
+        x_flat [C, n], else a batch of per-tensor candidates [k] against x_flat [1, n]."""
+        scale, zp = self.calculate_qparams(new_min, new_max)
+        scale, zp = scale.reshape(-1, 1), zp.reshape(-1, 1)
+        q = torch.clamp(torch.round(x_flat / scale) + zp, 0, self.n_levels - 1)
+        return ((q - zp) * scale - x_flat).abs_().pow_(2.4).mean(1)
+
+    def perform_1D_search(self, x):
+        if self.channel_wise:
+            y = torch.flatten(x, 1)
+            x_min, x_max = y.amin(1), y.amax(1)
+        else:
+            y = x.reshape(1, -1)
+            x_min, x_max = x.amin(), x.amax()
+        xrange = torch.max(x_min.abs(), x_max)
+        steps = torch.arange(1, self.num + 1, device=x.device)
+        if not self.channel_wise:
+            thres = _tdiv(xrange, self.num) * steps
+            new_min = torch.zeros_like(thres) if self.one_side_dist == 'pos' else -thres
+            new_max = torch.zeros_like(thres) if self.one_side_dist == 'neg' else thres
+            scores = [self._score_candidates(y, new_min[i:i + 8], new_max[i:i + 8], False) for i in range(0, self.num, 8)]
+            ind = torch.argmin(torch.cat(scores))
+            return new_min[ind], new_max[ind]
+        best_score = torch.full_like(x_min, 1e10)
+        best_min, best_max = x_min.clone(), x_max.clone()
+        for i in range(1, self.num + 1):
+            thres = _tdiv(xrange, self.num) * i
+            new_min = torch.zeros_like(x_min) if self.one_side_dist == 'pos' else -thres
+            new_max = torch.zeros_like(x_max) if self.one_side_dist == 'neg' else thres
+            score = self._score_candidates(y, new_min, new_max, True)
+            better = score < best_score
+            best_min = torch.where(better, new_min, best_min)
+            best_max = torch.where(better, new_max, best_max)
+            best_score = torch.min(score, best_score)
+        return best_min, best_max
+
+    def perform_2D_search(self, x):
+        if self.channel_wise:
+            y = torch.flatten(x, 1)
+            x_min, x_max = torch.clamp(y.amin(1), max=0.0), torch.clamp(y.amax(1), min=0.0)
+        else:
+            y = x.reshape(1, -1)
+            x_min, x_max = x.amin().reshape(1), x.amax().reshape(1)
+        xrange = x_max - x_min
+        best_score = torch.full_like(x_min, 1e10)
+        best_min, best_max = x_min.clone(), x_max.clone()
+        for i in range(1, self.num + 1):
+            tmp_max = _tdiv(xrange, self.num) * i
+            tmp_delta = _tdiv(tmp_max, 2 ** self.n_bits - 1)
+            for zp in range(0, self.n_levels):
+                new_min, new_max = -zp * tmp_delta, tmp_max - zp * tmp_delta
+                score = self._score_candidates(y, new_min, new_max, True)
+                better = score < best_score
+                best_min = torch.where(better, new_min, best_min)
+                best_max = torch.where(better, new_max, best_max)
+                best_score = torch.min(best_score, score)
+        if not self.channel_wise:
+            return best_min[0], best_max[0]
+        return best_min, best_max
+
+    def get_x_min_x_max(self, x):
+        if self.scale_method != 'mse':
+            raise NotImplementedError
+        if self.one_side_dist is None:
+            self.one_side_dist = 'pos' if x.min() >= 0.0 else 'neg' if x.max() <= 0.0 else 'no'
+        if self.one_side_dist != 'no' or self.sym:
+            best_min, best_max = self.perform_1D_search(x)
+        else:
+            best_min, best_max = self.perform_2D_search(x)
+        if self.leaf_param:
+            return self.update_quantize_range(best_min, best_max)
+        return best_min, best_max
+
+    def init_quantization_scale_1(self, x: torch.Tensor, channel_wise: bool = False):
+        with torch.no_grad():
+            x_min, x_max = self.get_x_min_x_max(x.detach())
+            delta, zero_point = self.calculate_qparams(x_min, x_max)
+        if channel_wise:
+            shape = [1] * x.dim()
+            shape[0] = x.shape[0]
+            delta, zero_point = delta.reshape(shape), zero_point.reshape(shape)
+        return delta, zero_point
+
+    # ---- forward -------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor):
+        if self.inited is False:
+            if self.scale_method != 'mse':
+                raise NotImplementedError
+            delta, self.zero_point = self.init_quantization_scale_1(x, self.channel_wise)
+            self.delta = torch.nn.Parameter(delta) if self.leaf_param else delta
+        if not x.is_cuda:
+            raise EdadmError("UniformAffineQuantizer needs CUDA tensors: the fake-quant kernel has no CPU fallback")
+        if self.is_training and self.prob < 1.0:
+            seed, offset = backend.next_stream(x.numel())
+            return ops.uaq_fake_quant(x, self.delta, self.zero_point, self.n_levels, None, self.prob, seed, offset)
+        return ops.uaq_fake_quant(x, self.delta, self.zero_point, self.n_levels)
+
+    def codes(self, x: torch.Tensor):
+        """Integer codes clamp(round(x/delta)+zp, 0, L-1) as uint8 (never materialised by the reference)."""
+        return ops.uaq_forward(x, self.delta, self.zero_point, self.n_levels, want_codes=True)[1]
+
+    def extra_repr(self):
+        s = 'bit={n_bits}, scale_method={scale_method}, symmetric={sym}, channel_wise={channel_wise},' \
+            ' leaf_param={leaf_param}'
+        return s.format(**self.__dict__)
+
+
+def _version_of(t):
+    return None if t is None else (t.data_ptr(), t._version, tuple(t.shape))
+
+
+class QuantModule(nn.Module):
+    """Quantized Conv2d / Conv1d / Linear with the reference's constructor, attributes and
+    `forward(input, split=0)` (quant_layer.py:360-446)."""
+
+    def __init__(self, org_module: Union[nn.Conv2d, nn.Linear, nn.Conv1d], weight_quant_params: dict = {},
+                 act_quant_params: dict = {}, disable_act_quant: bool = False, act_quant_mode: str = 'qdiff'):
+        super().__init__()
+        self.weight_quant_params = weight_quant_params
+        self.act_quant_params = act_quant_params
+        if isinstance(org_module, nn.Conv2d):
+            self.fwd_kwargs = dict(stride=org_module.stride, padding=org_module.padding,
+                                   dilation=org_module.dilation, groups=org_module.groups)
+            self.fwd_func = F.conv2d
+        elif isinstance(org_module, nn.Conv1d):
+            self.fwd_kwargs = dict(stride=org_module.stride, padding=org_module.padding,
+                                   dilation=org_module.dilation, groups=org_module.groups)
+            self.fwd_func = F.conv1d
+        else:
+            self.fwd_kwargs = dict()
+            self.fwd_func = F.linear
+        self.weight = org_module.weight
+        self.org_weight = org_module.weight.data.clone()
+        if org_module.bias is not None:
+            self.bias = org_module.bias
+            self.org_bias = org_module.bias.data.clone()
+        else:
+            self.bias = None
+            self.org_bias = None
+        self.use_weight_quant = False
+        self.use_act_quant = False
+        self.act_quant_mode = act_quant_mode
+        self.disable_act_quant = disable_act_quant
+        self.weight_quantizer = UniformAffineQuantizer(**self.weight_quant_params)
+        if self.act_quant_mode == 'qdiff':
+            self.act_quantizer = UniformAffineQuantizer(**self.act_quant_params)
+        self.split = 0
+        self.activation_function = StraightThrough()
+        self.ignore_reconstruction = False
+        self.extra_repr = org_module.extra_repr
+        self._packed = None       # (key, [PackedWeight, ...]) cache of the integer path
+        self.last_path = None     # 'fp' | 'int8' | 'fake' -- which branch the last forward took
+
+    # non-persistent caches must not leak into copies / state_dict
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        out = super()._apply(fn, *a, **k)
+        self.org_weight = fn(self.org_weight)
+        if self.org_bias is not None:
+            self.org_bias = fn(self.org_bias)
+        return out
+
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        self.use_weight_quant = weight_quant
+        self.use_act_quant = act_quant
+
+    def set_split(self):
+        self.weight_quantizer_0 = UniformAffineQuantizer(**self.weight_quant_params)
+        if self.act_quant_mode == 'qdiff':
+            self.act_quantizer_0 = UniformAffineQuantizer(**self.act_quant_params)
+
+    # ---- path selection ------------------------------------------------------------------------------
+    def _quantizers(self):
+        if self.split != 0:
+            return [self.weight_quantizer, self.weight_quantizer_0], [self.act_quantizer, self.act_quantizer_0]
+        return [self.weight_quantizer], [self.act_quantizer]
+
+    def _integer_path_ok(self, input):
+        if not (backend.integer_path and self.use_weight_quant and self.use_act_quant and not self.disable_act_quant):
+            return False
+        if not input.is_cuda or input.dtype != torch.float32 or torch.is_grad_enabled() and input.requires_grad:
+            return False
+        wqs, aqs = self._quantizers()
+        for aq in aqs:
+            if aq.inited is False or aq.delta is None or aq.channel_wise or (aq.is_training and aq.prob < 1.0):
+                return False
+            if torch.is_grad_enabled() and isinstance(aq.delta, nn.Parameter) and aq.delta.requires_grad and aq.is_training:
+                return False
+        for wq in wqs:
+            if getattr(wq, 'inited', True) is False or wq.delta is None:
+                return False
+            if getattr(wq, 'soft_targets', False):
+                return False
+            if getattr(wq, 'round_mode', 'learned_hard_sigmoid') != 'learned_hard_sigmoid':
+                return False
+        if torch.is_grad_enabled() and any(getattr(wq, 'alpha', None) is not None and wq.alpha.requires_grad and
+                                           getattr(wq, 'soft_targets', False) for wq in wqs):
+            return False
+        kw = self.fwd_kwargs
+        if kw:
+            if kw['groups'] != 1 or any(d != 1 for d in kw['dilation']):
+                return False
+            pad, stride = kw['padding'], kw['stride']
+            if isinstance(pad, str) or len(set(pad)) != 1 or len(set(stride)) != 1:
+                return False
+        return True
+
+    def _packed_weights(self):
+        wqs, _ = self._quantizers()
+        key = tuple((id(wq), wq.n_levels, _version_of(wq.delta), _version_of(wq.zero_point),
+                     _version_of(getattr(wq, 'alpha', None))) for wq in wqs) + (_version_of(self.weight), self.split)
+        if self._packed is not None and self._packed[0] == key:
+            return self._packed[1]
+        w = self.weight.detach()
+        if w.dim() == 3:                       # conv1d [N, C, k]
+            w = w.unsqueeze(2)
+        elif w.dim() == 2:                     # linear [N, K]
+            w = w.reshape(w.shape[0], w.shape[1], 1, 1)
+        packs = []
+        bounds = [(0, w.shape[1])] if self.split == 0 else [(0, self.split), (self.split, w.shape[1])]
+        for wq, (c0, c1) in zip(wqs, bounds):
+            alpha = getattr(wq, 'alpha', None)
+            packs.append(ops.pack_weight(w, wq.delta, wq.zero_point, wq.n_levels, alpha=alpha, c_begin=c0, c_end=c1))
+        self._packed = (key, packs)
+        return packs
+
+    def _forward_int8(self, input):
+        """Exact integer GEMM: out = dA*dW[n]*sum (qa-za)(qw-zw) + bias  == the reference's fp32 conv of the
+        dequantised tensors (quant_layer.py:414-434) without its per-product rounding."""
+        packs = self._packed_weights()
+        _, aqs = self._quantizers()
+        aq = ops.ActQuant(aqs[0].delta, aqs[0].zero_point, aqs[0].n_levels,
+                          self.split, aqs[1].delta if self.split else None,
+                          aqs[1].zero_point if self.split else None, aqs[1].n_levels if self.split else 0)
+        needs_rowsum = any(p.needs_rowsum for p in packs)
+        if needs_rowsum and self.split:
+            raise EdadmError("split shortcut with 8-bit weights is not supported on the integer path")
+        bias = None if self.bias is None else self.bias.detach()
+        pw0 = packs[0]
+        N = pw0.N
+        if self.fwd_func is F.linear:
+            lead = input.shape[:-1]
+            x2 = input.reshape(-1, input.shape[-1])
+            q, rowsum = ops.act_quant_rows(x2, aq, want_rowsum=needs_rowsum)
+            out = torch.empty((x2.shape[0], N), dtype=torch.float32, device=input.device)
+            if x2.shape[0] > 0:
+                self._gemm_chain(q, packs, aqs, out, 1, bias, rowsum)
+            return out.reshape(*lead, N)
+        x4 = input.unsqueeze(2) if self.fwd_func is F.conv1d else input
+        B, C, H, W = x4.shape
+        R, S = pw0.R, pw0.S
+        pad = int(self.fwd_kwargs['padding'][0])
+        stride = int(self.fwd_kwargs['stride'][0])
+        pad_h = 0 if self.fwd_func is F.conv1d else pad
+        if pad_h != pad:
+            raise EdadmError("conv1d with padding is not supported on the integer path")
+        Ho = (H + 2 * pad_h - R) // stride + 1
+        Wo = (W + 2 * pad - S) // stride + 1
+        q, chsum = ops.act_quant_nhwc(x4, aq, pad, want_chsum=needs_rowsum)
+        rowsum = ops.conv_rowsum(chsum, Ho, Wo, R, S, stride) if needs_rowsum else None
+        out = torch.empty((B, N, Ho, Wo), dtype=torch.float32, device=input.device)
+        if stride == 1 and _implicit_tiling_ok(B, Ho, Wo):
+            self._gemm_chain(q, packs, aqs, out, Ho * Wo, bias, rowsum)
+        else:
+            if self.split:
+                raise EdadmError("split shortcut on a strided / irregular conv is not supported on the integer path")
+            a = ops.im2col_u8(q, Ho, Wo, R, S, stride)
+            ops.qgemm_i8(a, pw0, aqs[0].delta, aqs[0].zero_point, out, Ho * Wo, bias=bias, rowsum=rowsum, filter_rs=(1, 1))
+        return out.squeeze(2) if self.fwd_func is F.conv1d else out
+
+    def _gemm_chain(self, q, packs, aqs, out, out_hw, bias, rowsum):
+        c_off = 0
+        for i, (pw, aqz) in enumerate(zip(packs, aqs)):
+            ops.qgemm_i8(q, pw, aqz.delta, aqz.zero_point, out, out_hw, bias=bias if i == 0 else None, rowsum=rowsum,
+                         a_c_offset=c_off, accumulate=i > 0)
+            c_off += pw.C
+
+    # ---- forward -------------------------------------------------------------------------------------
+    def forward(self, input: torch.Tensor, split: int = 0):
+        if split != 0 and self.split != 0:
+            assert split == self.split
+        elif split != 0:
+            logger.info(f"split at {split}!")
+            self.split = split
+            self.set_split()
+
+        if self._integer_path_ok(input):
+            self.last_path = 'int8'
+            return self.activation_function(self._forward_int8(input))
+
+        if not self.disable_act_quant and self.use_act_quant:
+            if self.split != 0:
+                input = torch.cat([self.act_quantizer(input[:, :self.split, :, :]),
+                                   self.act_quantizer_0(input[:, self.split:, :, :])], dim=1)
+            else:
+                input = self.act_quantizer(input)
+        if self.use_weight_quant:
+            if self.split != 0:
+                weight = torch.cat([self.weight_quantizer(self.weight[:, :self.split, ...]),
+                                    self.weight_quantizer_0(self.weight[:, self.split:, ...])], dim=1)
+            else:
+                weight = self.weight_quantizer(self.weight)
+            bias = self.bias
+        else:
+            weight = self.org_weight
+            bias = self.org_bias
+        self.last_path = 'fake' if (self.use_weight_quant or self.use_act_quant) else 'fp'
+        out = _library_fwd(self.fwd_func, input, weight, bias, self.fwd_kwargs)
+        return self.activation_function(out)
+
+
+def _implicit_tiling_ok(B, Ho, Wo):
+    """Mirror of the tile-shape checks in edadm_qgemm_i8: 128 consecutive output pixels form a W x H x B box."""
+    if Wo >= 128:
+        return Wo % 128 == 0
+    if 128 % Wo:
+        return False
+    rows = 128 // Wo
+    return (Ho % rows == 0) if rows <= Ho else (rows % Ho == 0)
+
+
+def _library_fwd(fn, input, weight, bias, kwargs):
+    """fp32 conv / linear of the calibration + FP paths (cuDNN / cuBLAS), TF32 off unless opted in."""
+    if not input.is_cuda or backend.allow_tf32:
+        return fn(input, weight, bias, **kwargs)
+    prev_c, prev_m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        return fn(input, weight, bias, **kwargs)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev_c
+        torch.backends.cuda.matmul.allow_tf32 = prev_m

@@ -107,7 +107,7 @@ def resblock_forward(blk, x, emb, split=0):
         h = blk.out_layers[1:](h)
     else:
         h = blk.out_layers(h + emb_out)
-    if split:
+    if split and not isinstance(blk.skip_connection, nn.Identity):
         return blk.skip_connection(x, split=split) + h
     return blk.skip_connection(x) + h
 
