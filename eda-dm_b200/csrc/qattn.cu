@@ -1,0 +1,342 @@
+// Fused quantized attention for sm_100a (replaces the bmm / softmax / fake-quant chain of
+// QuantAttnBlock.forward quant_block.py:431-445, cross_attn_forward :214-233 of the reference).
+//
+// Inputs are the u8 CODES of q, k (token-major [BH][T][dp]) and v (channel-major [BH][d][Tkp]) plus their per-token /
+// per-channel code sums; the kernel never sees fp32 q/k/v and the T x T probability matrix never leaves the SM:
+//
+//   S[t][s]  = dq*dk*scale * sum_c (q[t][c]-zq)(k[s][c]-zk)            int8 tcgen05 MMA into TMEM, exact
+//   P        = softmax_s(S)                                             fp32, two passes over the keys (row max / sum
+//                                                                       first, then the normalised probabilities)
+//   Pq[t][s] = clamp(rint(P/dP) + zP, 0, L-1)                           quantized in registers -> 128B-swizzled smem
+//   O[t][c]  = dP*dv * sum_s (Pq[t][s]-zP)(v[c][s]-zv)                  second tcgen05 MMA, accumulator in TMEM
+//
+// Zero-points are folded with the code sums (rq, rk, rv, and the running row sum of Pq), so operands stay raw u8.
+// One CTA = 128 queries x one chunk (<=256) of the head dim of one (batch, head).  Warp roles: 0 TMA producer,
+// 1 MMA issuer, 2..5 softmax + epilogue (thread == query row == TMEM lane).
+#include "tc05.cuh"
+
+namespace edadm {
+
+constexpr int ATT_M = 128;
+constexpr int ATT_S = 128;
+constexpr int ATT_KB = 128;
+constexpr int QK_STAGES = 3;
+constexpr int V_STAGES = 2;
+constexpr int ATT_TILE_BYTES = 128 * 128;       // 16 KB: Q chunk, K chunk, P tile
+constexpr int V_TILE_BYTES = 256 * 128;         // 32 KB
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TMEM_COLS = 512;              // S0 [0,128) S1 [128,256) O [256,512)
+
+struct AttnParams {
+  int Tq, Tk, d;
+  int k_chunks, k_last_mmas, s_tiles;
+  int d_chunk, heads;
+  long long o_sb, o_sh, o_st, o_sc;
+  float sm_scale;
+  const float *dq, *zq, *dk, *zk, *dv, *zv, *dpq, *zpq;
+  int p_levels;
+  const int32_t *rq, *rk, *rv;
+  float* out;
+};
+
+struct __align__(8) AttnBarriers {
+  uint64_t qk_full[QK_STAGES], qk_empty[QK_STAGES];
+  uint64_t v_full[V_STAGES], v_empty[V_STAGES];
+  uint64_t s_full[2], s_empty[2];
+  uint64_t p_full[2], p_empty[2];
+  uint64_t o_full;
+  uint32_t tmem_base;
+};
+
+constexpr int ATT_SMEM_BYTES = 1024 + QK_STAGES * 2 * ATT_TILE_BYTES + V_STAGES * V_TILE_BYTES + 2 * ATT_TILE_BYTES + 256;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+             const __grid_constant__ CUtensorMap map_v, AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_q = smem;
+  uint8_t* smem_k = smem_q + QK_STAGES * ATT_TILE_BYTES;
+  uint8_t* smem_v = smem_k + QK_STAGES * ATT_TILE_BYTES;
+  uint8_t* smem_p = smem_v + V_STAGES * V_TILE_BYTES;
+  AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem_p + 2 * ATT_TILE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_M;
+  const int dc = blockIdx.y;
+  const int bh = blockIdx.z;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+    for (int i = 0; i < QK_STAGES; ++i) { mbar_init(&bars->qk_full[i], 1); mbar_init(&bars->qk_empty[i], 1); }
+    for (int i = 0; i < V_STAGES; ++i) { mbar_init(&bars->v_full[i], 1); mbar_init(&bars->v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 4);
+      mbar_init(&bars->p_full[i], 4); mbar_init(&bars->p_empty[i], 1);
+    }
+    mbar_init(&bars->o_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(ATT_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int vs = 0; uint32_t vphase = 0;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int j = 0; j < p.s_tiles; ++j) {
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(&bars->qk_empty[stage], phase ^ 1);
+            mbar_expect_tx(&bars->qk_full[stage], 2 * ATT_TILE_BYTES);
+            tma_load_3d(smem_q + stage * ATT_TILE_BYTES, &map_q, &bars->qk_full[stage], kc * ATT_KB, q0, bh);
+            tma_load_3d(smem_k + stage * ATT_TILE_BYTES, &map_k, &bars->qk_full[stage], kc * ATT_KB, j * ATT_S, bh);
+            if (++stage == QK_STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (pass == 1) {
+            mbar_wait(&bars->v_empty[vs], vphase ^ 1);
+            mbar_expect_tx(&bars->v_full[vs], (uint32_t)p.d_chunk * ATT_KB);
+            tma_load_3d(smem_v + vs * V_TILE_BYTES, &map_v, &bars->v_full[vs], j * ATT_S, dc * p.d_chunk, bh);
+            if (++vs == V_STAGES) { vs = 0; vphase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_i8(ATT_S, 0, 0);
+      const uint32_t idesc_o = make_idesc_i8(p.d_chunk, 0, 0);
+      const uint32_t tmem_o = tmem_base + 256;
+      int stage = 0; uint32_t phase = 0;
+      int vs = 0; uint32_t vphase = 0;
+      auto issue_pv = [&](int jj) {
+        const int pb = jj & 1;
+        mbar_wait(&bars->p_full[pb], (uint32_t)((jj >> 1) & 1));
+        mbar_wait(&bars->v_full[vs], vphase);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(smem_u32(smem_p + pb * ATT_TILE_BYTES));
+        const uint64_t bdesc = make_smem_desc(smem_u32(smem_v + vs * V_TILE_BYTES));
+        for (int k = 0; k < ATT_S / UMMA_K; ++k)
+          umma_i8(tmem_o, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)), idesc_o, (jj | k) ? 1u : 0u);
+        umma_commit(&bars->v_empty[vs]);
+        umma_commit(&bars->p_empty[pb]);
+        if (++vs == V_STAGES) { vs = 0; vphase ^= 1; }
+      };
+      int g = 0;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int j = 0; j < p.s_tiles; ++j, ++g) {
+          const int sb = g & 1;
+          mbar_wait(&bars->s_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t tmem_s = tmem_base + (uint32_t)sb * ATT_S;
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            const int nmma = (kc == p.k_chunks - 1) ? p.k_last_mmas : ATT_KB / UMMA_K;
+            mbar_wait(&bars->qk_full[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = make_smem_desc(smem_u32(smem_q + stage * ATT_TILE_BYTES));
+            const uint64_t bdesc = make_smem_desc(smem_u32(smem_k + stage * ATT_TILE_BYTES));
+            for (int k = 0; k < nmma; ++k)
+              umma_i8(tmem_s, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)), idesc_s, (kc | k) ? 1u : 0u);
+            umma_commit(&bars->qk_empty[stage]);
+            if (++stage == QK_STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&bars->s_full[sb]);
+          if (pass == 1 && j > 0) issue_pv(j - 1);
+        }
+      }
+      issue_pv(p.s_tiles - 1);
+      umma_commit(&bars->o_full);
+    }
+  } else {
+    // ===================== softmax + epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int t = q0 + r;
+    const bool row_ok = t < p.Tq;
+    const int zq = (int)__ldg(p.zq), zk = (int)__ldg(p.zk);
+    const float alpha = __ldg(p.dq) * __ldg(p.dk) * p.sm_scale;
+    const int32_t* rk = p.rk + (size_t)bh * p.Tk;
+    const int row_const = p.d * zq * zk - (row_ok ? zk * __ldg(p.rq + (size_t)bh * p.Tq + t) : 0);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+    float m = -INFINITY, l = 0.f;
+    int g = 0;
+    // ---- pass 1: row max and sum ----
+    for (int j = 0; j < p.s_tiles; ++j, ++g) {
+      const int sb = g & 1;
+      mbar_wait(&bars->s_full[sb], (uint32_t)((g >> 1) & 1));
+      tc_fence_after();
+      for (int c0 = 0; c0 < ATT_S; c0 += 32) {
+        const int s0 = j * ATT_S + c0;
+        if (s0 >= p.Tk) break;
+        uint32_t raw[32];
+        tmem_ld32(lane_addr + (uint32_t)sb * ATT_S + c0, raw);
+        tmem_ld_wait();
+        float x[32];
+        float cmax = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int s = s0 + i;
+          if (s < p.Tk) {
+            x[i] = (float)((int)raw[i] + row_const - zq * __ldg(rk + s)) * alpha;
+            cmax = fmaxf(cmax, x[i]);
+          } else {
+            x[i] = -INFINITY;
+          }
+        }
+        const float m_new = fmaxf(m, cmax);
+        float add = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) add += expf(x[i] - m_new);
+        l = l * expf(m - m_new) + add;
+        m = m_new;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
+    }
+    // ---- pass 2: normalised probabilities -> codes -> smem (A operand of the P.V MMA) ----
+    const float dpq = __ldg(p.dpq), zpq = __ldg(p.zpq);
+    const float qmax = (float)(p.p_levels - 1);
+    int rp = 0;
+    for (int j = 0; j < p.s_tiles; ++j, ++g) {
+      const int sb = g & 1, pb = j & 1;
+      mbar_wait(&bars->s_full[sb], (uint32_t)((g >> 1) & 1));
+      mbar_wait(&bars->p_empty[pb], (uint32_t)(((j >> 1) & 1) ^ 1));
+      tc_fence_after();
+      uint8_t* prow = smem_p + pb * ATT_TILE_BYTES + r * 128;
+      for (int c0 = 0; c0 < ATT_S; c0 += 32) {
+        const int s0 = j * ATT_S + c0;
+        uint32_t packed[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (s0 < p.Tk) {
+          uint32_t raw[32];
+          tmem_ld32(lane_addr + (uint32_t)sb * ATT_S + c0, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int s = s0 + i;
+            uint32_t code = 0;
+            if (s < p.Tk) {
+              const float x = (float)((int)raw[i] + row_const - zq * __ldg(rk + s)) * alpha;
+              const float prob = expf(x - m) / l;
+              code = (uint32_t)fminf(fmaxf(rintf(prob / dpq) + zpq, 0.f), qmax);
+              rp += (int)code;
+            }
+            packed[i >> 2] |= code << (8 * (i & 3));
+          }
+        }
+        const int chunk = c0 >> 4;  // two 16-byte chunks per 32 columns, XOR-swizzled by the row (SWIZZLE_128B)
+        *reinterpret_cast<uint4*>(prow + (((chunk) ^ (r & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        *reinterpret_cast<uint4*>(prow + (((chunk + 1) ^ (r & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      }
+      fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&bars->p_full[pb]); mbar_arrive(&bars->s_empty[sb]); }
+    }
+    // ---- epilogue: O -> fp32 output ----
+    mbar_wait(&bars->o_full, 0);
+    tc_fence_after();
+    const int zv = (int)__ldg(p.zv), zp_i = (int)zpq;
+    const float oscale = dpq * __ldg(p.dv);
+    const int32_t* rv = p.rv + (size_t)bh * p.d;
+    const int b = bh / p.heads, h = bh - b * p.heads;
+    float* obase = p.out + b * p.o_sb + h * p.o_sh + (long long)t * p.o_st;
+    const int row_o = p.Tk * zp_i * zv - zv * rp;
+    for (int c0 = 0; c0 < p.d_chunk; c0 += 16) {
+      uint32_t raw[16];
+      tmem_ld16(lane_addr + 256 + c0, raw);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c = dc * p.d_chunk + c0 + i;
+          if (c < p.d) obase[(long long)c * p.o_sc] = (float)((int)raw[i] + row_o - zp_i * __ldg(rv + c)) * oscale;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(ATT_TMEM_COLS));
+  }
+}
+
+}  // namespace edadm
+
+using namespace edadm;
+
+// qc, kc: u8 codes [BH][Tq|Tk][dp] (dp % 16 == 0, padded bytes 0); vc: u8 codes [BH][d][Tkp] (Tkp % 16 == 0, padding 0);
+// rq[BH][Tq], rk[BH][Tk]: per-token code sums; rv[BH][d]: per-channel code sums.  Scalars are device pointers.
+// out fp32: element (b, h, t, c) at b*o_sb + h*o_sh + t*o_st + c*o_sc with bh = b*heads + h.
+extern "C" int edadm_qattn_fwd(const uint8_t* qc, const uint8_t* kc, const uint8_t* vc, const int32_t* rq, const int32_t* rk,
+                               const int32_t* rv, int BH, int heads, int Tq, int Tk, int d, int dp, int Tkp,
+                               const float* dq, const float* zq, const float* dk, const float* zk, const float* dv,
+                               const float* zv, const float* dpq, const float* zpq, int p_levels, float sm_scale, float* out,
+                               int64_t o_sb, int64_t o_sh, int64_t o_st, int64_t o_sc, void* stream) {
+  if (!qc || !kc || !vc || !rq || !rk || !rv || !dq || !zq || !dk || !zk || !dv || !zv || !dpq || !zpq || !out)
+    return fail(EDADM_ERR_ARG, "qattn_fwd: null pointer");
+  if (BH < 1 || heads < 1 || (BH % heads) || Tq < 1 || Tk < 1 || d < 1 || dp < d || (dp & 15) || Tkp < Tk || (Tkp & 15) ||
+      p_levels < 2 || p_levels > 256)
+    return fail(EDADM_ERR_ARG, "qattn_fwd: bad sizes BH=%d heads=%d Tq=%d Tk=%d d=%d dp=%d Tkp=%d", BH, heads, Tq, Tk, d, dp, Tkp);
+  if (BH > 65535) return fail(EDADM_ERR_UNSUPPORTED, "qattn_fwd: more than 65535 (batch x heads) per launch");
+  if ((((uintptr_t)qc | (uintptr_t)kc | (uintptr_t)vc) & 15)) return fail(EDADM_ERR_ARG, "qattn_fwd: operands must be 16-byte aligned");
+
+  AttnParams p;
+  p.Tq = Tq; p.Tk = Tk; p.d = d;
+  p.k_chunks = (dp + ATT_KB - 1) / ATT_KB;
+  p.k_last_mmas = (dp - (p.k_chunks - 1) * ATT_KB + UMMA_K - 1) / UMMA_K;
+  p.s_tiles = (Tk + ATT_S - 1) / ATT_S;
+  const int d_chunks = (d + 255) / 256;
+  p.d_chunk = (((d + d_chunks - 1) / d_chunks) + 15) & ~15;
+  p.heads = heads;
+  p.o_sb = o_sb; p.o_sh = o_sh; p.o_st = o_st; p.o_sc = o_sc;
+  p.sm_scale = sm_scale;
+  p.dq = dq; p.zq = zq; p.dk = dk; p.zk = zk; p.dv = dv; p.zv = zv; p.dpq = dpq; p.zpq = zpq;
+  p.p_levels = p_levels;
+  p.rq = rq; p.rk = rk; p.rv = rv; p.out = out;
+
+  CUtensorMap map_q, map_k, map_v;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)dp, (cuuint64_t)Tq, (cuuint64_t)BH};
+    cuuint64_t strides[2] = {(cuuint64_t)dp, (cuuint64_t)Tq * dp};
+    cuuint32_t box[3] = {(cuuint32_t)ATT_KB, (cuuint32_t)ATT_M, 1u};
+    int rc = encode_map(&map_q, qc, 3, dims, strides, box, "attention q codes");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)dp, (cuuint64_t)Tk, (cuuint64_t)BH};
+    cuuint64_t strides[2] = {(cuuint64_t)dp, (cuuint64_t)Tk * dp};
+    cuuint32_t box[3] = {(cuuint32_t)ATT_KB, (cuuint32_t)ATT_S, 1u};
+    int rc = encode_map(&map_k, kc, 3, dims, strides, box, "attention k codes");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Tkp, (cuuint64_t)d, (cuuint64_t)BH};
+    cuuint64_t strides[2] = {(cuuint64_t)Tkp, (cuuint64_t)d * Tkp};
+    cuuint32_t box[3] = {(cuuint32_t)ATT_S, (cuuint32_t)p.d_chunk, 1u};
+    int rc = encode_map(&map_v, vc, 3, dims, strides, box, "attention v codes");
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(qattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(EDADM_ERR_CUDA, "qattn_fwd: cannot opt in to %d B shared memory: %s", ATT_SMEM_BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((Tq + ATT_M - 1) / ATT_M, d_chunks, BH);
+  qattn_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(map_q, map_k, map_v, p);
+  return check_launch("qattn_fwd");
+}

@@ -28,12 +28,14 @@ _SIGNATURES = {
     "edadm_round_reg": (c_int, [P, c_int64, c_float, c_float, P, P, c_int, P, P]),
     "edadm_lp_loss_fwd": (c_int, [P, P, c_int64, c_float, c_float, P, P, P]),
     "edadm_lp_loss_bwd": (c_int, [P, P, c_int64, c_float, c_float, P, P, P]),
-    "edadm_act_quant_nhwc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P, c_int, P]),
-    "edadm_act_quant_rows": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, c_int, c_int, P, P, c_int, P]),
+    "edadm_act_quant_nhwc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P, c_int, c_float, P]),
+    "edadm_act_quant_rows": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, c_int, c_int, P, P, c_int, c_float, P]),
     "edadm_im2col_u8": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "edadm_conv_rowsum": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "edadm_pack_weight": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "edadm_qgemm_i8": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
+    "edadm_qattn_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int,
+                                c_float, P, c_int64, c_int64, c_int64, c_int64, P]),
 }
 
 _lib = None

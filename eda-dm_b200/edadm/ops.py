@@ -311,11 +311,12 @@ def pack_weight(w, delta, zero_point, n_levels, alpha=None, c_begin=0, c_end=Non
 class ActQuant:
     """(delta, zero_point, n_levels) of the one or two (split) activation quantizers of a QuantModule."""
 
-    __slots__ = ("delta0", "zp0", "levels0", "split", "delta1", "zp1", "levels1")
+    __slots__ = ("delta0", "zp0", "levels0", "split", "delta1", "zp1", "levels1", "prescale")
 
-    def __init__(self, delta0, zp0, levels0, split=0, delta1=None, zp1=None, levels1=0):
+    def __init__(self, delta0, zp0, levels0, split=0, delta1=None, zp1=None, levels1=0, prescale=1.0):
         self.delta0, self.zp0, self.levels0 = delta0, zp0, int(levels0)
         self.split, self.delta1, self.zp1, self.levels1 = int(split), delta1, zp1, int(levels1)
+        self.prescale = float(prescale)
 
 
 def act_quant_nhwc(x, aq: ActQuant, pad: int, want_chsum=False):
@@ -331,7 +332,7 @@ def act_quant_nhwc(x, aq: ActQuant, pad: int, want_chsum=False):
     d1 = _qparam(aq.delta1, dev) if aq.split else None
     z1 = _qparam(aq.zp1, dev) if aq.split else None
     lib.act_quant_nhwc(x.data_ptr(), q.data_ptr(), _ptr(chsum), B, C, H, W, Cp, pad, d0.data_ptr(), z0.data_ptr(),
-                       aq.levels0, aq.split, _ptr(d1), _ptr(z1), aq.levels1, _stream())
+                       aq.levels0, aq.split, _ptr(d1), _ptr(z1), aq.levels1, aq.prescale, _stream())
     return q, chsum
 
 
@@ -348,7 +349,7 @@ def act_quant_rows(x2d, aq: ActQuant, want_rowsum=False):
     d1 = _qparam(aq.delta1, dev) if aq.split else None
     z1 = _qparam(aq.zp1, dev) if aq.split else None
     lib.act_quant_rows(x2d.data_ptr(), q.data_ptr(), _ptr(rowsum), M, K, Kp, d0.data_ptr(), z0.data_ptr(), aq.levels0,
-                       aq.split, _ptr(d1), _ptr(z1), aq.levels1, _stream())
+                       aq.split, _ptr(d1), _ptr(z1), aq.levels1, aq.prescale, _stream())
     return q, rowsum
 
 
@@ -395,3 +396,67 @@ def qgemm_i8(q, pw: PackedWeight, delta_a, zp_a, out, out_hw, bias=None, rowsum=
         m = B * (Hp - R + 1) * (Wp - S + 1)
         prof.append((ev0, ev1, m * pw.N * pw.C * pw.R * pw.S))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K5  fused quantized attention
+# ------------------------------------------------------------------------------------------------
+class AttnQuant:
+    """(delta, zero_point, n_levels) of the q, k, v and softmax quantizers of one attention site."""
+
+    __slots__ = ("q", "k", "v", "w")
+
+    def __init__(self, q, k, v, w):
+        self.q, self.k, self.v, self.w = q, k, v, w   # each: (delta, zero_point, n_levels)
+
+
+def _codes_token_major_from_bct(x, quant, prescale):
+    """x fp32 [BH, d, T] -> codes [BH, T, dp] + per-token code sums [BH, T]."""
+    BH, d, T = x.shape
+    aq = ActQuant(quant[0], quant[1], quant[2], prescale=prescale)
+    q, chsum = act_quant_nhwc(x.reshape(BH, d, 1, T), aq, 0, want_chsum=True)
+    return q.reshape(BH, T, q.shape[-1]), chsum.reshape(BH, T)
+
+
+def _codes_rows(x2d, quant, prescale=1.0):
+    aq = ActQuant(quant[0], quant[1], quant[2], prescale=prescale)
+    return act_quant_rows(x2d, aq, want_rowsum=True)
+
+
+def qattn(qc, kc, vc, rq, rk, rv, heads, d, Tk, aquant: AttnQuant, sm_scale, out, strides):
+    """qc [BH,Tq,dp], kc [BH,Tk,dp], vc [BH,d,Tkp] u8 codes -> out (fp32, written through `strides` = (sb, sh, st, sc))."""
+    BH, Tq, dp = qc.shape
+    Tkp = vc.shape[-1]
+    dev = qc.device
+    s = [_qparam(v, dev) for v in (aquant.q[0], aquant.q[1], aquant.k[0], aquant.k[1], aquant.v[0], aquant.v[1],
+                                   aquant.w[0], aquant.w[1])]
+    lib.qattn_fwd(qc.data_ptr(), kc.data_ptr(), vc.data_ptr(), rq.data_ptr(), rk.data_ptr(), rv.data_ptr(), BH, int(heads),
+                  Tq, int(Tk), int(d), dp, Tkp, *[t.data_ptr() for t in s], int(aquant.w[2]), float(sm_scale), out.data_ptr(),
+                  int(strides[0]), int(strides[1]), int(strides[2]), int(strides[3]), _stream())
+    return out
+
+
+def qattn_bct(q, k, v, aquant: AttnQuant, prescale, sm_scale):
+    """q, k, v fp32 [BH, d, T] (channel-major; DDIM AttnBlock and the LDM legacy attention) -> [BH, d, T]."""
+    _need_cuda(q, k, v)
+    BH, d, T = q.shape
+    qc, rq = _codes_token_major_from_bct(_f32c(q), aquant.q, prescale)
+    kc, rk = _codes_token_major_from_bct(_f32c(k), aquant.k, prescale)
+    vc, rv = _codes_rows(_f32c(v).reshape(BH * d, T), aquant.v)
+    out = torch.empty((BH, d, T), dtype=torch.float32, device=q.device)
+    return qattn(qc, kc, vc.reshape(BH, d, -1), rq, rk, rv.reshape(BH, d), 1, d, T, aquant, sm_scale, out, (d * T, 0, 1, T))
+
+
+def qattn_bnd(q, k, v, heads, aquant: AttnQuant, sm_scale):
+    """q [BH, Tq, d], k, v [BH, Tk, d] fp32 (token-major; cross_attn_forward) -> [B, Tq, heads*d] (heads merged)."""
+    _need_cuda(q, k, v)
+    BH, Tq, d = q.shape
+    Tk = k.shape[1]
+    qc, rq = _codes_rows(_f32c(q).reshape(BH * Tq, d), aquant.q)
+    kc, rk = _codes_rows(_f32c(k).reshape(BH * Tk, d), aquant.k)
+    aqv = ActQuant(aquant.v[0], aquant.v[1], aquant.v[2])
+    vc, rv = act_quant_nhwc(_f32c(v).reshape(BH, Tk, 1, d), aqv, 0, want_chsum=True)   # "channels" = keys -> [BH,1,d,Tkp]
+    B = BH // heads
+    out = torch.empty((B, Tq, heads * d), dtype=torch.float32, device=q.device)
+    return qattn(qc.reshape(BH, Tq, -1), kc.reshape(BH, Tk, -1), vc.reshape(BH, d, -1), rq.reshape(BH, Tq), rk.reshape(BH, Tk),
+                 rv.reshape(BH, d), heads, d, Tk, aquant, sm_scale, out, (Tq * heads * d, d, heads * d, 1))

@@ -174,12 +174,12 @@ def cross_attn_forward(self, x, context=None, mask=None):
     if mask is not None:
         raise NotImplementedError("attention masks are not used by any EDA-DM configuration")
     if self.use_act_quant:
-        out = qattn.quantized_attention_bnd(q, k, v, self.scale, self.act_quantizer_q, self.act_quantizer_k,
+        out = qattn.quantized_attention_bnd(q, k, v, h, self.scale, self.act_quantizer_q, self.act_quantizer_k,
                                             self.act_quantizer_v, self.act_quantizer_w)
     else:
         attn = (th.einsum('bid,bjd->bij', q, k) * self.scale).softmax(dim=-1)
-        out = th.einsum('bij,bjd->bid', attn, v)
-    return self.to_out(_zoo_ldm._heads_merge(out, h))
+        out = _zoo_ldm._heads_merge(th.einsum('bij,bjd->bid', attn, v), h)
+    return self.to_out(out)
 
 
 class QuantBasicTransformerBlock(BaseQuantBlock):

@@ -9,6 +9,7 @@ from .quant_block import get_specials, BaseQuantBlock
 from .quant_block import QuantBasicTransformerBlock, QuantResBlock  # noqa: F401
 from .quant_block import QuantQKMatMul, QuantSMVMatMul, QuantAttnBlock
 from .quant_layer import QuantModule, UniformAffineQuantizer, StraightThrough
+from . import attention as qattn
 
 logger = logging.getLogger(__name__)
 
@@ -51,6 +52,9 @@ class QuantModel(nn.Module):
                 setattr(module, name, wrapper(act_quant_params))
             else:
                 setattr(module, name, wrapper(child, act_quant_params))
+        if isinstance(getattr(module, 'qkv_matmul', None), QuantQKMatMul) and \
+                isinstance(getattr(module, 'smv_matmul', None), QuantSMVMatMul) and hasattr(module, 'n_heads'):
+            qattn.patch_legacy_attention(module)   # lets the two matmuls + softmax run as ONE fused kernel
 
     def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
         for m in self.model.modules():

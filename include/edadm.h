@@ -77,13 +77,14 @@ int edadm_lp_loss_bwd(const float* pred, const float* tgt, int64_t n, float p, f
  * act_quant_nhwc: x fp32 [B][C][H][W] -> q [B][H+2pad][W+2pad][Cp]; halo pixels hold the zero-point
  * code (zero padding of F.conv2d on dequantised values == code zp), padded channels hold 0.
  * split != 0: channels >= split use the second quantizer (quant_layer.py:415-419).
- * chsum (nullable): int32 [B][H+2pad][W+2pad] per-pixel sum of codes (for 8-bit weight zero-points). */
+ * chsum (nullable): int32 [B][H+2pad][W+2pad] per-pixel sum of codes (for 8-bit weight zero-points).
+ * prescale: x is multiplied by it (fp32) before quantization (the q*scale of QuantQKMatMul, quant_block.py:130). */
 int edadm_act_quant_nhwc(const float* x, uint8_t* q, int32_t* chsum, int B, int C, int H, int W, int Cp, int pad,
                          const float* delta0, const float* zp0, int n_levels0, int split, const float* delta1,
-                         const float* zp1, int n_levels1, void* stream);
+                         const float* zp1, int n_levels1, float prescale, void* stream);
 int edadm_act_quant_rows(const float* x, uint8_t* q, int32_t* rowsum, int64_t M, int K, int Kp, const float* delta0,
                          const float* zp0, int n_levels0, int split, const float* delta1, const float* zp1,
-                         int n_levels1, void* stream);
+                         int n_levels1, float prescale, void* stream);
 int edadm_im2col_u8(const uint8_t* q, uint8_t* a, int B, int Hp, int Wp, int Cp, int Ho, int Wo, int R, int S,
                     int stride, void* stream);
 int edadm_conv_rowsum(const int32_t* chsum, int32_t* rowsum, int B, int Hp, int Wp, int Ho, int Wo, int R, int S,
@@ -106,6 +107,19 @@ int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_
                    int R, int S, int Cp_w, const float* delta_a, const float* zp_a, const float* delta_w,
                    const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum, const float* bias, float* out,
                    int out_hw, int accumulate, int silu, void* stream);
+
+/* ---- K5: fused quantized attention (tcgen05 kind::i8 for Q.K^T and P.V, softmax + P quantization on chip) ----
+ * Replaces the bmm/einsum - softmax - fake-quant chain of QuantAttnBlock.forward (qdiff/quant_block.py:431-445),
+ * QuantQKMatMul + softmax + QuantSMVMatMul (:128-139, :157-162, openaimodel.py:402-405) and cross_attn_forward
+ * (:214-233).  qc/kc: u8 codes [BH][T][dp] (token-major), vc: u8 codes [BH][d][Tkp] (channel-major), produced by
+ * edadm_act_quant_nhwc / _rows together with the code sums rq[BH][Tq], rk[BH][Tk], rv[BH][d].
+ *   out[b,h,t,c] = dP*dv * sum_s (Pq[t,s]-zP)(v[c,s]-zv),  Pq = clamp(rint(softmax_s(dq*dk*scale*sum_c(q-zq)(k-zk))/dP)+zP)
+ * written at b*o_sb + h*o_sh + t*o_st + c*o_sc (bh = b*heads + h).                                                   */
+int edadm_qattn_fwd(const uint8_t* qc, const uint8_t* kc, const uint8_t* vc, const int32_t* rq, const int32_t* rk,
+                    const int32_t* rv, int BH, int heads, int Tq, int Tk, int d, int dp, int Tkp, const float* dq,
+                    const float* zq, const float* dk, const float* zk, const float* dv, const float* zv, const float* dpq,
+                    const float* zpq, int p_levels, float sm_scale, float* out, int64_t o_sb, int64_t o_sh, int64_t o_st,
+                    int64_t o_sc, void* stream);
 
 #ifdef __cplusplus
 }

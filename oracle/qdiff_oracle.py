@@ -32,7 +32,7 @@ def uaq_codes(x, delta, zero_point, n_levels):
 
 
 # ---- qdiff/quant_layer.py:267-276 (forward body; `keep` replaces rand_like(x) < prob) ---------------
-def uaq_forward(x, delta, zero_point, n_levels, keep=None):
+def uaq_forward(x, delta, zero_point, n_levels, keep=None, **_unused):
     x_int = round_ste(x / delta) + zero_point
     x_quant = torch.clamp(x_int, 0, n_levels - 1)
     x_dequant = (x_quant - zero_point) * delta

@@ -271,3 +271,68 @@ def test_qgemm_conv(cuda, B, C, H, N, k, bits):
     out, ref, exact = _run_qconv(cuda, x, w, bias, bits, k // 2, kind="conv")
     assert _rel_l2(out, exact) < 1e-6
     assert _rel_l2(out, ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+def _attn_quant_params(q, k, v, probs):
+    out = {}
+    for name, t, kw in (("q", q, dict(sym=True)), ("k", k, dict(sym=True)), ("v", v, dict(sym=True)), ("w", probs, dict(sym=False))):
+        d, z, _ = O.init_scale(t, 8, False, running={}, **kw)
+        out[name] = dict(delta=d, zero_point=z, n_levels=256)
+    return out
+
+
+def _to_aquant(cuda, qp):
+    from edadm import ops
+    return ops.AttnQuant(*[(qp[n]["delta"].to(cuda), qp[n]["zero_point"].to(cuda), 256) for n in ("q", "k", "v", "w")])
+
+
+@pytest.mark.parametrize("B,C,H", [(2, 256, 16), (3, 64, 8), (2, 32, 4), (1, 96, 12)])
+def test_qattn_ddim_layout(cuda, B, C, H):
+    """QuantAttnBlock attention core (quant_block.py:431-445): fused kernel vs oracle.  q/k/v codes are bit-exact by
+    construction (same producer kernels as above); the probabilities go through a different-order fp32 softmax so single
+    codes may flip at .5 boundaries -> relative L2 <= 1e-3 on the block output (north_star tolerance)."""
+    from edadm import ops
+    g = torch.Generator().manual_seed(21)
+    q, k, v = (torch.randn(B, C, H, H, generator=g) * s for s in (1.0, 1.2, 0.8))
+    scale = int(C) ** -0.5
+    fp_probs = torch.softmax(torch.bmm(q.reshape(B, C, -1).permute(0, 2, 1), k.reshape(B, C, -1)) * scale, dim=2)
+    qp = _attn_quant_params(q, k, v, fp_probs)
+    ref = O.attn_core_ddim(q, k, v, qp)
+    out = ops.qattn_bct(q.reshape(B, C, -1).to(cuda), k.reshape(B, C, -1).to(cuda), v.reshape(B, C, -1).to(cuda),
+                        _to_aquant(cuda, qp), 1.0, scale)
+    assert _rel_l2(out.cpu().reshape(ref.shape), ref) < 1e-3
+
+
+@pytest.mark.parametrize("B,heads,ch,T", [(2, 8, 24, 1024), (2, 2, 16, 64), (1, 4, 48, 256), (3, 7, 32, 100), (2, 8, 96, 16)])
+def test_qattn_ldm_legacy_layout(cuda, B, heads, ch, T):
+    from edadm import ops
+    g = torch.Generator().manual_seed(22)
+    qkv = torch.randn(B, heads * 3 * ch, T, generator=g)
+    q, k, v = qkv.reshape(B * heads, ch * 3, T).split(ch, dim=1)
+    scale = 1 / (ch ** 0.25)
+    fp_probs = torch.softmax(torch.einsum("bct,bcs->bts", q * scale, k * scale), -1)
+    qp = _attn_quant_params(q * scale, k * scale, v, fp_probs)
+    ref = O.attn_core_ldm(qkv, heads, qp)
+    out = ops.qattn_bct(q.to(cuda), k.to(cuda), v.to(cuda), _to_aquant(cuda, qp), scale, 1.0)
+    assert _rel_l2(out.cpu().reshape(ref.shape), ref) < 1e-3
+
+
+@pytest.mark.parametrize("B,heads,d,Tq,Tk", [(2, 1, 384, 256, 256), (2, 8, 40, 128, 77), (1, 1, 576, 64, 1), (2, 8, 80, 300, 300),
+                                             (1, 1, 960, 64, 64)])
+def test_qattn_cross_layout(cuda, B, heads, d, Tq, Tk):
+    from edadm import ops
+    g = torch.Generator().manual_seed(23)
+    q = torch.randn(B, Tq, heads * d, generator=g)
+    k = torch.randn(B, Tk, heads * d, generator=g)
+    v = torch.randn(B, Tk, heads * d, generator=g)
+    scale = d ** -0.5
+
+    def sp(t):
+        return t.reshape(t.shape[0], t.shape[1], heads, d).permute(0, 2, 1, 3).reshape(t.shape[0] * heads, t.shape[1], d)
+    fp_probs = (torch.einsum("bid,bjd->bij", sp(q), sp(k)) * scale).softmax(-1)
+    qp = _attn_quant_params(sp(q), sp(k), sp(v), fp_probs)
+    ref = O.attn_core_cross(q, k, v, heads, scale, qp)
+    out = ops.qattn_bnd(sp(q).contiguous().to(cuda), sp(k).contiguous().to(cuda), sp(v).contiguous().to(cuda), heads,
+                        _to_aquant(cuda, qp), scale)
+    assert _rel_l2(out.cpu(), ref) < 1e-3

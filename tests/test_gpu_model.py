@@ -139,7 +139,7 @@ def test_ddim_tiny_scale_search_on_gpu(cuda):
         y = qnn(x[:4], t[:4])
     table = H.qtable(g)
     named = dict(qnn.named_modules())
-    n_w = n_a_exact = 0
+    n_w = n_a_exact = n_a = n_a_close = 0
     for name, (d, z, bits) in table.items():
         q = named[name]
         ours_d, ours_z = q.delta.detach().cpu().reshape(-1), q.zero_point.cpu().reshape(-1)
@@ -150,11 +150,14 @@ def test_ddim_tiny_scale_search_on_gpu(cuda):
             n_w += 1
         else:
             # activations of later layers already carry cross-platform code flips (chaotic regime, see the end-to-end
-            # test) so the argmin may move by a grid step (1 %) or a few: 6 % on delta, +-1 on zero-point
-            assert torch.allclose(ours_d, d.reshape(-1), rtol=6e-2), name
+            # test) so the argmin may move by a grid step (1 %) or a few: all within 15 %, 80 % within 2 %, +-1 on zero-point
+            assert torch.allclose(ours_d, d.reshape(-1), rtol=1.5e-1), name
             assert float((ours_z - z.reshape(-1)).abs().max()) <= 1.0, name
+            n_a += 1
+            n_a_close += int(torch.allclose(ours_d, d.reshape(-1), rtol=2e-2))
             n_a_exact += int(torch.allclose(ours_d, d.reshape(-1), rtol=1e-6) and torch.equal(ours_z, z.reshape(-1)))
     assert n_w >= 50
+    assert n_a_close >= 0.8 * n_a, (n_a_close, n_a)
     # the quantizers in front of the first code flip agree exactly
     for name in ("model.temb.dense.0.act_quantizer", "model.temb.dense.1.act_quantizer", "model.conv_in.act_quantizer",
                  "model.down.0.block.0.conv1.act_quantizer"):
