@@ -12,10 +12,16 @@
 //
 // Zero-points are folded with the code sums (rq, rk, rv, and the running row sum of Pq), so operands stay raw u8.
 // One CTA = 128 queries x one chunk (<=256) of the head dim of one (batch, head).  Warp roles: 0 TMA producer,
-// 1 MMA issuer, 2..5 softmax + epilogue (thread == query row == TMEM lane).
+// 1 MMA issuer, 2..9 softmax + epilogue (two threads per query row == TMEM lane, 64 key columns each).
 #include "tc05.cuh"
 
 namespace edadm {
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 constexpr int ATT_M = 128;
 constexpr int ATT_S = 128;
@@ -24,7 +30,7 @@ constexpr int QK_STAGES = 3;
 constexpr int V_STAGES = 2;
 constexpr int ATT_TILE_BYTES = 128 * 128;       // 16 KB: Q chunk, K chunk, P tile
 constexpr int V_TILE_BYTES = 256 * 128;         // 32 KB
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;            // TMA warp + MMA warp + 8 softmax warps
 constexpr int ATT_TMEM_COLS = 512;              // S0 [0,128) S1 [128,256) O [256,512)
 
 struct AttnParams {
@@ -61,6 +67,9 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   uint8_t* smem_p = smem_v + V_STAGES * V_TILE_BYTES;
   AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem_p + 2 * ATT_TILE_BYTES);
 
+  __shared__ int colint[2][ATT_S];          // zq * (code sum of key s) for the S tile in each TMEM buffer
+  __shared__ float stat_m[2][ATT_M], stat_l[2][ATT_M];
+  __shared__ int stat_rp[2][ATT_M];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * ATT_M;
   const int dc = blockIdx.y;
@@ -71,8 +80,8 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     for (int i = 0; i < QK_STAGES; ++i) { mbar_init(&bars->qk_full[i], 1); mbar_init(&bars->qk_empty[i], 1); }
     for (int i = 0; i < V_STAGES; ++i) { mbar_init(&bars->v_full[i], 1); mbar_init(&bars->v_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 4);
-      mbar_init(&bars->p_full[i], 4); mbar_init(&bars->p_empty[i], 1);
+      mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 8);
+      mbar_init(&bars->p_full[i], 8); mbar_init(&bars->p_empty[i], 1);
     }
     mbar_init(&bars->o_full, 1);
     fence_barrier_init();
@@ -157,64 +166,86 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       umma_commit(&bars->o_full);
     }
   } else {
-    // ===================== softmax + epilogue (warps 2..5) =====================
+    // ===================== softmax + epilogue (warps 2..9) =====================
+    // Two threads per query row: warps w and w+4 share a TMEM lane quarter and split every 128-key tile into two
+    // halves of 64 columns.  Row statistics and the code row-sum are merged through shared memory.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const int t = q0 + r;
     const bool row_ok = t < p.Tq;
+    const int st = threadIdx.x - 64;            // 0..255 among the softmax threads
     const int zq = (int)__ldg(p.zq), zk = (int)__ldg(p.zk);
     const float alpha = __ldg(p.dq) * __ldg(p.dk) * p.sm_scale;
+    const float alpha2 = alpha * 1.4426950408889634f;   // to the base-2 exponent domain
     const int32_t* rk = p.rk + (size_t)bh * p.Tk;
     const int row_const = p.d * zq * zk - (row_ok ? zk * __ldg(p.rq + (size_t)bh * p.Tq + t) : 0);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int col_base = half * 64;
 
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f;     // m in units of x = S*alpha (natural domain), l = sum 2^((x-m)*log2e)
     int g = 0;
     // ---- pass 1: row max and sum ----
     for (int j = 0; j < p.s_tiles; ++j, ++g) {
       const int sb = g & 1;
+      if (st < ATT_S) { const int s = j * ATT_S + st; colint[sb][st] = s < p.Tk ? zq * __ldg(rk + s) : 0; }
       mbar_wait(&bars->s_full[sb], (uint32_t)((g >> 1) & 1));
       tc_fence_after();
-      for (int c0 = 0; c0 < ATT_S; c0 += 32) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = col_base + cc * 32;
         const int s0 = j * ATT_S + c0;
-        if (s0 >= p.Tk) break;
-        uint32_t raw[32];
-        tmem_ld32(lane_addr + (uint32_t)sb * ATT_S + c0, raw);
-        tmem_ld_wait();
-        float x[32];
-        float cmax = -INFINITY;
+        if (s0 < p.Tk) {
+          uint32_t raw[32];
+          tmem_ld32(lane_addr + (uint32_t)sb * ATT_S + c0, raw);
+          tmem_ld_wait();
+          float x[32];
+          float cmax = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int s = s0 + i;
-          if (s < p.Tk) {
-            x[i] = (float)((int)raw[i] + row_const - zq * __ldg(rk + s)) * alpha;
+          for (int i = 0; i < 32; ++i) {
+            x[i] = (s0 + i < p.Tk) ? (float)((int)raw[i] + row_const - colint[sb][c0 + i]) : -INFINITY;
             cmax = fmaxf(cmax, x[i]);
-          } else {
-            x[i] = -INFINITY;
           }
-        }
-        const float m_new = fmaxf(m, cmax);
-        float add = 0.f;
+          const float m_new = fmaxf(m, cmax * alpha);
+          const float mb = m_new * 1.4426950408889634f;
+          float add = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) add += expf(x[i] - m_new);
-        l = l * expf(m - m_new) + add;
-        m = m_new;
+          for (int i = 0; i < 32; ++i) add += ex2_approx(fmaf(x[i], alpha2, -mb));
+          l = l * ex2_approx((m - m_new) * 1.4426950408889634f) + add;
+          m = m_new;
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
     }
+    // merge the two column halves of every row
+    stat_m[half][r] = m; stat_l[half][r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    {
+      const float mo = stat_m[half ^ 1][r], lo = stat_l[half ^ 1][r];
+      const float mm = fmaxf(m, mo);
+      l = l * ex2_approx((m - mm) * 1.4426950408889634f) + lo * ex2_approx((mo - mm) * 1.4426950408889634f);
+      m = mm;
+    }
     // ---- pass 2: normalised probabilities -> codes -> smem (A operand of the P.V MMA) ----
     const float dpq = __ldg(p.dpq), zpq = __ldg(p.zpq);
     const float qmax = (float)(p.p_levels - 1);
+    const float kq = (1.0f / l) / dpq;            // code = rint(2^((x-m)log2e) * kq) + zP
+    const float mb = m * 1.4426950408889634f;
     int rp = 0;
     for (int j = 0; j < p.s_tiles; ++j, ++g) {
       const int sb = g & 1, pb = j & 1;
+      if (st < ATT_S) { const int s = j * ATT_S + st; colint[sb][st] = s < p.Tk ? zq * __ldg(rk + s) : 0; }
       mbar_wait(&bars->s_full[sb], (uint32_t)((g >> 1) & 1));
       mbar_wait(&bars->p_empty[pb], (uint32_t)(((j >> 1) & 1) ^ 1));
       tc_fence_after();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       uint8_t* prow = smem_p + pb * ATT_TILE_BYTES + r * 128;
-      for (int c0 = 0; c0 < ATT_S; c0 += 32) {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = col_base + cc * 32;
         const int s0 = j * ATT_S + c0;
         uint32_t packed[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (s0 < p.Tk) {
@@ -223,14 +254,11 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int s = s0 + i;
-            uint32_t code = 0;
-            if (s < p.Tk) {
-              const float x = (float)((int)raw[i] + row_const - zq * __ldg(rk + s)) * alpha;
-              const float prob = expf(x - m) / l;
-              code = (uint32_t)fminf(fmaxf(rintf(prob / dpq) + zpq, 0.f), qmax);
-              rp += (int)code;
-            }
+            const float x = (float)((int)raw[i] + row_const - colint[sb][c0 + i]);
+            const float e = ex2_approx(fmaf(x, alpha2, -mb));
+            uint32_t code = (uint32_t)fminf(fmaxf(rintf(e * kq) + zpq, 0.f), qmax);
+            code = (s0 + i < p.Tk) ? code : 0u;
+            rp += (int)code;
             packed[i >> 2] |= code << (8 * (i & 3));
           }
         }
@@ -243,7 +271,10 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) { mbar_arrive(&bars->p_full[pb]); mbar_arrive(&bars->s_empty[sb]); }
     }
-    // ---- epilogue: O -> fp32 output ----
+    // ---- epilogue: O -> fp32 output (the two threads of a row take alternate 16-column groups) ----
+    stat_rp[half][r] = rp;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    rp += stat_rp[half ^ 1][r];
     mbar_wait(&bars->o_full, 0);
     tc_fence_after();
     const int zv = (int)__ldg(p.zv), zp_i = (int)zpq;
@@ -252,7 +283,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     const int b = bh / p.heads, h = bh - b * p.heads;
     float* obase = p.out + b * p.o_sb + h * p.o_sh + (long long)t * p.o_st;
     const int row_o = p.Tk * zp_i * zv - zv * rp;
-    for (int c0 = 0; c0 < p.d_chunk; c0 += 16) {
+    for (int c0 = half * 16; c0 < p.d_chunk; c0 += 32) {
       uint32_t raw[16];
       tmem_ld16(lane_addr + 256 + c0, raw);
       tmem_ld_wait();

@@ -175,7 +175,7 @@ def test_scale_search_unit_vectors_on_gpu(cuda):
     y0 = q(T(u["act_x0"]).to(cuda))
     y1 = q(T(u["act_x1"]).to(cuda))
     assert np.array_equal(q.delta.detach().cpu().numpy(), u["act_delta"]) and np.array_equal(q.zero_point.cpu().numpy(), u["act_zp"])
-    assert np.array_equal(y0.cpu().numpy(), u["act_y0"]) and np.array_equal(y1.detach().cpu().numpy(), u["act_y1"])
+    assert np.array_equal(y0.detach().cpu().numpy(), u["act_y0"]) and np.array_equal(y1.detach().cpu().numpy(), u["act_y1"])
     pw = dict(H.AQ); pw.update(symmetric=False, always_zero=True)
     q = UniformAffineQuantizer(**pw)
     yp = q(T(u["pos_x"]).to(cuda))
