@@ -30,11 +30,14 @@ class UnitWalker:
             logger.info('Reconstruction for block %s', name)
             self.on_block(module)
 
-    def _unrolled_level(self, level, n_blocks, resample_attr):
-        for i in range(n_blocks):
+    def _unrolled_level(self, level, resample_attr):
+        # the reference spells this out for 2 (down) / 3 (up) block+attention pairs; any count works the same way
+        for i in range(len(level.block)):
             self.on_block(level.block[i])
-            self.on_block(level.attn[i])
-        self.on_layer(getattr(level, resample_attr).conv)
+            if i < len(level.attn):
+                self.on_block(level.attn[i])
+        if hasattr(level, resample_attr):
+            self.on_layer(getattr(level, resample_attr).conv)
 
     def walk(self, parent: nn.Module):
         for name, module in parent.named_children():
@@ -42,7 +45,7 @@ class UnitWalker:
                 self._down_seen = 'down'
             if self._down_seen == 'down' and name == '1' and not isinstance(module, BaseQuantBlock):
                 logger.info('reconstruction for down 1 modulelist')
-                self._unrolled_level(module, 2, 'downsample')
+                self._unrolled_level(module, 'downsample')
                 self._down_seen = 'over'
             elif isinstance(module, (QuantModule, BaseQuantBlock)):
                 self._unit(name, module)
@@ -55,7 +58,7 @@ class UnitWalker:
         for name, module in reversed(list(parent.named_children())):
             if name == '1':
                 logger.info('reconstruction for up 1 modulelist')
-                self._unrolled_level(module, 3, 'upsample')
+                self._unrolled_level(module, 'upsample')
             elif isinstance(module, (QuantModule, BaseQuantBlock)):
                 self._unit(name, module)
             else:

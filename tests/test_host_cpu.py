@@ -1,0 +1,222 @@
+"""CPU tests (-m "not gpu"): C-ABI library loads and exports every symbol include/edadm.h declares, host logic of the
+qdiff drop-in (model rewrite, state switching, search == oracle, no-CPU-fallback behaviour), world_size-2 gloo tests of
+the data-parallel plumbing."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from edadm import native
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("edadm_build", os.path.join(ROOT, "eda-dm_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    mod.build_lib()
+    handle = native.load_library()
+    header = open(os.path.join(ROOT, "include", "edadm.h")).read()
+    declared = set(re.findall(r"\b(edadm_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in include/edadm.h but not exported"
+    assert declared == set(native.exported_symbols()), declared ^ set(native.exported_symbols())
+    assert handle.edadm_abi_version() == 1
+    assert handle.edadm_reduce_slots() > 0
+
+
+def test_argument_errors_are_reported_not_crashing():
+    from edadm import native
+    lib = native.lib
+    with pytest.raises(native.EdadmError, match="null pointer"):
+        lib.uaq_fwd(None, None, None, None, None, 16, 1, 1, 256, None, 1.0, 0, 0, None)
+
+
+def test_no_cpu_fallback_for_quantized_path():
+    from qdiff.quant_layer import UniformAffineQuantizer, QuantModule
+    from edadm.native import EdadmError
+    q = UniformAffineQuantizer(**H.AQ)
+    with pytest.raises(EdadmError):
+        q(torch.randn(4, 4))
+    m = QuantModule(torch.nn.Linear(8, 8), H.WQ, H.AQ)
+    assert m(torch.randn(2, 8)).shape == (2, 8)         # FP branch works on CPU
+    m.set_quant_state(True, True)
+    with pytest.raises(EdadmError):
+        m(torch.randn(2, 8))
+
+
+def _qmodel(model):
+    from qdiff import QuantModel
+    qnn = QuantModel(model, H.WQ, H.AQ, sm_abit=8)
+    qnn.set_first_last_layer_to_8bit()
+    qnn.disable_network_output_quantization()
+    return qnn
+
+
+def test_quant_model_rewrite_ddim():
+    from qdiff.quant_layer import QuantModule, UniformAffineQuantizer
+    from qdiff.quant_block import QuantResnetBlock, QuantAttnBlock, BaseQuantBlock
+    g = H.load("ddim_tiny.npz")
+    model = H.ddim_tiny_model()
+    model.load_state_dict(H.state_dict(g))
+    qnn = _qmodel(model)
+    mods = dict(qnn.named_modules())
+    assert isinstance(mods["model.down.0.block.0"], QuantResnetBlock)
+    assert isinstance(mods["model.down.1.attn.0"], QuantAttnBlock)
+    assert sum(isinstance(m, QuantModule) for m in mods.values()) == 51
+    # first / last weight quantizers 8 bit (the "first" one is the time-embedding MLP)
+    assert mods["model.temb.dense.0"].weight_quantizer.n_bits == 8
+    assert mods["model.conv_out"].weight_quantizer.n_bits == 8
+    assert mods["model.conv_in"].weight_quantizer.n_bits == 4
+    assert mods["model.conv_out"].disable_act_quant is True
+    # FP forward equals the reference's FP output, state switching toggles every unit
+    x, t = torch.from_numpy(g["x"])[:4], torch.from_numpy(g["t"])[:4]
+    with torch.no_grad():
+        assert H.rel_l2(qnn(x, t), torch.from_numpy(g["y_fp"])) < 1e-6
+    qnn.set_quant_state(True, False)
+    assert all(m.use_weight_quant and not m.use_act_quant for m in mods.values() if isinstance(m, (QuantModule, BaseQuantBlock)))
+    # golden quantizer names exist in the product model (after split twins are created by a split forward)
+    qnn.set_quant_state(False, False)
+    qnn.model.config.split_shortcut = True
+    with torch.no_grad():
+        qnn(x, t)
+    mods = dict(qnn.named_modules())
+    for name in H.qtable(g):
+        assert isinstance(mods[name], UniformAffineQuantizer), name
+
+
+@pytest.mark.parametrize("name", ["ldm_tiny.npz", "ldm_tiny_b.npz", "ldm_xattn_tiny.npz"])
+def test_quant_model_rewrite_ldm(name):
+    from qdiff.quant_layer import UniformAffineQuantizer
+    from qdiff.quant_block import QuantResBlock, QuantQKMatMul, QuantSMVMatMul, QuantBasicTransformerBlock
+    g = H.load(name)
+    model = H.ldm_model(name)
+    model.load_state_dict(H.state_dict(g))
+    qnn = _qmodel(model)
+    kinds = {type(m) for m in qnn.modules()}
+    assert QuantResBlock in kinds
+    assert (QuantBasicTransformerBlock in kinds) == ("xattn" in name)
+    if "xattn" not in name:
+        assert QuantQKMatMul in kinds and QuantSMVMatMul in kinds
+    args = [torch.from_numpy(g["x"])[:4], torch.from_numpy(g["t"])[:4]] + ([torch.from_numpy(g["ctx"])[:4]] if "ctx" in g.files else [])
+    qnn.model.split_shortcut = True
+    with torch.no_grad():
+        assert H.rel_l2(qnn(*args), torch.from_numpy(g["y_fp"])) < 1e-6
+    mods = dict(qnn.named_modules())
+    for qname in H.qtable(g):
+        assert isinstance(mods[qname], UniformAffineQuantizer), qname
+
+
+def test_scale_search_equals_oracle_on_cpu():
+    """The product's range search (pure tensor ops, device independent) == the oracle's restatement == the reference."""
+    from qdiff.quant_layer import UniformAffineQuantizer
+    u = H.load("unit.npz")
+    q = UniformAffineQuantizer(**H.AQ)
+    for key in ("act_x0", "act_x1"):
+        d, z = q.init_quantization_scale_1(torch.from_numpy(u[key]), False)
+    assert torch.equal(d, torch.from_numpy(u["act_delta"])) and torch.equal(z, torch.from_numpy(u["act_zp"]))
+    for bits in (4, 8):
+        p = dict(H.WQ); p["n_bits"] = bits
+        q = UniformAffineQuantizer(**p)
+        d, z = q.init_quantization_scale_1(torch.from_numpy(u["w"]), True)
+        assert torch.equal(d, torch.from_numpy(u[f"w{bits}_delta"])) and torch.equal(z, torch.from_numpy(u[f"w{bits}_zp"]))
+    # asymmetric two-sided input -> 2-D search; compare with the reference-style brute force on a tiny tensor
+    p = dict(H.AQ); p.update(symmetric=False, n_bits=3, leaf_param=False)
+    q = UniformAffineQuantizer(**p)
+    x = torch.tensor([-0.3, -0.1, 0.0, 0.2, 0.5, 0.9, 1.4])
+    d, z = q.init_quantization_scale_1(x, False)
+    assert 0.0 < float(d) < 1.0 and 0.0 <= float(z) <= 7.0
+
+
+def test_implicit_tiling_rule_matches_c_side():
+    from qdiff.quant_layer import _implicit_tiling_ok
+    assert _implicit_tiling_ok(100, 32, 32) and _implicit_tiling_ok(3, 64, 64) and _implicit_tiling_ok(8, 4, 4)
+    assert _implicit_tiling_ok(1, 1, 1024) and _implicit_tiling_ok(5, 2, 2)
+    assert not _implicit_tiling_ok(2, 12, 12) and not _implicit_tiling_ok(2, 17, 17)
+    assert not _implicit_tiling_ok(1, 3, 64)            # 2 rows per tile do not divide 3
+
+
+def test_walker_visits_units_in_reference_order():
+    from qdiff._walker import UnitWalker
+    g = H.load("ddim_tiny.npz")
+    qnn = _qmodel(H.ddim_tiny_model())
+    order = []
+    names = {id(m): n for n, m in qnn.named_modules()}
+    UnitWalker(lambda m: order.append(("layer", names[id(m)])), lambda m: order.append(("block", names[id(m)]))).walk(qnn)
+    flat = [n for _, n in order]
+    assert flat[0] == "model.temb.dense.0" and flat[1] == "model.temb.dense.1" and flat[2] == "model.conv_in"
+    assert flat[3] == "model.down.0.block.0"
+    # `up` is walked from its last level to its first; level 1 (attention) unrolled block/attn pairs then upsample
+    up = [n for n in flat if ".up." in n]
+    assert up[0].startswith("model.up.1.block.0") and up[1].startswith("model.up.1.attn.0")
+    assert up[-1].startswith("model.up.0.block")
+    assert flat[-1] == "model.conv_out"
+    kinds = dict((n, k) for k, n in order)
+    assert kinds["model.down.0.downsample.conv"] == "layer"
+
+
+def test_grad_bucket_views_and_sharding():
+    from qdiff import dist as qdist
+    a = torch.nn.Parameter(torch.zeros(3, 4))
+    b = torch.nn.Parameter(torch.zeros(()))
+    bucket = qdist.GradBucket([a, b])
+    (a.sum() * 2 + b * 3).backward()
+    assert bucket.flat.tolist() == [2.0] * 12 + [3.0]
+    assert a.grad.data_ptr() == bucket.flat.data_ptr()
+    bucket.zero()
+    assert float(a.grad.abs().sum()) == 0.0
+    assert [qdist.shard_rows(10, r, 4) for r in range(4)] == [(0, 2), (2, 5), (5, 7), (7, 10)]
+
+
+DIST_SCRIPT = r'''
+import os, sys
+sys.path[:0] = [os.environ["EDADM_ROOT"], os.path.join(os.environ["EDADM_ROOT"], "eda-dm_b200")]
+import torch, torch.distributed as dist
+from qdiff import dist as qdist
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+assert qdist.is_active() and qdist.world_size() == 2
+x = torch.arange(20.).reshape(10, 2)
+(shard,) = qdist.shard_calibration([x])
+assert shard.shape[0] == 5 and float(shard[0, 0]) == (0.0 if r == 0 else 10.0)
+# identical parameters on both ranks, rank-dependent gradients -> mean after the single flat all-reduce
+p1 = torch.nn.Parameter(torch.ones(4)); p2 = torch.nn.Parameter(torch.ones(()))
+bucket = qdist.GradBucket([p1, p2])
+((p1 * (r + 1)).sum() + p2 * (10 * (r + 1))).backward()
+bucket.all_reduce_mean()
+assert torch.allclose(p1.grad, torch.full((4,), 1.5)) and abs(float(p2.grad) - 15.0) < 1e-6
+# data-parallel equivalence: mean over ranks of per-shard mean-loss gradients == gradient of the global mean loss
+g = torch.Generator().manual_seed(0)
+data = torch.randn(8, 3, generator=g); tgt = torch.randn(8, generator=g)
+wt = torch.nn.Parameter(torch.zeros(3))
+bucket = qdist.GradBucket([wt])
+lo, hi = qdist.shard_rows(8)
+((data[lo:hi] @ wt - tgt[lo:hi]) ** 2).mean().backward()
+bucket.all_reduce_mean()
+wref = torch.zeros(3, requires_grad=True)
+((data @ wref - tgt) ** 2).mean().backward()
+assert torch.allclose(wt.grad, wref.grad, atol=1e-6)
+opt = torch.optim.Adam([wt], lr=0.1); opt.step()
+gathered = [torch.zeros(3) for _ in range(w)]
+dist.all_gather(gathered, wt.detach())
+assert torch.equal(gathered[0], gathered[1])           # replicas stay in lock-step without a broadcast
+dist.barrier(); dist.destroy_process_group()
+print("rank", r, "ok")
+'''
+
+
+def test_data_parallel_plumbing_gloo_world2(tmp_path):
+    script = tmp_path / "dist_check.py"
+    script.write_text(DIST_SCRIPT)
+    env = dict(os.environ, EDADM_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29617", str(script)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("ok") == 2
