@@ -11,9 +11,10 @@
 //                                B tile (BLOCK_N out-channels x 128 B) through a rank-3 map over [Np][taps][Cp].
 //   warp 1      MMA issuer     : tcgen05.mma.cta_group::1.kind::i8, M=128, N=BLOCK_N (multiple of 16, <=256),
 //                                K=32 per instruction, accumulators in TMEM (2 stages x 256 columns).
-//   warps 2..5  epilogue       : tcgen05.ld 32x32b -> zero-point fold, per-channel dequant, bias, SiLU ->
-//                                coalesced NCHW stores (TMEM lane == output pixel == consecutive address).
-// Shared memory: 4 pipeline stages x (16 KB A + 32 KB B), 128B-swizzled K-major operands.
+//   warps 2..9  epilogue       : tcgen05.ld 32x32b (two warps per lane quarter, alternate 16-column chunks, next chunk's
+//                                load in flight) -> int32 zero-point fold, per-channel dequant, bias, SiLU ->
+//                                coalesced NCHW stores (TMEM lane == output pixel == consecutive address) or float4 rows.
+// Shared memory: up to 8 pipeline stages x (16 KB A + BLOCK_N x 128 B), 128B-swizzled K-major operands.
 #include "tc05.cuh"
 
 namespace edadm {
@@ -21,12 +22,13 @@ namespace edadm {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 128;        // bytes == int8 elements per K step (one 128B swizzle atom)
 constexpr int MAX_BLOCK_N = 256;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K;
-constexpr int B_STAGE_BYTES = MAX_BLOCK_N * BLOCK_K;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct GemmParams {
   // problem
@@ -37,6 +39,7 @@ struct GemmParams {
   // tile -> coordinate mapping of the activation tensor map (dims: C, W, H, B)
   int Wo, HoWo;             // output row length and pixels per image (2-D GEMM: Wo = HoWo = 2^30)
   int block_n, n_tiles, m_tiles;
+  int stages, b_stage_bytes;
   // epilogue
   int out_hw;               // pixels per image of the OUTPUT layout (1 => row-major [M][N])
   int accumulate, silu;
@@ -51,23 +54,68 @@ struct GemmParams {
 };
 
 struct __align__(8) PipeBarriers {
-  uint64_t full[STAGES];
-  uint64_t empty[STAGES];
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
   uint64_t tmem_full[ACC_STAGES];
   uint64_t tmem_empty[ACC_STAGES];
   uint32_t tmem_base;
 };
 
 constexpr int EPI_VEC_BYTES = MAX_BLOCK_N * 4 * 4;  // scale, zterm, cw, bias per column
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_VEC_BYTES + 256;
+constexpr int SMEM_FIXED = 1024 /*align slack*/ + EPI_VEC_BYTES + 256 /*barriers*/;
+
+// one 16-column chunk of the epilogue for one output row: int32 zero-point fold, fp32 scale + bias, store
+template <bool GENERIC>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[16], int c0, int n_valid, int rs, const float* epi_scale,
+                                               const int* epi_zterm, const int* epi_cw, const float* epi_bias, float* dst,
+                                               long long col_stride, bool accumulate, bool silu) {
+  if (!GENERIC) {
+    // all 16 columns valid, no rowsum term, plain store
+    const int4* zt = reinterpret_cast<const int4*>(epi_zterm + c0);
+    const float4* sc = reinterpret_cast<const float4*>(epi_scale + c0);
+    const float4* bi = reinterpret_cast<const float4*>(epi_bias + c0);
+    if (col_stride == 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int4 z = zt[q]; const float4 s = sc[q]; const float4 b = bi[q];
+        float4 v;
+        v.x = fmaf((float)((int)r[4 * q + 0] + z.x), s.x, b.x);
+        v.y = fmaf((float)((int)r[4 * q + 1] + z.y), s.y, b.y);
+        v.z = fmaf((float)((int)r[4 * q + 2] + z.z), s.z, b.z);
+        v.w = fmaf((float)((int)r[4 * q + 3] + z.w), s.w, b.w);
+        *reinterpret_cast<float4*>(dst + 4 * q) = v;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int4 z = zt[q]; const float4 s = sc[q]; const float4 b = bi[q];
+        dst[0] = fmaf((float)((int)r[4 * q + 0] + z.x), s.x, b.x); dst += col_stride;
+        dst[0] = fmaf((float)((int)r[4 * q + 1] + z.y), s.y, b.y); dst += col_stride;
+        dst[0] = fmaf((float)((int)r[4 * q + 2] + z.z), s.z, b.z); dst += col_stride;
+        dst[0] = fmaf((float)((int)r[4 * q + 3] + z.w), s.w, b.w); dst += col_stride;
+      }
+    }
+  } else {
+    for (int j = 0; j < 16; ++j) {
+      if (j < n_valid) {
+        const float iv = (float)((int)r[j] + epi_cw[c0 + j] * rs + epi_zterm[c0 + j]);
+        float v = fmaf(iv, epi_scale[c0 + j], epi_bias[c0 + j]);
+        float* d = dst + (long long)j * col_stride;
+        if (accumulate) v += *d;
+        if (silu) v = v / (1.f + __expf(-v));
+        *d = v;
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  float* epi_scale = reinterpret_cast<float*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint8_t* smem_b = smem + p.stages * A_STAGE_BYTES;
+  float* epi_scale = reinterpret_cast<float*>(smem_b + p.stages * p.b_stage_bytes);
   int* epi_zterm = reinterpret_cast<int*>(epi_scale + MAX_BLOCK_N);
   int* epi_cw = epi_zterm + MAX_BLOCK_N;
   float* epi_bias = reinterpret_cast<float*>(epi_cw + MAX_BLOCK_N);
@@ -77,13 +125,14 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
   const int k_iters = p.taps * p.k_chunks;
+  const int stages = p.stages;
   const uint32_t stage_tx = A_STAGE_BYTES + (uint32_t)p.block_n * BLOCK_K;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], 4); }
+    for (int i = 0; i < stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], EPI_WARPS); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -114,8 +163,8 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             mbar_wait(&bars->empty[stage], phase ^ 1);
             mbar_expect_tx(&bars->full[stage], stage_tx);
             tma_load_4d(smem_a + stage * A_STAGE_BYTES, &map_a, &bars->full[stage], p.a_c_offset + kc * BLOCK_K, ow0 + kw, oh0 + kh, b0);
-            tma_load_3d(smem_b + stage * B_STAGE_BYTES, &map_b, &bars->full[stage], kc * BLOCK_K, tap, n0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            tma_load_3d(smem_b + stage * p.b_stage_bytes, &map_b, &bars->full[stage], kc * BLOCK_K, tap, n0);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -138,30 +187,34 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
-          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * p.b_stage_bytes));
           for (int k = 0; k < nmma; ++k)
             umma_i8(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)), idesc, (it | k) ? 1u : 0u);
           umma_commit(&bars->empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&bars->tmem_full[acc]);
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9): two warps per TMEM lane quarter, alternate 16-column chunks =====================
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;              // 0..127
+    const int et = threadIdx.x - 64;              // 0..255
     const float da = __ldg(p.delta_a);
     const int za = (int)__ldg(p.zp_a);
+    // float4 row stores need 16-byte aligned rows
+    const bool generic_all = p.cw != nullptr || p.accumulate || p.silu ||
+                             (p.out_hw == 1 && ((p.N & 3) || (reinterpret_cast<uintptr_t>(p.out) & 15)));
+    const long long col_stride = p.out_hw;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
       const int n0 = n_blk * p.block_n;
-      // stage per-column vectors
-      for (int j = et; j < p.block_n; j += 128) {
+      for (int j = et; j < p.block_n; j += EPI_WARPS * 32) {
         const int n = n0 + j;
         const bool ok = n < p.N;
         epi_scale[j] = ok ? da * __ldg(p.delta_w + n) : 0.f;
@@ -169,41 +222,44 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         epi_cw[j] = (ok && p.cw) ? __ldg(p.cw + n) : 0;
         epi_bias[j] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       const int m = m_blk * BLOCK_M + row_in_tile;
       const bool row_ok = m < p.M;
       const int rs = (row_ok && p.rowsum) ? __ldg(p.rowsum + m) : 0;
       const long long img = row_ok ? m / p.out_hw : 0;
       const long long pix = row_ok ? m - img * p.out_hw : 0;
-      float* out_row = p.out + img * (long long)p.N * p.out_hw + pix;
+      float* out_row = p.out + img * (long long)p.N * p.out_hw + pix + (long long)n0 * p.out_hw;
 
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BLOCK_N;
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
+      uint32_t r0[16], r1[16];
+      int c0 = half * 16;
+      if (c0 < p.block_n) { tmem_ld16(taddr + c0, r0); }
+      tmem_ld_wait();
+      // software pipeline: the TMEM load of the next chunk is in flight while this one is converted and stored
+      for (; c0 < p.block_n; c0 += 64) {
+        const int c1 = c0 + 32;
+        if (c1 < p.block_n) tmem_ld16(taddr + c1, r1);
         if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + c0 + j;
-            if (n < p.N) {
-              // zero-point fold in int32 (exact: |terms| < 2^30), one rounding when converting to fp32
-              const float iv = (float)((int)r[j] + epi_cw[c0 + j] * rs + epi_zterm[c0 + j]);
-              float v = iv * epi_scale[c0 + j] + epi_bias[c0 + j];
-              float* dst = out_row + (long long)n * p.out_hw;
-              if (p.accumulate) v += *dst;
-              if (p.silu) v = v / (1.f + __expf(-v));
-              *dst = v;
-            }
-          }
+          const int nv = p.N - (n0 + c0);
+          if (!generic_all && nv >= 16) epilogue_chunk<false>(r0, c0, 16, rs, epi_scale, epi_zterm, epi_cw, epi_bias, out_row + (long long)c0 * col_stride, col_stride, false, false);
+          else epilogue_chunk<true>(r0, c0, nv, rs, epi_scale, epi_zterm, epi_cw, epi_bias, out_row + (long long)c0 * col_stride, col_stride, p.accumulate, p.silu);
         }
+        tmem_ld_wait();
+        const int c2 = c0 + 64;
+        if (c2 < p.block_n) tmem_ld16(taddr + c2, r0);
+        if (c1 < p.block_n && row_ok) {
+          const int nv = p.N - (n0 + c1);
+          if (!generic_all && nv >= 16) epilogue_chunk<false>(r1, c1, 16, rs, epi_scale, epi_zterm, epi_cw, epi_bias, out_row + (long long)c1 * col_stride, col_stride, false, false);
+          else epilogue_chunk<true>(r1, c1, nv, rs, epi_scale, epi_zterm, epi_cw, epi_bias, out_row + (long long)c1 * col_stride, col_stride, p.accumulate, p.silu);
+        }
+        tmem_ld_wait();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // epi_* vectors are rewritten next tile
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // epi_* vectors are rewritten next tile
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -297,18 +353,22 @@ extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_ac
   p.Wo = flat ? (1 << 30) : Wo;
   p.HoWo = flat ? (1 << 30) : Ho * Wo;
   p.block_n = block_n; p.n_tiles = n_tiles; p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  p.b_stage_bytes = (block_n * BLOCK_K + 1023) & ~1023;
+  p.stages = (SMEM_LIMIT - SMEM_FIXED) / (A_STAGE_BYTES + p.b_stage_bytes);
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  const int smem_bytes = SMEM_FIXED + p.stages * (A_STAGE_BYTES + p.b_stage_bytes);
   p.out_hw = out_hw; p.accumulate = accumulate; p.silu = silu;
   p.delta_a = delta_a; p.zp_a = zp_a; p.delta_w = delta_w; p.wsum_eff = wsum_eff; p.cw = cw; p.rowsum = rowsum;
   p.bias = bias; p.out = out;
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(qgemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return fail(EDADM_ERR_CUDA, "qgemm_i8: cannot opt in to %d B shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(qgemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) return fail(EDADM_ERR_CUDA, "qgemm_i8: cannot opt in to %d B shared memory: %s", SMEM_LIMIT, cudaGetErrorString(e));
     attr_set = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  qgemm_i8_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(map_a, map_b, p);
+  qgemm_i8_kernel<<<grid, GEMM_THREADS, smem_bytes, (cudaStream_t)stream>>>(map_a, map_b, p);
   return check_launch("qgemm_i8");
 }
