@@ -376,7 +376,7 @@ def main():
                        "quant_modules": len(paths), "on_int8_tcgen05_path": n_int8, "cuda_graph": graph is not None,
                        "l2": "weights + activations of one forward exceed the 126 MB L2 (no flush needed)",
                        "unet_steps_per_s": world * 1e3 / ms_step, "gemm_gflop_per_sample": flops_step / batch / 1e9,
-                       "attention": "fake-quant kernels + library bmm (fused kernel: next round)"},
+                       "attention": "fused tcgen05 kernel (edadm_qattn_fwd)"},
             "e2e": {"value": world * batch * 1e3 / ms_e2e, "unit": "img-steps/s", "h2d_bytes_per_step": in_bytes,
                     "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e},
             "gpu_launches": launches_per_step * args.steps,
