@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="do not capture the UNet forward in a CUDA graph")
     ap.add_argument("--no-recon", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--recon-iters", type=int, default=12)
+    ap.add_argument("--recon-iters", type=int, default=40)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     kind, batch, shape, ctx, gflop_per_sample = WORKLOADS[args.workload]
@@ -213,6 +213,9 @@ def main():
     from qdiff.quant_block import BaseQuantBlock
 
     native.load_library()                      # fail loudly if the CUDA extension is missing
+    if os.environ.get("EDADM_TF32"):
+        from qdiff.quant_layer import backend
+        backend.allow_tf32 = True
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -358,6 +361,7 @@ def main():
         recon = {"unit": type(unit).__name__, "iters_per_s": 1e3 / ms_it, "samples_per_s": world * rb * 1e3 / ms_it,
                  "ms_per_iter": ms_it, "batch_per_gpu": rb, "global_batch": rb * world, "scaling": "weak",
                  "allreduce_bytes_per_iter": timing.get("bucket_bytes", 0) if world > 1 else 0,
+                 "cuda_graph": timing.get("cuda_graph", False),
                  "semantics": "reference loop: quant fwd + FP fwd + quant fwd (FBR) + backward, QDrop 0.5"}
         qnn.set_quant_state(True, True)
 

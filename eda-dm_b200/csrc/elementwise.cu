@@ -12,7 +12,8 @@ namespace edadm {
 
 struct QDrop {
   const uint8_t* mask;  // explicit keep-mask (1 = take quantized value), may be null
-  float prob;           // used when mask == null and prob < 1: keep iff u01 < prob
+  const float* rnd;     // explicit uniform draws (torch.rand_like): keep iff rnd[i] < prob -- the reference's own stream
+  float prob;           // used when mask == null and prob < 1: keep iff u < prob
   uint2 key;
   uint64_t offset;
 };
@@ -20,6 +21,7 @@ struct QDrop {
 __device__ __forceinline__ bool qdrop_keep(const QDrop& q, int64_t i, uint4& rnd, int64_t& rnd_quad) {
   if (q.mask) return q.mask[i] != 0;
   if (q.prob >= 1.0f) return true;
+  if (q.rnd) return __ldcs(q.rnd + i) < q.prob;
   const int64_t quad = (i + (int64_t)q.offset) >> 2;
   if (quad != rnd_quad) {
     rnd = philox4x32_10(make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), 0u, 0u), q.key);
@@ -309,9 +311,10 @@ lp_loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tgt
 
 using namespace edadm;
 
-static QDrop make_qdrop(const uint8_t* mask, float prob, uint64_t seed, uint64_t offset) {
+static QDrop make_qdrop(const uint8_t* mask, const float* rnd, float prob, uint64_t seed, uint64_t offset) {
   QDrop q;
   q.mask = mask;
+  q.rnd = rnd;
   q.prob = prob;
   q.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   q.offset = offset;
@@ -322,14 +325,14 @@ extern "C" int edadm_reduce_slots(void) { return sm_count() * 8; }
 
 extern "C" int edadm_uaq_fwd(const float* x, float* y, uint8_t* codes, const float* delta,
                              const float* zero_point, int64_t n, int64_t channels, int64_t inner,
-                             int n_levels, const uint8_t* keep_mask, float qdrop_prob, uint64_t seed,
-                             uint64_t offset, void* stream) {
+                             int n_levels, const uint8_t* keep_mask, const float* keep_rand, float qdrop_prob,
+                             uint64_t seed, uint64_t offset, void* stream) {
   if (!x || !y || !delta || !zero_point) return fail(EDADM_ERR_ARG, "uaq_fwd: null pointer");
   if (n < 0 || channels < 1 || inner < 1 || n_levels < 2 || n_levels > 256)
     return fail(EDADM_ERR_ARG, "uaq_fwd: bad sizes n=%lld channels=%lld inner=%lld levels=%d",
                 (long long)n, (long long)channels, (long long)inner, n_levels);
   if (n == 0) return EDADM_OK;
-  const QDrop qd = make_qdrop(keep_mask, qdrop_prob, seed, offset);
+  const QDrop qd = make_qdrop(keep_mask, keep_rand, qdrop_prob, seed, offset);
   const int grid = stream_grid((n + 3) / 4);
   const float qmax = (float)(n_levels - 1);
   cudaStream_t s = (cudaStream_t)stream;
@@ -342,8 +345,8 @@ extern "C" int edadm_uaq_fwd(const float* x, float* y, uint8_t* codes, const flo
 
 extern "C" int edadm_uaq_bwd(const float* gy, const float* x, const float* delta, const float* zero_point,
                              int64_t n, int64_t channels, int64_t inner, int n_levels,
-                             const uint8_t* keep_mask, float qdrop_prob, uint64_t seed, uint64_t offset,
-                             float* gx, float* gdelta, int accumulate_gdelta, double* partials,
+                             const uint8_t* keep_mask, const float* keep_rand, float qdrop_prob, uint64_t seed,
+                             uint64_t offset, float* gx, float* gdelta, int accumulate_gdelta, double* partials,
                              void* stream) {
   if (!gy || !x || !gx || !delta || !zero_point) return fail(EDADM_ERR_ARG, "uaq_bwd: null pointer");
   if (gdelta && channels != 1)
@@ -352,7 +355,7 @@ extern "C" int edadm_uaq_bwd(const float* gy, const float* x, const float* delta
   if (n < 0 || channels < 1 || inner < 1 || n_levels < 2 || n_levels > 256)
     return fail(EDADM_ERR_ARG, "uaq_bwd: bad sizes");
   cudaStream_t s = (cudaStream_t)stream;
-  const QDrop qd = make_qdrop(keep_mask, qdrop_prob, seed, offset);
+  const QDrop qd = make_qdrop(keep_mask, keep_rand, qdrop_prob, seed, offset);
   const int grid = stream_grid((n + 3) / 4);
   const float qmax = (float)(n_levels - 1);
   if (n > 0) {

@@ -20,8 +20,8 @@ _SIGNATURES = {
     "edadm_last_error": (c_char_p, []),
     "edadm_abi_version": (c_int, []),
     "edadm_reduce_slots": (c_int, []),
-    "edadm_uaq_fwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, c_int, P, c_float, c_uint64, c_uint64, P]),
-    "edadm_uaq_bwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int, P, c_float, c_uint64, c_uint64, P, P, c_int, P, P]),
+    "edadm_uaq_fwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, c_int, P, P, c_float, c_uint64, c_uint64, P]),
+    "edadm_uaq_bwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int, P, P, c_float, c_uint64, c_uint64, P, P, c_int, P, P]),
     "edadm_adaround_fwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int64, c_int, c_int, P, P, P]),
     "edadm_adaround_bwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int64, c_int, P, c_int, P]),
     "edadm_adaround_init_alpha": (c_int, [P, P, c_int64, c_int64, c_int64, P, P]),

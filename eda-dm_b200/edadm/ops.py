@@ -12,6 +12,7 @@ import torch
 from .native import lib, EdadmError
 
 _partials_cache = {}
+_EMPTY = torch.empty(0)
 
 
 def _stream():
@@ -66,7 +67,7 @@ def _qparam(t, device) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # K2  UniformAffineQuantizer
 # ------------------------------------------------------------------------------------------------
-def uaq_forward(x, delta, zero_point, n_levels, keep_mask=None, prob=1.0, seed=0, offset=0, want_codes=False):
+def uaq_forward(x, delta, zero_point, n_levels, keep_mask=None, prob=1.0, seed=0, offset=0, want_codes=False, keep_rand=None):
     _need_cuda(x)
     x = _f32c(x)
     d = _qparam(delta, x.device)
@@ -78,8 +79,10 @@ def uaq_forward(x, delta, zero_point, n_levels, keep_mask=None, prob=1.0, seed=0
     codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_codes else None
     if keep_mask is not None:
         keep_mask = keep_mask.to(torch.uint8).contiguous()
+    if keep_rand is not None:
+        keep_rand = _f32c(keep_rand)
     lib.uaq_fwd(x.data_ptr(), y.data_ptr(), _ptr(codes), d.data_ptr(), z.data_ptr(), x.numel(), channels, inner,
-                int(n_levels), _ptr(keep_mask), float(prob), int(seed), int(offset), _stream())
+                int(n_levels), _ptr(keep_mask), _ptr(keep_rand), float(prob), int(seed), int(offset), _stream())
     return (y, codes) if want_codes else y
 
 
@@ -87,17 +90,20 @@ class UAQFunction(torch.autograd.Function):
     """Fake-quant with straight-through gradient (quant_layer.py:19-23, 267-274) as one kernel each way."""
 
     @staticmethod
-    def forward(ctx, x, delta, zero_point, n_levels, keep_mask, prob, seed, offset):
+    def forward(ctx, x, delta, zero_point, n_levels, keep_mask, prob, seed, offset, keep_rand=None):
         xc = _f32c(x)
-        y = uaq_forward(xc, delta, zero_point, n_levels, keep_mask, prob, seed, offset)
-        ctx.save_for_backward(xc, delta, zero_point, keep_mask if keep_mask is not None else torch.empty(0))
-        ctx.meta = (int(n_levels), float(prob), int(seed), int(offset), keep_mask is not None)
+        if keep_rand is not None:
+            keep_rand = _f32c(keep_rand)
+        y = uaq_forward(xc, delta, zero_point, n_levels, keep_mask, prob, seed, offset, keep_rand=keep_rand)
+        ctx.save_for_backward(xc, delta, zero_point, keep_mask if keep_mask is not None else _EMPTY,
+                              keep_rand if keep_rand is not None else _EMPTY)
+        ctx.meta = (int(n_levels), float(prob), int(seed), int(offset), keep_mask is not None, keep_rand is not None)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, delta, zero_point, keep_mask = ctx.saved_tensors
-        n_levels, prob, seed, offset, has_mask = ctx.meta
+        x, delta, zero_point, keep_mask, keep_rand = ctx.saved_tensors
+        n_levels, prob, seed, offset, has_mask, has_rand = ctx.meta
         gy = _f32c(gy)
         d = _qparam(delta, x.device)
         z = _qparam(zero_point, x.device)
@@ -107,14 +113,14 @@ class UAQFunction(torch.autograd.Function):
         gd = torch.zeros(1, dtype=torch.float32, device=x.device) if want_gd else None
         mask = keep_mask.to(torch.uint8).contiguous() if has_mask else None
         lib.uaq_bwd(gy.data_ptr(), x.data_ptr(), d.data_ptr(), z.data_ptr(), x.numel(), channels, inner, n_levels,
-                    _ptr(mask), prob, seed, offset, gx.data_ptr(), _ptr(gd), 0,
+                    _ptr(mask), keep_rand.data_ptr() if has_rand else None, prob, seed, offset, gx.data_ptr(), _ptr(gd), 0,
                     _partials(x.device).data_ptr() if want_gd else None, _stream())
         gdelta = gd.reshape(delta.shape) if want_gd else None
-        return gx, gdelta, None, None, None, None, None, None
+        return gx, gdelta, None, None, None, None, None, None, None
 
 
-def uaq_fake_quant(x, delta, zero_point, n_levels, keep_mask=None, prob=1.0, seed=0, offset=0):
-    return UAQFunction.apply(x, delta, zero_point, n_levels, keep_mask, prob, seed, offset)
+def uaq_fake_quant(x, delta, zero_point, n_levels, keep_mask=None, prob=1.0, seed=0, offset=0, keep_rand=None):
+    return UAQFunction.apply(x, delta, zero_point, n_levels, keep_mask, prob, seed, offset, keep_rand)
 
 
 # ------------------------------------------------------------------------------------------------

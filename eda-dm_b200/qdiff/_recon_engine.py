@@ -13,16 +13,21 @@ What is different on B200:
     single all-reduce per step -- data parallel over the calibration rows of the unit;
   * the cache builder shards the calibration set by rank.
 """
+import contextlib
+import logging
+import math
 import random
 
 import torch
 
-from .quant_layer import QuantModule, lp_loss
+from .quant_layer import QuantModule, lp_loss, backend
 from .quant_block import (BaseQuantBlock, QuantAttnBlock, QuantAttentionBlock, QuantBasicTransformerBlock)
 from .adaptive_rounding import AdaRoundQuantizer
 from .utils import AttentionMap
 from edadm import ops
 from . import dist as qdist
+
+logger = logging.getLogger(__name__)
 
 
 class LinearTempDecay:
@@ -166,55 +171,89 @@ def _take(t, idx, device):
     return out if out.device == device else out.to(device, non_blocking=True)
 
 
+def _cosine_lr(lr0, t, t_max):
+    """Closed form of CosineAnnealingLR(T_max=t_max, eta_min=0) after t scheduler steps."""
+    return lr0 * (1.0 + math.cos(math.pi * min(t, t_max) / t_max)) / 2.0
+
+
+def _graph_capturable(unit, device):
+    if device.type != 'cuda' or not backend.recon_cuda_graph:
+        return False
+    for m in unit.modules():
+        # activation checkpointing re-enters autograd and snapshots RNG state: keep those units on the eager loop
+        if isinstance(m, QuantAttentionBlock) or getattr(m, 'use_checkpoint', False) or getattr(m, 'checkpoint', False) is True:
+            return False
+    return True
+
+
 def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, asym, b_range, warmup, act_quant, lr_a,
                 lr_w, p, input_prob, keep_gpu, recon_w, recon_a, add_loss, cache_builder, cache_batch_size=32,
                 transformer=False, is_layer=False, split_aware=True, attn_only=False, return_losses=False, timing=None):
+    """One reconstruction unit.  After three eager iterations the whole step -- input mixing, the (up to three)
+    forwards, both losses, backward, the gradient all-reduce and both Adam updates -- is captured in ONE CUDA graph and
+    replayed; per iteration the host only draws the minibatch indices, gathers the cached rows into static buffers and
+    writes the two cosine learning rates."""
     unit.set_quant_state(True, act_quant)
     w_para, a_para, hooks, trained = prepare_unit(unit, act_quant, recon_w, recon_a, transformer,
                                                   with_hooks=not (is_layer or attn_only), split_aware=split_aware,
                                                   attn_only=attn_only)
+    device = next(model.parameters()).device
+    use_graph = _graph_capturable(unit, device) and bool(w_para or a_para)
     w_opt = a_opt = w_sched = a_sched = None
-    if w_para:
-        w_opt = torch.optim.Adam(w_para, lr=lr_w)
-        w_sched = torch.optim.lr_scheduler.CosineAnnealingLR(w_opt, T_max=iters, eta_min=0.)
-    if a_para:
-        a_opt = torch.optim.Adam(a_para, lr=lr_a)
-        a_sched = torch.optim.lr_scheduler.CosineAnnealingLR(a_opt, T_max=iters, eta_min=0.)
+    w_lr = a_lr = None
+    if use_graph:   # learning rates live on the device so the captured Adam steps see the schedule
+        w_lr = torch.tensor(float(lr_w), device=device)
+        a_lr = torch.tensor(float(lr_a), device=device)
+        if w_para:
+            w_opt = torch.optim.Adam(w_para, lr=w_lr, capturable=True)
+        if a_para:
+            a_opt = torch.optim.Adam(a_para, lr=a_lr, capturable=True)
+    else:
+        if w_para:
+            w_opt = torch.optim.Adam(w_para, lr=lr_w)
+            w_sched = torch.optim.lr_scheduler.CosineAnnealingLR(w_opt, T_max=iters, eta_min=0.)
+        if a_para:
+            a_opt = torch.optim.Adam(a_para, lr=lr_a)
+            a_sched = torch.optim.lr_scheduler.CosineAnnealingLR(a_opt, T_max=iters, eta_min=0.)
     loss_func = LossFunction(unit, round_loss='none', weight=weight, max_count=iters, rec_loss=opt_mode,
                              b_range=b_range, decay_start=0, warmup=warmup, p=p)
 
     resblock, cached_inps, cached_outs = cache_builder(model, unit, cali_data, asym, act_quant,
                                                        batch_size=cache_batch_size, input_prob=True, keep_gpu=keep_gpu)
-    device = next(model.parameters()).device
     sz = cached_outs.size(0)
     model.block_count = model.block_count + 1
     bucket = qdist.GradBucket(w_para + a_para) if (w_para or a_para) else None
     rng = random if not qdist.is_active() else random.Random(random.getrandbits(48) + 7919 * qdist.rank())
     losses = []
     fbr = (not is_layer) and len(hooks) != 0 and add_loss != 0.0
+    bsz = min(batch_size, sz)
 
-    for it in range(iters):
-        if timing is not None and it == timing.get('warmup', 0):
-            timing['start'], timing['end'] = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            qdist.barrier()
-            torch.cuda.synchronize()
-            timing['start'].record()
-        idx = rng.sample(range(sz), min(batch_size, sz))
-        idx_t = torch.as_tensor(idx, device=cached_outs.device)
-        cur_out = _take(cached_outs, idx_t, device)
-        if resblock:
-            cur_inp, cur_sym = _take(cached_inps[0][0], idx_t, device), _take(cached_inps[1][0], idx_t, device)
-            emb_inp, emb_sym = _take(cached_inps[0][1], idx_t, device), _take(cached_inps[1][1], idx_t, device)
-        else:
-            cur_inp, cur_sym = _take(cached_inps[0], idx_t, device), _take(cached_inps[1], idx_t, device)
-            emb_inp = emb_sym = None
+    # cache tensors in the order (out, inp, sym[, emb_inp, emb_sym]); static minibatch buffers for the graph
+    if resblock:
+        sources = [cached_outs, cached_inps[0][0], cached_inps[1][0], cached_inps[0][1], cached_inps[1][1]]
+    else:
+        sources = [cached_outs, cached_inps[0], cached_inps[1]]
+    static = [torch.empty((bsz,) + tuple(t.shape[1:]), dtype=t.dtype, device=device) for t in sources] if use_graph else None
+    loss_out = torch.zeros((), dtype=torch.float32, device=device)
+
+    def gather(idx):
+        idx_t = torch.as_tensor(idx, device=sources[0].device)
+        rows = [_take(t, idx_t, device) for t in sources]
+        if static is None:
+            return rows
+        for dst, src in zip(static, rows):
+            dst.copy_(src, non_blocking=True)
+        return static
+
+    def step(rows):
+        cur_out, cur_inp, cur_sym = rows[0], rows[1], rows[2]
+        emb_inp, emb_sym = (rows[3], rows[4]) if resblock else (None, None)
         if input_prob < 1.0:
             cur_inp = torch.where(torch.rand_like(cur_inp) < input_prob, cur_inp, cur_sym)
         elif not is_layer:
             cur_inp = cur_sym
         if bucket is not None:
             bucket.zero()
-
         args_q = (cur_inp, emb_inp) if resblock else (cur_inp,)
         args_fp = (cur_sym, emb_sym) if resblock else (cur_sym,)
         out_quant = unit(*args_q)
@@ -234,19 +273,60 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
         loss.backward()
         if bucket is not None:
             bucket.all_reduce_mean()
-        for step in (w_opt, a_opt, w_sched, a_sched):
-            if step is not None:
-                step.step()
-        if return_losses:
-            losses.append(block_loss.detach())
+        for opt in (w_opt, a_opt):
+            if opt is not None:
+                opt.step()
+        loss_out.copy_(block_loss.detach())
+
+    graph = None
+    n_eager = 3
+    # Warm-up iterations and the capture run on ONE non-default stream (library handles / workspaces used by the
+    # autograd thread must never have been bound to the legacy stream, or capture is invalidated).
+    side = torch.cuda.Stream(device=device) if use_graph else None
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream(device))
+    stream_ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
+    with stream_ctx:
+        for it in range(iters):
+            if use_graph and graph is None and it == n_eager:
+                try:
+                    side.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=side):
+                        step(static)
+                except Exception as exc:  # keep optimising eagerly; the captured work never ran
+                    logger.warning("CUDA-graph capture of the reconstruction step failed (%s); continuing eagerly", exc)
+                    graph, use_graph = False, False
+            if timing is not None and it == timing.get('warmup', 0):
+                timing['start'], timing['end'] = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                qdist.barrier()
+                torch.cuda.synchronize()
+                timing['start'].record()
+            rows = gather(rng.sample(range(sz), bsz))
+            if w_lr is not None:
+                w_lr.fill_(_cosine_lr(lr_w, it, iters))
+                a_lr.fill_(_cosine_lr(lr_a, it, iters))
+            if graph:
+                graph.replay()
+            else:
+                step(rows)
+                for sched in (w_sched, a_sched):
+                    if sched is not None:
+                        sched.step()
+            if return_losses:
+                losses.append(loss_out.clone())
+        if timing is not None and 'start' in timing:
+            timing['end'].record()
+    if side is not None:
+        torch.cuda.current_stream(device).wait_stream(side)
 
     if timing is not None and 'start' in timing:
-        timing['end'].record()
         torch.cuda.synchronize()
         qdist.barrier()
         timing['iters'] = iters - timing.get('warmup', 0)
         timing['ms_per_iter'] = timing['start'].elapsed_time(timing['end']) / max(1, timing['iters'])
         timing['bucket_bytes'] = bucket.nbytes() if bucket is not None else 0
+        timing['cuda_graph'] = bool(graph)
     finish_unit(unit, trained, hooks, attn_only)
     if bucket is not None:
         for prm in bucket.params:

@@ -29,6 +29,9 @@ class _Backend:
     """Process-wide knobs of the calibration path (defaults reproduce the reference's fp32 numerics)."""
     allow_tf32 = False       # library conv/matmul of the calibration path in strict fp32
     integer_path = True      # use the tcgen05 int8 GEMM whenever it applies
+    recon_cuda_graph = True  # capture the reconstruction iteration in one CUDA graph after 3 eager iterations
+    qdrop_inkernel_rng = False  # False: QDrop masks come from torch.rand_like (the reference's stream, graph-safe);
+                                # True: drawn inside the kernel (Philox4x32, no extra memory pass)
     qdrop_seed = None        # None -> torch.initial_seed()
     qdrop_offset = 0         # running Philox offset (one fresh sub-stream per fake-quant call)
 
@@ -218,8 +221,12 @@ class UniformAffineQuantizer(nn.Module):
         if not x.is_cuda:
             raise EdadmError("UniformAffineQuantizer needs CUDA tensors: the fake-quant kernel has no CPU fallback")
         if self.is_training and self.prob < 1.0:
-            seed, offset = backend.next_stream(x.numel())
-            return ops.uaq_fake_quant(x, self.delta, self.zero_point, self.n_levels, None, self.prob, seed, offset)
+            if backend.qdrop_inkernel_rng:
+                seed, offset = backend.next_stream(x.numel())
+                return ops.uaq_fake_quant(x, self.delta, self.zero_point, self.n_levels, None, self.prob, seed, offset)
+            # torch.where(torch.rand_like(x) < prob, x_dequant, x) -- reference quant_layer.py:271-272, same draws
+            return ops.uaq_fake_quant(x, self.delta, self.zero_point, self.n_levels, None, self.prob, 0, 0,
+                                      keep_rand=torch.rand_like(x))
         return ops.uaq_fake_quant(x, self.delta, self.zero_point, self.n_levels)
 
     def codes(self, x: torch.Tensor):

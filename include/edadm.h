@@ -34,17 +34,18 @@ int edadm_reduce_slots(void);
  * `torch.where(rand_like(x) < prob, x_dequant, x)`), and its autograd graph (round_ste :19-23).
  *   y = keep ? (clamp(rint(x/delta)+zp, 0, n_levels-1) - zp) * delta : x
  * delta/zero_point: 1 element (channels==1) or `channels` elements; channel of element i is
- * (i / inner) % channels.  keep_mask (u8, nullable) is an explicit QDrop mask; when null and
- * qdrop_prob < 1 a Philox4x32-10 stream keyed by (seed, offset) draws the mask (same draw in bwd).
+ * (i / inner) % channels.  QDrop (qdrop_prob < 1): keep_mask (u8, nullable) is an explicit mask; else keep_rand
+ * (fp32, nullable) holds the uniform draws of `torch.rand_like(x)` and keep = rand < prob, i.e. the reference's own
+ * random stream; else a Philox4x32-10 stream keyed by (seed, offset) draws the mask in the kernel (same draw in bwd).
  * codes (nullable) receives the integer codes as u8.                                             */
 int edadm_uaq_fwd(const float* x, float* y, uint8_t* codes, const float* delta, const float* zero_point,
                   int64_t n, int64_t channels, int64_t inner, int n_levels, const uint8_t* keep_mask,
-                  float qdrop_prob, uint64_t seed, uint64_t offset, void* stream);
+                  const float* keep_rand, float qdrop_prob, uint64_t seed, uint64_t offset, void* stream);
 /* gx = straight-through gradient; gdelta (nullable, per-tensor only) = LSQ step-size gradient,
  * reduced in fp64 through `partials` (edadm_reduce_slots() doubles).                              */
 int edadm_uaq_bwd(const float* gy, const float* x, const float* delta, const float* zero_point, int64_t n,
-                  int64_t channels, int64_t inner, int n_levels, const uint8_t* keep_mask, float qdrop_prob,
-                  uint64_t seed, uint64_t offset, float* gx, float* gdelta, int accumulate_gdelta,
+                  int64_t channels, int64_t inner, int n_levels, const uint8_t* keep_mask, const float* keep_rand,
+                  float qdrop_prob, uint64_t seed, uint64_t offset, float* gx, float* gdelta, int accumulate_gdelta,
                   double* partials, void* stream);
 
 /* ---- K3: AdaRoundQuantizer -----------------------------------------------------------------------

@@ -35,7 +35,7 @@ def test_argument_errors_are_reported_not_crashing():
     from edadm import native
     lib = native.lib
     with pytest.raises(native.EdadmError, match="null pointer"):
-        lib.uaq_fwd(None, None, None, None, None, 16, 1, 1, 256, None, 1.0, 0, 0, None)
+        lib.uaq_fwd(None, None, None, None, None, 16, 1, 1, 256, None, None, 1.0, 0, 0, None)
 
 
 def test_no_cpu_fallback_for_quantized_path():
