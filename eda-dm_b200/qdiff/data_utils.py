@@ -76,8 +76,10 @@ class GetLayerInpOut:
 
 
 def save_inp_oup_data(model: QuantModel, layer: Union[QuantModule, BaseQuantBlock], cali_data, asym: bool = False,
-                      act_quant: bool = False, batch_size: int = 32, input_prob: bool = False, keep_gpu: bool = True):
-    """Returns (Resblock, cached_inps, cached_outs) laid out exactly like the reference (data_utils.py:67-75)."""
+                      act_quant: bool = False, batch_size: int = 32, input_prob: bool = False, keep_gpu: bool = True,
+                      batch_transform=None):
+    """Returns (Resblock, cached_inps, cached_outs) laid out exactly like the reference (data_utils.py:67-75).
+    `batch_transform` maps one calibration slice to the model's positional inputs (classifier-free-guidance variant)."""
     device = next(model.parameters()).device
     get_inp_out = GetLayerInpOut(model, layer, device=device, asym=asym, input_prob=input_prob, act_quant=act_quant)
     cali_data = qdist.shard_calibration(cali_data)
@@ -85,7 +87,8 @@ def save_inp_oup_data(model: QuantModel, layer: Union[QuantModule, BaseQuantBloc
     inps, outs, syms, temb_inps, temb_syms = [], [], [], [], []
     resblock = False
     for i in range(int(cali_data[0].size(0) / batch_size)):
-        res = get_inp_out([_[i * batch_size:(i + 1) * batch_size] for _ in cali_data])
+        batch = [_[i * batch_size:(i + 1) * batch_size] for _ in cali_data]
+        res = get_inp_out(batch_transform(batch) if batch_transform is not None else batch)
         resblock, cur_inp, cur_out = res[0], res[1], res[2]
         cur_sym = res[3] if input_prob else None
         if resblock:

@@ -10,7 +10,6 @@ from types import MethodType
 
 import torch as th
 import torch.nn as nn
-from torch.utils.checkpoint import checkpoint as _torch_checkpoint
 
 from unet_zoo import ddpm_unet as _zoo_ddpm
 from unet_zoo import ldm_unet as _zoo_ldm
@@ -36,10 +35,39 @@ _ref_ResnetBlock, _ref_AttnBlock = _optional('ddim.models.diffusion', 'ResnetBlo
 _TimestepBases = tuple(c for c in (_zoo_ldm.TimestepBlock, _ref_TimestepBlock) if c is not None)
 
 
+class _Recompute(th.autograd.Function):
+    """Activation recompute with the reference's semantics (ldm/modules/diffusionmodules/util.py:119-148): the forward
+    runs WITHOUT recording a graph, the backward re-runs it with grad enabled and differentiates w.r.t. the inputs and
+    the explicitly listed parameters.  Two consequences the reconstruction loop inherits from the reference: tensors tapped
+    by forward hooks inside such a block carry no gradient (the FBR terms of checkpointed units are constants), and QDrop
+    masks are re-drawn in the recompute."""
+
+    @staticmethod
+    def forward(ctx, func, n_inputs, *args):
+        ctx.func = func
+        ctx.inputs = list(args[:n_inputs])
+        ctx.params = list(args[n_inputs:])
+        with th.no_grad():
+            return func(*ctx.inputs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        inputs = [x.detach().requires_grad_(True) if th.is_tensor(x) else x for x in ctx.inputs]
+        with th.enable_grad():
+            outputs = ctx.func(*[x.view_as(x) if th.is_tensor(x) else x for x in inputs])
+        wrt = [x for x in inputs if th.is_tensor(x)] + ctx.params
+        got = th.autograd.grad(outputs, wrt, grads, allow_unused=True)
+        it = iter(got)
+        in_grads = [next(it) if th.is_tensor(x) else None for x in inputs]
+        ctx.inputs = ctx.params = None
+        return (None, None) + tuple(in_grads) + tuple(it)
+
+
 def checkpoint(func, inputs, params, flag):
-    """Activation recompute when `flag` and a gradient is being recorded (reference util.py:102-148)."""
+    """Recompute `func(*inputs)` in the backward pass when `flag` and a gradient is being recorded."""
     if flag and th.is_grad_enabled():
-        return _torch_checkpoint(func, *inputs, use_reentrant=False)
+        params = [p for p in params if p.requires_grad]
+        return _Recompute.apply(func, len(inputs), *(tuple(inputs) + tuple(params)))
     return func(*inputs)
 
 

@@ -268,10 +268,60 @@ def ldm_xattn_tiny():
                                     use_spatial_transformer=True, transformer_depth=1, context_dim=24), ctx_dim=24)
 
 
+def cfg_recon():
+    """qdiff_control (classifier-free-guidance) reconstruction on the tiny spatial-transformer UNet."""
+    import qdiff_control.block_recon as ref_cfg_recon
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    kw = dict(image_size=8, in_channels=3, out_channels=3, model_channels=32, attention_resolutions=[1, 2], num_res_blocks=1,
+              channel_mult=[1, 2], num_heads=2, use_spatial_transformer=True, transformer_depth=1, context_dim=24)
+    torch.manual_seed(0)
+    model = UNetModel(**kw).eval()
+    gi = torch.Generator().manual_seed(3)
+    for p_ in model.parameters():
+        if p_.dim() > 1 and float(p_.abs().max()) == 0.0:
+            p_.data.copy_(torch.randn(p_.shape, generator=gi) * 0.05)
+    state = {k: npy(v) for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(999)
+    n = 16
+    x = torch.randn(n, 3, 8, 8, generator=g)
+    t = torch.randint(0, 1000, (n,), generator=g)
+    index = torch.zeros(n, dtype=torch.long)
+    cond = torch.randn(n, 3, 24, generator=g)
+    uncond = torch.randn(1, 3, 24, generator=g).repeat(n, 1, 1)
+    cali = (x, t, index, cond, uncond)
+    qnn = QuantModel(model, WQ, AQ, sm_abit=8).eval()
+    qnn.set_first_last_layer_to_8bit()
+    qnn.disable_network_output_quantization()
+    qnn.model.split_shortcut = True
+    _init_all(qnn, [torch.cat([x, x]), torch.cat([t, t]), torch.cat([uncond, cond])], 8)
+    out = dict(x=npy(x), t=npy(t), index=npy(index), cond=npy(cond), uncond=npy(uncond))
+    out.update({"sd." + k: v for k, v in state.items()})
+    pack_table("q.", quantizer_table(qnn), out)
+    kwargs = dict(cali_data=cali, iters=4, batch_size=4, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2, act_quant=True,
+                  opt_mode='mse', lr_a=4e-4, lr_w=1e-2, p=2.0, input_prob=1.0, keep_gpu=True, recon_w=True, recon_a=True,
+                  add_loss=0.8)
+    random.seed(55); torch.manual_seed(55)
+    trace, undo = _record_losses(ref_cfg_recon)
+    res = qnn.model.input_blocks[1][0]
+    ref_cfg_recon.block_reconstruction(qnn, res, **kwargs)
+    undo()
+    out.update(recon_res_loss=np.array(trace), recon_res_alpha=npy(res.in_layers[2].weight_quantizer.alpha))
+    random.seed(56); torch.manual_seed(56)
+    trace, undo = _record_losses(ref_cfg_recon)
+    tb = qnn.model.input_blocks[1][1].transformer_blocks[0]
+    ref_cfg_recon.block_reconstruction(qnn, tb, **kwargs)
+    undo()
+    out.update(recon_tb_loss=np.array(trace),
+               recon_tb_delta=np.array([float(tb.attn1.act_quantizer_q.delta), float(tb.attn1.act_quantizer_w.delta),
+                                        float(tb.attn2.act_quantizer_k.delta), float(tb.attn2.act_quantizer_v.delta)]))
+    np.savez_compressed(os.path.join(OUT, "cfg_xattn_tiny.npz"), **out)
+    print("cfg_xattn_tiny.npz")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["unit", "ddim", "ldm", "xattn"]
+    which = sys.argv[1:] or ["unit", "ddim", "ldm", "xattn", "cfg"]
     if "unit" in which:
         unit_vectors()
     if "ddim" in which:
@@ -280,3 +330,5 @@ if __name__ == "__main__":
         ldm_tiny()
     if "xattn" in which:
         ldm_xattn_tiny()
+    if "cfg" in which:
+        cfg_recon()

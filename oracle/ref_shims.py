@@ -31,6 +31,16 @@ def install(reference_root: str = REFERENCE_ROOT):
         sys.modules["matplotlib"] = mpl
         sys.modules["matplotlib.pyplot"] = plt
 
+    # qdiff_control/coco_prompt.py imports dataset tooling that is irrelevant to the hot path
+    for name in ("pycocotools", "pycocotools.coco", "skimage", "skimage.io"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                mod = types.ModuleType(name)
+                if name == "pycocotools.coco":
+                    mod.COCO = object
+                sys.modules[name] = mod
     try:
         import omegaconf  # noqa: F401
     except Exception:

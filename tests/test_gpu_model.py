@@ -235,3 +235,34 @@ def test_ddim_tiny_reconstruction_traces(cuda):
     with torch.no_grad():
         y = qnn(x[:4], t[:4])
     assert H.rel_l2(y.cpu(), T(g["y_after_recon"])) < 1e-1     # chaotic end-to-end regime, see above
+
+
+def test_cfg_reconstruction_traces_qdiff_control(cuda):
+    """qdiff_control.block_reconstruction (CFG cache: [x;x],[t;t],[uncond;cond]; transformer-block step sizes trainable)
+    replays the reference's loss trajectory on the tiny spatial-transformer UNet."""
+    from qdiff_control.block_recon import block_reconstruction
+    g = H.load("cfg_xattn_tiny.npz")
+    qnn = _product(g, H.ldm_model("ldm_xattn_tiny.npz"), cuda, _set_split_ldm)
+    cali = tuple(T(g[k]).to(cuda) for k in ("x", "t", "index", "cond", "uncond"))
+    with torch.no_grad():
+        qnn(cali[0][:4], cali[1][:4], cali[3][:4])                  # creates the split twins
+    H.install_qparams(qnn, H.qtable(g))
+    kw = dict(RECON_KW); kw.update(batch_size=4)
+
+    random.seed(55); torch.manual_seed(55)
+    res = qnn.model.input_blocks[1][0]
+    losses = block_reconstruction(qnn, res, cali_data=cali, return_losses=True, **kw)
+    ref = g["recon_res_loss"]
+    assert abs(losses[0].item() - ref[0]) <= 1e-3 * abs(ref[0])
+    assert np.allclose(losses.cpu().numpy(), ref, rtol=5e-3)
+    assert H.rel_l2(res.in_layers[2].weight_quantizer.alpha.detach().cpu(), T(g["recon_res_alpha"])) < 5e-3
+
+    random.seed(56); torch.manual_seed(56)
+    tb = qnn.model.input_blocks[1][1].transformer_blocks[0]
+    losses = block_reconstruction(qnn, tb, cali_data=cali, return_losses=True, **kw)
+    # this unit sits behind the reconstructed ResBlock: inputs carry cross-platform code flips -> 5e-2 (see above)
+    assert np.allclose(losses.cpu().numpy(), g["recon_tb_loss"], rtol=5e-2)
+    d = [float(tb.attn1.act_quantizer_q.delta), float(tb.attn1.act_quantizer_w.delta),
+         float(tb.attn2.act_quantizer_k.delta), float(tb.attn2.act_quantizer_v.delta)]
+    # the softmax step size (2e-4) moves by Adam-normalised steps of up to 4e-4: compare it absolutely
+    assert np.allclose(d, g["recon_tb_delta"], rtol=1e-2, atol=1e-4)
