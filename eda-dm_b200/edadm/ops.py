@@ -342,6 +342,40 @@ def act_quant_nhwc(x, aq: ActQuant, pad: int, want_chsum=False):
     return q, chsum
 
 
+def gn_fold(x, gamma, beta, groups, eps, scale=None, shift=None):
+    """GroupNorm statistics of x [B,C,...] folded into per-(sample, channel) affine (a, s), both [B, C]."""
+    _need_cuda(x)
+    x = _f32c(x)
+    B, C = x.shape[0], x.shape[1]
+    HW = x.numel() // (B * C)
+    a = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    s = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    g = None if gamma is None else _f32c(gamma.detach())
+    b = None if beta is None else _f32c(beta.detach())
+    sc = None if scale is None else _f32c(scale.detach()).reshape(B, C)
+    sh = None if shift is None else _f32c(shift.detach()).reshape(B, C)
+    lib.gn_fold(x.data_ptr(), _ptr(g), _ptr(b), _ptr(sc), _ptr(sh), B, C, HW, int(groups), float(eps), a.data_ptr(), s.data_ptr(),
+                _stream())
+    return a, s
+
+
+def norm_act_quant_nhwc(x, aff_a, aff_s, silu, aq: ActQuant, pad: int, want_chsum=False):
+    """silu(a*x+s) -> u8 codes [B,H+2p,W+2p,Cp] in one pass (GroupNorm + SiLU + activation quantizer)."""
+    _need_cuda(x)
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    Cp = _round_up(C, 16)
+    q = torch.empty((B, H + 2 * pad, W + 2 * pad, Cp), dtype=torch.uint8, device=x.device)
+    chsum = torch.empty((B, H + 2 * pad, W + 2 * pad), dtype=torch.int32, device=x.device) if want_chsum else None
+    dev = x.device
+    d0, z0 = _qparam(aq.delta0, dev), _qparam(aq.zp0, dev)
+    d1 = _qparam(aq.delta1, dev) if aq.split else None
+    z1 = _qparam(aq.zp1, dev) if aq.split else None
+    lib.norm_act_quant_nhwc(x.data_ptr(), aff_a.data_ptr(), aff_s.data_ptr(), 1 if silu else 0, q.data_ptr(), _ptr(chsum), B, C, H, W,
+                            Cp, pad, d0.data_ptr(), z0.data_ptr(), aq.levels0, aq.split, _ptr(d1), _ptr(z1), aq.levels1, _stream())
+    return q, chsum
+
+
 def act_quant_rows(x2d, aq: ActQuant, want_rowsum=False):
     """x fp32 [M,K] -> u8 codes [M,Kp]."""
     _need_cuda(x2d)

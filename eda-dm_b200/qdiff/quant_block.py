@@ -75,6 +75,13 @@ def nonlinearity(x):
     return x * th.sigmoid(x)
 
 
+def _prenorm_ok(conv, block):
+    """GroupNorm -> SiLU -> (dropout) -> conv may be fused when the conv is a QuantModule and dropout is inactive."""
+    drop = getattr(block, 'dropout', None)
+    p_drop = drop.p if isinstance(drop, nn.Dropout) else (drop or 0.0)
+    return isinstance(conv, QuantModule) and (not block.training or p_drop == 0)
+
+
 class BaseQuantBlock(nn.Module):
     """Common state of all quantized blocks (reference quant_block.py:20-43)."""
 
@@ -120,7 +127,33 @@ class QuantResBlock(BaseQuantBlock, *_TimestepBases):
         assert x.shape[2] == x.shape[3]
         if split != 0:
             self.split = split
-        return _zoo_ldm.resblock_forward(self, x, emb, self.split if split != 0 else 0)
+        return _quant_resblock_forward(self, x, emb, self.split if split != 0 else 0)
+
+
+def _quant_resblock_forward(blk, x, emb, split=0):
+    """Dataflow of the LDM ResBlock (reference quant_block.py:86-116) with GroupNorm + SiLU folded into the activation
+    producer of the following QuantModule wherever nothing sits in between (no resampling, inactive dropout)."""
+    in_conv, out_conv = blk.in_layers[-1], blk.out_layers[-1]
+    fuse = _prenorm_ok(in_conv, blk) and _prenorm_ok(out_conv, blk)
+    if not fuse:
+        return _zoo_ldm.resblock_forward(blk, x, emb, split)
+    if blk.updown:
+        h = blk.in_layers[:-1](x)
+        h, x = blk.h_upd(h), blk.x_upd(x)
+        h = in_conv(h)
+    else:
+        h = in_conv.forward_prenorm(x, blk.in_layers[0])
+    emb_out = blk.emb_layers(emb).type(h.dtype)
+    while emb_out.dim() < h.dim():
+        emb_out = emb_out[..., None]
+    if blk.use_scale_shift_norm:
+        scale, shift = th.chunk(emb_out, 2, dim=1)
+        h = out_conv.forward_prenorm(h, blk.out_layers[0], scale=scale, shift=shift)
+    else:
+        h = out_conv.forward_prenorm(h + emb_out, blk.out_layers[0])
+    if split and not isinstance(blk.skip_connection, nn.Identity):
+        return blk.skip_connection(x, split=split) + h
+    return blk.skip_connection(x) + h
 
 
 # ---- LDM attention: the two matmuls -----------------------------------------------------------------------
@@ -266,9 +299,14 @@ class QuantResnetBlock(BaseQuantBlock):
     def forward(self, x, temb=None, split=0):
         if split != 0:
             self.split = split
-        h = self.conv1(nonlinearity(self.norm1(x)))
-        h = h + self.temb_proj(nonlinearity(temb))[:, :, None, None]
-        h = self.conv2(self.dropout(nonlinearity(self.norm2(h))))
+        if _prenorm_ok(self.conv1, self) and _prenorm_ok(self.conv2, self):
+            h = self.conv1.forward_prenorm(x, self.norm1, act_fn=nonlinearity)
+            h = h + self.temb_proj(nonlinearity(temb))[:, :, None, None]
+            h = self.conv2.forward_prenorm(h, self.norm2, act_fn=nonlinearity)
+        else:
+            h = self.conv1(nonlinearity(self.norm1(x)))
+            h = h + self.temb_proj(nonlinearity(temb))[:, :, None, None]
+            h = self.conv2(self.dropout(nonlinearity(self.norm2(h))))
         if self.in_channels != self.out_channels:
             x = self.conv_shortcut(x) if self.use_conv_shortcut else self.nin_shortcut(x, split=self.split)
         return x + h

@@ -29,6 +29,7 @@ class _Backend:
     """Process-wide knobs of the calibration path (defaults reproduce the reference's fp32 numerics)."""
     allow_tf32 = False       # library conv/matmul of the calibration path in strict fp32
     integer_path = True      # use the tcgen05 int8 GEMM whenever it applies
+    fuse_norm = True         # GroupNorm + SiLU + activation quantizer as one producer pass on the integer path
     recon_cuda_graph = True  # capture the reconstruction iteration in one CUDA graph after 3 eager iterations
     qdrop_inkernel_rng = False  # False: QDrop masks come from torch.rand_like (the reference's stream, graph-safe);
                                 # True: drawn inside the kernel (Philox4x32, no extra memory pass)
@@ -358,7 +359,28 @@ class QuantModule(nn.Module):
         self._packed = (key, packs)
         return packs
 
-    def _forward_int8(self, input):
+    def forward_prenorm(self, x, norm, silu: bool = True, scale=None, shift=None, split: int = 0, act_fn=F.silu):
+        """`self(silu(norm(x) [* (1 + scale) + shift]))` for a GroupNorm `norm` in front of this conv.  On the integer
+        path GroupNorm + conditioning + SiLU + activation quantization run as ONE producer pass (edadm_gn_fold +
+        edadm_norm_act_quant_nhwc); otherwise it is computed module by module like the reference does."""
+        if split != 0 and self.split == 0:
+            self.split = split
+            self.set_split()
+        fusable = (backend.fuse_norm and isinstance(norm, nn.GroupNorm) and self.fwd_func is F.conv2d and x.dim() == 4
+                   and self._integer_path_ok(x) and not self._forward_hooks and not self._forward_pre_hooks
+                   and not norm._forward_hooks)
+        if not fusable:
+            h = norm(x)
+            if scale is not None:
+                h = h * (1 + scale) + shift
+            if silu:
+                h = act_fn(h)      # the block's own formulation of swish (x*sigmoid(x) in the DDIM UNet, nn.SiLU in LDM)
+            return self(h, split=split) if split else self(h)
+        self.last_path = 'int8'
+        a, s = ops.gn_fold(x, norm.weight, norm.bias, norm.num_groups, norm.eps, scale, shift)
+        return self.activation_function(self._forward_int8(x, affine=(a, s, silu)))
+
+    def _forward_int8(self, input, affine=None):
         """Exact integer GEMM: out = dA*dW[n]*sum (qa-za)(qw-zw) + bias  == the reference's fp32 conv of the
         dequantised tensors (quant_layer.py:414-434) without its per-product rounding."""
         packs = self._packed_weights()
@@ -390,7 +412,10 @@ class QuantModule(nn.Module):
             raise EdadmError("conv1d with padding is not supported on the integer path")
         Ho = (H + 2 * pad_h - R) // stride + 1
         Wo = (W + 2 * pad - S) // stride + 1
-        q, chsum = ops.act_quant_nhwc(x4, aq, pad, want_chsum=needs_rowsum)
+        if affine is not None:
+            q, chsum = ops.norm_act_quant_nhwc(x4, affine[0], affine[1], affine[2], aq, pad, want_chsum=needs_rowsum)
+        else:
+            q, chsum = ops.act_quant_nhwc(x4, aq, pad, want_chsum=needs_rowsum)
         rowsum = ops.conv_rowsum(chsum, Ho, Wo, R, S, stride) if needs_rowsum else None
         out = torch.empty((B, N, Ho, Wo), dtype=torch.float32, device=input.device)
         if stride == 1 and _implicit_tiling_ok(B, Ho, Wo):

@@ -336,3 +336,33 @@ def test_qattn_cross_layout(cuda, B, heads, d, Tq, Tk):
     out = ops.qattn_bnd(sp(q).contiguous().to(cuda), sp(k).contiguous().to(cuda), sp(v).contiguous().to(cuda), heads,
                         _to_aquant(cuda, qp), scale)
     assert _rel_l2(out.cpu(), ref) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,C,H,scale_shift", [(3, 64, 16, False), (2, 192, 8, True), (2, 96, 4, False)])
+def test_groupnorm_silu_quant_producer(cuda, B, C, H, scale_shift):
+    """GroupNorm (+ scale-shift) + SiLU + quantize in one pass vs the module-by-module path: the codes agree except where
+    silu(gn(x))/delta lands within an ulp of a .5 boundary (different-order fp32 arithmetic in GroupNorm itself)."""
+    from edadm import ops
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, C, H, H, generator=g) * 2 + 0.3
+    gn = torch.nn.GroupNorm(32, C, eps=1e-5)
+    gn.weight.data = torch.randn(C, generator=g) * 0.5 + 1
+    gn.bias.data = torch.randn(C, generator=g) * 0.2
+    scale = torch.randn(B, C, 1, 1, generator=g) * 0.3 if scale_shift else None
+    shift = torch.randn(B, C, 1, 1, generator=g) * 0.3 if scale_shift else None
+    with torch.no_grad():
+        h = gn(x)
+        if scale_shift:
+            h = h * (1 + scale) + shift
+        h = F.silu(h)
+    d, z = _act_params(h)
+    ref_codes = O.uaq_codes(h, d, z, 256).permute(0, 2, 3, 1)
+    gn = gn.to(cuda)
+    a, s = ops.gn_fold(x.to(cuda), gn.weight, gn.bias, 32, gn.eps, None if scale is None else scale.to(cuda),
+                       None if shift is None else shift.to(cuda))
+    q, _ = ops.norm_act_quant_nhwc(x.to(cuda), a, s, True, ops.ActQuant(d.to(cuda), z.to(cuda), 256), 1)
+    codes = q.cpu()[:, 1:-1, 1:-1, :C].float()
+    diff = (codes - ref_codes).abs()
+    assert float(diff.max()) <= 1.0                                   # never more than one code step
+    assert float((diff > 0).float().mean()) < 2e-3                    # and only at rounding boundaries
