@@ -23,6 +23,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// d = (c << 16) | (sat_u8(a) << 8) | sat_u8(b)
+__device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c) {
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 constexpr int ATT_M = 128;
 constexpr int ATT_S = 128;
 constexpr int ATT_KB = 128;
@@ -67,7 +74,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   uint8_t* smem_p = smem_v + V_STAGES * V_TILE_BYTES;
   AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem_p + 2 * ATT_TILE_BYTES);
 
-  __shared__ int colint[2][ATT_S];          // zq * (code sum of key s) for the S tile in each TMEM buffer
+  __shared__ __align__(16) int colint[2][ATT_S];          // zq * (code sum of key s) for the S tile in each TMEM buffer
   __shared__ float stat_m[2][ATT_M], stat_l[2][ATT_M];
   __shared__ int stat_rp[2][ATT_M];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -182,6 +189,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     const int row_const = p.d * zq * zk - (row_ok ? zk * __ldg(p.rq + (size_t)bh * p.Tq + t) : 0);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int col_base = half * 64;
+    const float rc_a = (float)row_const * alpha, rc_a2 = (float)row_const * alpha2;   // row constant folded into the FMA
 
     float m = -INFINITY, l = 0.f;     // m in units of x = S*alpha (natural domain), l = sum 2^((x-m)*log2e)
     int g = 0;
@@ -200,20 +208,40 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
           uint32_t raw[32];
           tmem_ld32(lane_addr + (uint32_t)sb * ATT_S + c0, raw);
           tmem_ld_wait();
-          float x[32];
-          float cmax = -INFINITY;
+          const int4* cv = reinterpret_cast<const int4*>(&colint[sb][c0]);
+          int v[32];
+          if (s0 + 32 <= p.Tk) {
+            // full chunk: integer max first (2 instructions / score), then one FMA + ex2 + add per score
+            int vmax = INT_MIN;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            x[i] = (s0 + i < p.Tk) ? (float)((int)raw[i] + row_const - colint[sb][c0 + i]) : -INFINITY;
-            cmax = fmaxf(cmax, x[i]);
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const int4 c4 = cv[q4];
+              v[4 * q4 + 0] = (int)raw[4 * q4 + 0] - c4.x; v[4 * q4 + 1] = (int)raw[4 * q4 + 1] - c4.y;
+              v[4 * q4 + 2] = (int)raw[4 * q4 + 2] - c4.z; v[4 * q4 + 3] = (int)raw[4 * q4 + 3] - c4.w;
+              vmax = max(max(max(vmax, v[4 * q4 + 0]), max(v[4 * q4 + 1], v[4 * q4 + 2])), v[4 * q4 + 3]);
+            }
+            const float m_new = fmaxf(m, fmaf((float)vmax, alpha, rc_a));
+            const float cexp = rc_a2 - m_new * 1.4426950408889634f;
+            float add = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) add += ex2_approx(fmaf((float)v[i], alpha2, cexp));
+            l = l * ex2_approx((m - m_new) * 1.4426950408889634f) + add;
+            m = m_new;
+          } else {
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              v[i] = (int)raw[i] - colint[sb][c0 + i];
+              if (s0 + i < p.Tk) cmax = fmaxf(cmax, fmaf((float)v[i], alpha, rc_a));
+            }
+            const float m_new = fmaxf(m, cmax);
+            const float cexp = rc_a2 - m_new * 1.4426950408889634f;
+            float add = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) add += (s0 + i < p.Tk) ? ex2_approx(fmaf((float)v[i], alpha2, cexp)) : 0.f;
+            l = l * ex2_approx((m - m_new) * 1.4426950408889634f) + add;
+            m = m_new;
           }
-          const float m_new = fmaxf(m, cmax * alpha);
-          const float mb = m_new * 1.4426950408889634f;
-          float add = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) add += ex2_approx(fmaf(x[i], alpha2, -mb));
-          l = l * ex2_approx((m - m_new) * 1.4426950408889634f) + add;
-          m = m_new;
         }
       }
       tc_fence_before();
@@ -233,7 +261,9 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     const float dpq = __ldg(p.dpq), zpq = __ldg(p.zpq);
     const float qmax = (float)(p.p_levels - 1);
     const float kq = (1.0f / l) / dpq;            // code = rint(2^((x-m)log2e) * kq) + zP
-    const float mb = m * 1.4426950408889634f;
+    const float cexp2 = rc_a2 - m * 1.4426950408889634f;
+    const int zp_i = (int)zpq;
+    const bool fast_codes = p.p_levels == 256;
     int rp = 0;
     for (int j = 0; j < p.s_tiles; ++j, ++g) {
       const int sb = g & 1, pb = j & 1;
@@ -252,14 +282,30 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
           uint32_t raw[32];
           tmem_ld32(lane_addr + (uint32_t)sb * ATT_S + c0, raw);
           tmem_ld_wait();
+          const int4* cv = reinterpret_cast<const int4*>(&colint[sb][c0]);
+          if (fast_codes && s0 + 32 <= p.Tk) {
+            // full chunk, 8-bit codes: FMA + ex2 + mul + cvt.rni per score, saturating pack 2 codes / instruction
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = (float)((int)raw[i] + row_const - colint[sb][c0 + i]);
-            const float e = ex2_approx(fmaf(x, alpha2, -mb));
-            uint32_t code = (uint32_t)fminf(fmaxf(rintf(e * kq) + zpq, 0.f), qmax);
-            code = (s0 + i < p.Tk) ? code : 0u;
-            rp += (int)code;
-            packed[i >> 2] |= code << (8 * (i & 3));
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const int4 c4 = cv[q4];
+              const int k0 = __float2int_rn(ex2_approx(fmaf((float)((int)raw[4 * q4 + 0] - c4.x), alpha2, cexp2)) * kq) + zp_i;
+              const int k1 = __float2int_rn(ex2_approx(fmaf((float)((int)raw[4 * q4 + 1] - c4.y), alpha2, cexp2)) * kq) + zp_i;
+              const int k2 = __float2int_rn(ex2_approx(fmaf((float)((int)raw[4 * q4 + 2] - c4.z), alpha2, cexp2)) * kq) + zp_i;
+              const int k3 = __float2int_rn(ex2_approx(fmaf((float)((int)raw[4 * q4 + 3] - c4.w), alpha2, cexp2)) * kq) + zp_i;
+              const uint32_t w = pack_sat_u8(k1, k0, pack_sat_u8(k3, k2, 0u));
+              packed[q4] = w;
+              rp = (int)__dp4a(w, 0x01010101u, (unsigned)rp);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float x = (float)((int)raw[i] - colint[sb][c0 + i]);
+              const float e = ex2_approx(fmaf(x, alpha2, cexp2));
+              uint32_t code = (uint32_t)fminf(fmaxf(rintf(e * kq) + zpq, 0.f), qmax);
+              code = (s0 + i < p.Tk) ? code : 0u;
+              rp += (int)code;
+              packed[i >> 2] |= code << (8 * (i & 3));
+            }
           }
         }
         const int chunk = c0 >> 4;  // two 16-byte chunks per 32 columns, XOR-swizzled by the row (SWIZZLE_128B)
@@ -277,7 +323,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     rp += stat_rp[half ^ 1][r];
     mbar_wait(&bars->o_full, 0);
     tc_fence_after();
-    const int zv = (int)__ldg(p.zv), zp_i = (int)zpq;
+    const int zv = (int)__ldg(p.zv);
     const float oscale = dpq * __ldg(p.dv);
     const int32_t* rv = p.rv + (size_t)bh * p.d;
     const int b = bh / p.heads, h = bh - b * p.heads;
