@@ -12,7 +12,7 @@
 //
 // Zero-points are folded with the code sums (rq, rk, rv, and the running row sum of Pq), so operands stay raw u8.
 // One CTA = 128 queries x one chunk (<=256) of the head dim of one (batch, head).  Warp roles: 0 TMA producer,
-// 1 MMA issuer, 2..9 softmax + epilogue (two threads per query row == TMEM lane, 64 key columns each).
+// 1 MMA issuer, 2..17 softmax + epilogue (four threads per query row == TMEM lane, 32 key columns each).
 #include "tc05.cuh"
 
 namespace edadm {
@@ -24,6 +24,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // d = (c << 16) | (sat_u8(a) << 8) | sat_u8(b)
+constexpr int MAGIC_I = 0x4B400000;          // bit pattern of 12582912.0f = 1.5 * 2^23
+constexpr float MAGIC_F = 12582912.0f;
+
+// exact (float)v for a biased integer b = v + BIAS (BIAS = MAGIC_I when SMALL, else 0)
+template <bool SMALL>
+__device__ __forceinline__ float biased_to_float(int b) {
+  return SMALL ? (__int_as_float(b) - MAGIC_F) : (float)b;
+}
+
+// rint(t) for 0 <= t < 2^22 without the XU pipe: the add rounds to nearest-even, the low mantissa bits are the integer
+__device__ __forceinline__ int rint_magic(float t) { return __float_as_int(t + MAGIC_F) - MAGIC_I; }
+
 __device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c) {
   uint32_t d;
   asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -37,7 +49,10 @@ constexpr int QK_STAGES = 3;
 constexpr int V_STAGES = 2;
 constexpr int ATT_TILE_BYTES = 128 * 128;       // 16 KB: Q chunk, K chunk, P tile
 constexpr int V_TILE_BYTES = 256 * 128;         // 32 KB
-constexpr int ATT_THREADS = 320;            // TMA warp + MMA warp + 8 softmax warps
+constexpr int SM_PARTS = 4;                 // softmax threads per query row
+constexpr int SM_COLS = ATT_S / SM_PARTS;   // key columns of a tile per softmax thread
+constexpr int SM_WARPS = 4 * SM_PARTS;
+constexpr int ATT_THREADS = 64 + 32 * SM_WARPS;   // TMA warp + MMA warp + 16 softmax warps
 constexpr int ATT_TMEM_COLS = 512;              // S0 [0,128) S1 [128,256) O [256,512)
 
 struct AttnParams {
@@ -63,6 +78,10 @@ struct __align__(8) AttnBarriers {
 
 constexpr int ATT_SMEM_BYTES = 1024 + QK_STAGES * 2 * ATT_TILE_BYTES + V_STAGES * V_TILE_BYTES + 2 * ATT_TILE_BYTES + 256;
 
+// SMALL_V: |raw - zq*rk| < 2^22 (head dim <= 64), so int -> float goes through the exact magic-number add instead of I2F.
+// The softmax is bound by the 16-op/clk XU pipe (ex2, I2F, F2I); with the conversions moved to the ALU/FMA pipes only the
+// two ex2 per score remain there.
+template <bool SMALL_V>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
              const __grid_constant__ CUtensorMap map_v, AttnParams p) {
@@ -75,8 +94,8 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem_p + 2 * ATT_TILE_BYTES);
 
   __shared__ __align__(16) int colint[2][ATT_S];          // zq * (code sum of key s) for the S tile in each TMEM buffer
-  __shared__ float stat_m[2][ATT_M], stat_l[2][ATT_M];
-  __shared__ int stat_rp[2][ATT_M];
+  __shared__ float stat_m[SM_PARTS][ATT_M], stat_l[SM_PARTS][ATT_M];
+  __shared__ int stat_rp[SM_PARTS][ATT_M];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * ATT_M;
   const int dc = blockIdx.y;
@@ -87,8 +106,8 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     for (int i = 0; i < QK_STAGES; ++i) { mbar_init(&bars->qk_full[i], 1); mbar_init(&bars->qk_empty[i], 1); }
     for (int i = 0; i < V_STAGES; ++i) { mbar_init(&bars->v_full[i], 1); mbar_init(&bars->v_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], 8);
-      mbar_init(&bars->p_full[i], 8); mbar_init(&bars->p_empty[i], 1);
+      mbar_init(&bars->s_full[i], 1); mbar_init(&bars->s_empty[i], SM_WARPS);
+      mbar_init(&bars->p_full[i], SM_WARPS); mbar_init(&bars->p_empty[i], 1);
     }
     mbar_init(&bars->o_full, 1);
     fence_barrier_init();
@@ -173,22 +192,24 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       umma_commit(&bars->o_full);
     }
   } else {
-    // ===================== softmax + epilogue (warps 2..9) =====================
-    // Two threads per query row: warps w and w+4 share a TMEM lane quarter and split every 128-key tile into two
-    // halves of 64 columns.  Row statistics and the code row-sum are merged through shared memory.
+    // ===================== softmax + epilogue (warps 2..17) =====================
+    // Four threads per query row: warps w, w+4, w+8, w+12 share a TMEM lane quarter and split every 128-key tile into
+    // four parts of 32 columns (two 16-column TMEM loads each).  16 warps = 4 per scheduler, which is what hides the
+    // TMEM / MUFU / dependent-issue latencies of the softmax math.  Row statistics and the code row-sum are merged
+    // through shared memory.
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;           // 0..3
     const int r = quarter * 32 + lane;
     const int t = q0 + r;
     const bool row_ok = t < p.Tq;
-    const int st = threadIdx.x - 64;            // 0..255 among the softmax threads
+    const int st = threadIdx.x - 64;            // 0..511 among the softmax threads
     const int zq = (int)__ldg(p.zq), zk = (int)__ldg(p.zk);
     const float alpha = __ldg(p.dq) * __ldg(p.dk) * p.sm_scale;
     const float alpha2 = alpha * 1.4426950408889634f;   // to the base-2 exponent domain
     const int32_t* rk = p.rk + (size_t)bh * p.Tk;
     const int row_const = p.d * zq * zk - (row_ok ? zk * __ldg(p.rq + (size_t)bh * p.Tq + t) : 0);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int col_base = half * 64;
+    const int col_base = part * SM_COLS;
     const float rc_a = (float)row_const * alpha, rc_a2 = (float)row_const * alpha2;   // row constant folded into the FMA
 
     float m = -INFINITY, l = 0.f;     // m in units of x = S*alpha (natural domain), l = sum 2^((x-m)*log2e)
@@ -196,49 +217,49 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     // ---- pass 1: row max and sum ----
     for (int j = 0; j < p.s_tiles; ++j, ++g) {
       const int sb = g & 1;
-      if (st < ATT_S) { const int s = j * ATT_S + st; colint[sb][st] = s < p.Tk ? zq * __ldg(rk + s) : 0; }
+      if (st < ATT_S) { const int s = j * ATT_S + st; colint[sb][st] = (SMALL_V ? MAGIC_I : 0) - (s < p.Tk ? zq * __ldg(rk + s) : 0); }
       mbar_wait(&bars->s_full[sb], (uint32_t)((g >> 1) & 1));
       tc_fence_after();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c0 = col_base + cc * 32;
+      for (int cc = 0; cc < SM_COLS / 16; ++cc) {
+        const int c0 = col_base + cc * 16;
         const int s0 = j * ATT_S + c0;
         if (s0 < p.Tk) {
-          uint32_t raw[32];
-          tmem_ld32(lane_addr + (uint32_t)sb * ATT_S + c0, raw);
+          uint32_t raw[16];
+          tmem_ld16(lane_addr + (uint32_t)sb * ATT_S + c0, raw);
           tmem_ld_wait();
           const int4* cv = reinterpret_cast<const int4*>(&colint[sb][c0]);
-          int v[32];
-          if (s0 + 32 <= p.Tk) {
+          int v[16];
+          if (s0 + 16 <= p.Tk) {
             // full chunk: integer max first (2 instructions / score), then one FMA + ex2 + add per score
             int vmax = INT_MIN;
 #pragma unroll
-            for (int q4 = 0; q4 < 8; ++q4) {
+            for (int q4 = 0; q4 < 4; ++q4) {
               const int4 c4 = cv[q4];
-              v[4 * q4 + 0] = (int)raw[4 * q4 + 0] - c4.x; v[4 * q4 + 1] = (int)raw[4 * q4 + 1] - c4.y;
-              v[4 * q4 + 2] = (int)raw[4 * q4 + 2] - c4.z; v[4 * q4 + 3] = (int)raw[4 * q4 + 3] - c4.w;
+              v[4 * q4 + 0] = (int)raw[4 * q4 + 0] + c4.x; v[4 * q4 + 1] = (int)raw[4 * q4 + 1] + c4.y;
+              v[4 * q4 + 2] = (int)raw[4 * q4 + 2] + c4.z; v[4 * q4 + 3] = (int)raw[4 * q4 + 3] + c4.w;
               vmax = max(max(max(vmax, v[4 * q4 + 0]), max(v[4 * q4 + 1], v[4 * q4 + 2])), v[4 * q4 + 3]);
             }
-            const float m_new = fmaxf(m, fmaf((float)vmax, alpha, rc_a));
+            const float m_new = fmaxf(m, fmaf(biased_to_float<SMALL_V>(vmax), alpha, rc_a));
             const float cexp = rc_a2 - m_new * 1.4426950408889634f;
             float add = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) add += ex2_approx(fmaf((float)v[i], alpha2, cexp));
+            for (int i = 0; i < 16; ++i) add += ex2_approx(fmaf(biased_to_float<SMALL_V>(v[i]), alpha2, cexp));
             l = l * ex2_approx((m - m_new) * 1.4426950408889634f) + add;
             m = m_new;
           } else {
             float cmax = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              v[i] = (int)raw[i] - colint[sb][c0 + i];
-              if (s0 + i < p.Tk) cmax = fmaxf(cmax, fmaf((float)v[i], alpha, rc_a));
+            for (int i = 0; i < 16; ++i) {
+              v[i] = (int)raw[i] + colint[sb][c0 + i];
+              if (s0 + i < p.Tk) cmax = fmaxf(cmax, fmaf(biased_to_float<SMALL_V>(v[i]), alpha, rc_a));
             }
             const float m_new = fmaxf(m, cmax);
             const float cexp = rc_a2 - m_new * 1.4426950408889634f;
             float add = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) add += (s0 + i < p.Tk) ? ex2_approx(fmaf((float)v[i], alpha2, cexp)) : 0.f;
+            for (int i = 0; i < 16; ++i) add += (s0 + i < p.Tk) ? ex2_approx(fmaf(biased_to_float<SMALL_V>(v[i]), alpha2, cexp)) : 0.f;
             l = l * ex2_approx((m - m_new) * 1.4426950408889634f) + add;
             m = m_new;
           }
@@ -248,14 +269,20 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
     }
-    // merge the two column halves of every row
-    stat_m[half][r] = m; stat_l[half][r] = l;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // merge the column parts of every row
+    stat_m[part][r] = m; stat_l[part][r] = l;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
     {
-      const float mo = stat_m[half ^ 1][r], lo = stat_l[half ^ 1][r];
-      const float mm = fmaxf(m, mo);
-      l = l * ex2_approx((m - mm) * 1.4426950408889634f) + lo * ex2_approx((mo - mm) * 1.4426950408889634f);
-      m = mm;
+      float mm = m;
+#pragma unroll
+      for (int o = 0; o < SM_PARTS; ++o) mm = fmaxf(mm, stat_m[o][r]);
+      float ll = 0.f;
+#pragma unroll
+      for (int o = 0; o < SM_PARTS; ++o) {
+        const float mo = stat_m[o][r];
+        ll += (mo == -INFINITY) ? 0.f : stat_l[o][r] * ex2_approx((mo - mm) * 1.4426950408889634f);
+      }
+      m = mm; l = ll;
     }
     // ---- pass 2: normalised probabilities -> codes -> smem (A operand of the P.V MMA) ----
     const float dpq = __ldg(p.dpq), zpq = __ldg(p.zpq);
@@ -267,39 +294,39 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     int rp = 0;
     for (int j = 0; j < p.s_tiles; ++j, ++g) {
       const int sb = g & 1, pb = j & 1;
-      if (st < ATT_S) { const int s = j * ATT_S + st; colint[sb][st] = s < p.Tk ? zq * __ldg(rk + s) : 0; }
+      if (st < ATT_S) { const int s = j * ATT_S + st; colint[sb][st] = (SMALL_V ? MAGIC_I : 0) - (s < p.Tk ? zq * __ldg(rk + s) : 0); }
       mbar_wait(&bars->s_full[sb], (uint32_t)((g >> 1) & 1));
       mbar_wait(&bars->p_empty[pb], (uint32_t)(((j >> 1) & 1) ^ 1));
       tc_fence_after();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       uint8_t* prow = smem_p + pb * ATT_TILE_BYTES + r * 128;
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c0 = col_base + cc * 32;
+      for (int cc = 0; cc < SM_COLS / 16; ++cc) {
+        const int c0 = col_base + cc * 16;
         const int s0 = j * ATT_S + c0;
-        uint32_t packed[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t packed[4] = {0, 0, 0, 0};
         if (s0 < p.Tk) {
-          uint32_t raw[32];
-          tmem_ld32(lane_addr + (uint32_t)sb * ATT_S + c0, raw);
+          uint32_t raw[16];
+          tmem_ld16(lane_addr + (uint32_t)sb * ATT_S + c0, raw);
           tmem_ld_wait();
           const int4* cv = reinterpret_cast<const int4*>(&colint[sb][c0]);
-          if (fast_codes && s0 + 32 <= p.Tk) {
+          if (fast_codes && s0 + 16 <= p.Tk) {
             // full chunk, 8-bit codes: FMA + ex2 + mul + cvt.rni per score, saturating pack 2 codes / instruction
 #pragma unroll
-            for (int q4 = 0; q4 < 8; ++q4) {
+            for (int q4 = 0; q4 < 4; ++q4) {
               const int4 c4 = cv[q4];
-              const int k0 = __float2int_rn(ex2_approx(fmaf((float)((int)raw[4 * q4 + 0] - c4.x), alpha2, cexp2)) * kq) + zp_i;
-              const int k1 = __float2int_rn(ex2_approx(fmaf((float)((int)raw[4 * q4 + 1] - c4.y), alpha2, cexp2)) * kq) + zp_i;
-              const int k2 = __float2int_rn(ex2_approx(fmaf((float)((int)raw[4 * q4 + 2] - c4.z), alpha2, cexp2)) * kq) + zp_i;
-              const int k3 = __float2int_rn(ex2_approx(fmaf((float)((int)raw[4 * q4 + 3] - c4.w), alpha2, cexp2)) * kq) + zp_i;
+              const int k0 = rint_magic(ex2_approx(fmaf(biased_to_float<SMALL_V>((int)raw[4 * q4 + 0] + c4.x), alpha2, cexp2)) * kq) + zp_i;
+              const int k1 = rint_magic(ex2_approx(fmaf(biased_to_float<SMALL_V>((int)raw[4 * q4 + 1] + c4.y), alpha2, cexp2)) * kq) + zp_i;
+              const int k2 = rint_magic(ex2_approx(fmaf(biased_to_float<SMALL_V>((int)raw[4 * q4 + 2] + c4.z), alpha2, cexp2)) * kq) + zp_i;
+              const int k3 = rint_magic(ex2_approx(fmaf(biased_to_float<SMALL_V>((int)raw[4 * q4 + 3] + c4.w), alpha2, cexp2)) * kq) + zp_i;
               const uint32_t w = pack_sat_u8(k1, k0, pack_sat_u8(k3, k2, 0u));
               packed[q4] = w;
               rp = (int)__dp4a(w, 0x01010101u, (unsigned)rp);
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float x = (float)((int)raw[i] - colint[sb][c0 + i]);
+            for (int i = 0; i < 16; ++i) {
+              const float x = biased_to_float<SMALL_V>((int)raw[i] + colint[sb][c0 + i]);
               const float e = ex2_approx(fmaf(x, alpha2, cexp2));
               uint32_t code = (uint32_t)fminf(fmaxf(rintf(e * kq) + zpq, 0.f), qmax);
               code = (s0 + i < p.Tk) ? code : 0u;
@@ -308,19 +335,20 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             }
           }
         }
-        const int chunk = c0 >> 4;  // two 16-byte chunks per 32 columns, XOR-swizzled by the row (SWIZZLE_128B)
-        *reinterpret_cast<uint4*>(prow + (((chunk) ^ (r & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        *reinterpret_cast<uint4*>(prow + (((chunk + 1) ^ (r & 7)) << 4)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        const int chunk = c0 >> 4;  // one 16-byte chunk per 16 columns, XOR-swizzled by the row (SWIZZLE_128B)
+        *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
       }
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(&bars->p_full[pb]); mbar_arrive(&bars->s_empty[sb]); }
     }
-    // ---- epilogue: O -> fp32 output (the two threads of a row take alternate 16-column groups) ----
-    stat_rp[half][r] = rp;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    rp += stat_rp[half ^ 1][r];
+    // ---- epilogue: O -> fp32 output (the four threads of a row take alternate 16-column groups) ----
+    stat_rp[part][r] = rp;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    rp = 0;
+#pragma unroll
+    for (int o = 0; o < SM_PARTS; ++o) rp += stat_rp[o][r];
     mbar_wait(&bars->o_full, 0);
     tc_fence_after();
     const int zv = (int)__ldg(p.zv);
@@ -329,7 +357,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     const int b = bh / p.heads, h = bh - b * p.heads;
     float* obase = p.out + b * p.o_sb + h * p.o_sh + (long long)t * p.o_st;
     const int row_o = p.Tk * zp_i * zv - zv * rp;
-    for (int c0 = half * 16; c0 < p.d_chunk; c0 += 32) {
+    for (int c0 = part * 16; c0 < p.d_chunk; c0 += 16 * SM_PARTS) {
       uint32_t raw[16];
       tmem_ld16(lane_addr + 256 + c0, raw);
       tmem_ld_wait();
@@ -409,11 +437,16 @@ extern "C" int edadm_qattn_fwd(const uint8_t* qc, const uint8_t* kc, const uint8
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(qattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(qattn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(qattn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
     if (e != cudaSuccess) return fail(EDADM_ERR_CUDA, "qattn_fwd: cannot opt in to %d B shared memory: %s", ATT_SMEM_BYTES, cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((Tq + ATT_M - 1) / ATT_M, d_chunks, BH);
-  qattn_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(map_q, map_k, map_v, p);
+  // |raw - zq*rk| <= 255*255*max(d, dp): the magic-number int->float conversion is exact below 2^22
+  if ((long long)dp * 65025LL < (1LL << 22))
+    qattn_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(map_q, map_k, map_v, p);
+  else
+    qattn_kernel<false><<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(map_q, map_k, map_v, p);
   return check_launch("qattn_fwd");
 }

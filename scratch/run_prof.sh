@@ -1,2 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k qattn 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q 2>&1 | tail -2
+timeout 300 python scratch/bench_attn.py
+timeout 300 python scratch/bench_gemm.py 2>&1 | cut -c1-110
 timeout 900 python bench.py --steps 10 --no-cpu-baseline --no-recon 2>&1 | tail -1 | cut -c1-330
