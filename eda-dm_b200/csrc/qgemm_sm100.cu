@@ -40,6 +40,7 @@ struct GemmParams {
   int Wo, HoWo;             // output row length and pixels per image (2-D GEMM: Wo = HoWo = 2^30)
   int block_n, n_tiles, m_tiles;
   int stages, b_stage_bytes;
+  int row_staging;          // 1: row-major output staged through shared memory for 128-byte coalesced row stores
   // epilogue
   int out_hw;               // pixels per image of the OUTPUT layout (1 => row-major [M][N])
   int accumulate, silu;
@@ -63,6 +64,8 @@ struct __align__(8) PipeBarriers {
 
 constexpr int EPI_VEC_BYTES = MAX_BLOCK_N * 4 * 4;  // scale, zterm, cw, bias per column
 constexpr int SMEM_FIXED = 1024 /*align slack*/ + EPI_VEC_BYTES + 256 /*barriers*/;
+constexpr int ROW_STAGE_LD = 36;                                   // floats per staged row (32 + pad, 16-byte aligned)
+constexpr int ROW_STAGE_BYTES = EPI_WARPS * 32 * ROW_STAGE_LD * 4;  // one 32x32 fp32 tile per epilogue warp
 
 // one 16-column chunk of the epilogue for one output row: int32 zero-point fold, fp32 scale + bias, store
 template <bool GENERIC>
@@ -120,6 +123,7 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   int* epi_cw = epi_zterm + MAX_BLOCK_N;
   float* epi_bias = reinterpret_cast<float*>(epi_cw + MAX_BLOCK_N);
   PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(epi_bias + MAX_BLOCK_N);
+  float* row_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // only when p.row_staging
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -233,6 +237,43 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BLOCK_N;
+      if (p.row_staging) {
+        // row-major output: 32-column chunks; values go through a per-warp 32x32 smem tile so that every store
+        // instruction writes four complete 128-byte row segments instead of 32 scattered 16-byte pieces
+        float* tile_s = row_stage + (warp - 2) * 32 * ROW_STAGE_LD;
+        const int m_base = m_blk * BLOCK_M + quarter * 32;
+        for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          tmem_ld_wait();
+          const int4* zt = reinterpret_cast<const int4*>(epi_zterm + c0);
+          const float4* sc = reinterpret_cast<const float4*>(epi_scale + c0);
+          const float4* bi = reinterpret_cast<const float4*>(epi_bias + c0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int4 z = zt[q]; const float4 s4 = sc[q]; const float4 b4 = bi[q];
+            float4 v;
+            v.x = fmaf((float)((int)r[4 * q + 0] + z.x), s4.x, b4.x);
+            v.y = fmaf((float)((int)r[4 * q + 1] + z.y), s4.y, b4.y);
+            v.z = fmaf((float)((int)r[4 * q + 2] + z.z), s4.z, b4.z);
+            v.w = fmaf((float)((int)r[4 * q + 3] + z.w), s4.w, b4.w);
+            *reinterpret_cast<float4*>(tile_s + lane * ROW_STAGE_LD + 4 * q) = v;
+          }
+          __syncwarp();
+          const int cq = (lane & 7) * 4;                 // 8 lanes x float4 = one 128-byte row segment
+          const int ncol = n0 + c0 + cq;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3);
+            const int mm = m_base + rr;
+            if (mm < p.M && ncol < p.N) {
+              const float4 v = *reinterpret_cast<const float4*>(tile_s + rr * ROW_STAGE_LD + cq);
+              *reinterpret_cast<float4*>(p.out + (long long)mm * p.N + ncol) = v;
+            }
+          }
+          __syncwarp();
+        }
+      } else {
       uint32_t r0[16], r1[16];
       int c0 = half * 16;
       if (c0 < p.block_n) { tmem_ld16(taddr + c0, r0); }
@@ -255,6 +296,7 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           else epilogue_chunk<true>(r1, c1, nv, rs, epi_scale, epi_zterm, epi_cw, epi_bias, out_row + (long long)c1 * col_stride, col_stride, p.accumulate, p.silu);
         }
         tmem_ld_wait();
+      }
       }
       tc_fence_before();
       __syncwarp();
@@ -354,9 +396,13 @@ extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_ac
   p.HoWo = flat ? (1 << 30) : Ho * Wo;
   p.block_n = block_n; p.n_tiles = n_tiles; p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
   p.b_stage_bytes = (block_n * BLOCK_K + 1023) & ~1023;
-  p.stages = (SMEM_LIMIT - SMEM_FIXED) / (A_STAGE_BYTES + p.b_stage_bytes);
+  // row-major outputs (linear layers) are staged through smem; needs whole float4s per row and no rowsum / accumulate / SiLU
+  p.row_staging = (out_hw == 1 && !cw && !accumulate && !silu && (N % 4) == 0 && (block_n % 32) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 1 : 0;
+  const int fixed = SMEM_FIXED + (p.row_staging ? ROW_STAGE_BYTES : 0);
+  p.stages = (SMEM_LIMIT - fixed) / (A_STAGE_BYTES + p.b_stage_bytes);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-  const int smem_bytes = SMEM_FIXED + p.stages * (A_STAGE_BYTES + p.b_stage_bytes);
+  const int smem_bytes = fixed + p.stages * (A_STAGE_BYTES + p.b_stage_bytes);
   p.out_hw = out_hw; p.accumulate = accumulate; p.silu = silu;
   p.delta_a = delta_a; p.zp_a = zp_a; p.delta_w = delta_w; p.wsum_eff = wsum_eff; p.cw = cw; p.rowsum = rowsum;
   p.bias = bias; p.out = out;
