@@ -325,10 +325,20 @@ class ActQuant:
         self.prescale = float(prescale)
 
 
+def _batch_strided(x):
+    """(tensor, batch stride) for a 4-D fp32 view whose samples are dense but spaced apart (q/k/v slices of one tensor)."""
+    if x.dtype == torch.float32 and not x.is_contiguous() and x.dim() == 4:
+        B, C, H, W = x.shape
+        sb, sc, sh, sw = x.stride()
+        if sw == 1 and (H == 1 or sh == W) and sc == H * W and sb >= C * H * W:
+            return x, sb
+    return _f32c(x), 0
+
+
 def act_quant_nhwc(x, aq: ActQuant, pad: int, want_chsum=False):
     """x fp32 [B,C,H,W] -> u8 codes [B,H+2p,W+2p,Cp] (halo = zero-point code)."""
     _need_cuda(x)
-    x = _f32c(x)
+    x, bstride = _batch_strided(x)
     B, C, H, W = x.shape
     Cp = _round_up(C, 16)
     q = torch.empty((B, H + 2 * pad, W + 2 * pad, Cp), dtype=torch.uint8, device=x.device)
@@ -338,7 +348,7 @@ def act_quant_nhwc(x, aq: ActQuant, pad: int, want_chsum=False):
     d1 = _qparam(aq.delta1, dev) if aq.split else None
     z1 = _qparam(aq.zp1, dev) if aq.split else None
     lib.act_quant_nhwc(x.data_ptr(), q.data_ptr(), _ptr(chsum), B, C, H, W, Cp, pad, d0.data_ptr(), z0.data_ptr(),
-                       aq.levels0, aq.split, _ptr(d1), _ptr(z1), aq.levels1, aq.prescale, _stream())
+                       aq.levels0, aq.split, _ptr(d1), _ptr(z1), aq.levels1, aq.prescale, int(bstride), _stream())
     return q, chsum
 
 
@@ -376,10 +386,12 @@ def norm_act_quant_nhwc(x, aff_a, aff_s, silu, aq: ActQuant, pad: int, want_chsu
     return q, chsum
 
 
-def act_quant_rows(x2d, aq: ActQuant, want_rowsum=False):
-    """x fp32 [M,K] -> u8 codes [M,Kp]."""
+def act_quant_rows(x2d, aq: ActQuant, want_rowsum=False, row_group=0, group_stride=0):
+    """x fp32 [M,K] -> u8 codes [M,Kp].  row_group/group_stride: rows come in dense groups spaced `group_stride` elements
+    apart (a [G, row_group, K] view of a larger tensor); x2d is then the storage-sharing view's base."""
     _need_cuda(x2d)
-    x2d = _f32c(x2d)
+    if not row_group:
+        x2d = _f32c(x2d)
     M, K = x2d.shape
     Kp = _round_up(K, 16)
     q = torch.empty((M, Kp), dtype=torch.uint8, device=x2d.device)
@@ -389,7 +401,7 @@ def act_quant_rows(x2d, aq: ActQuant, want_rowsum=False):
     d1 = _qparam(aq.delta1, dev) if aq.split else None
     z1 = _qparam(aq.zp1, dev) if aq.split else None
     lib.act_quant_rows(x2d.data_ptr(), q.data_ptr(), _ptr(rowsum), M, K, Kp, d0.data_ptr(), z0.data_ptr(), aq.levels0,
-                       aq.split, _ptr(d1), _ptr(z1), aq.levels1, aq.prescale, _stream())
+                       aq.split, _ptr(d1), _ptr(z1), aq.levels1, aq.prescale, int(row_group), int(group_stride), _stream())
     return q, rowsum
 
 
@@ -454,7 +466,7 @@ def _codes_token_major_from_bct(x, quant, prescale):
     """x fp32 [BH, d, T] -> codes [BH, T, dp] + per-token code sums [BH, T]."""
     BH, d, T = x.shape
     aq = ActQuant(quant[0], quant[1], quant[2], prescale=prescale)
-    q, chsum = act_quant_nhwc(x.reshape(BH, d, 1, T), aq, 0, want_chsum=True)
+    q, chsum = act_quant_nhwc(x.unsqueeze(2), aq, 0, want_chsum=True)
     return q.reshape(BH, T, q.shape[-1]), chsum.reshape(BH, T)
 
 
@@ -480,9 +492,14 @@ def qattn_bct(q, k, v, aquant: AttnQuant, prescale, sm_scale):
     """q, k, v fp32 [BH, d, T] (channel-major; DDIM AttnBlock and the LDM legacy attention) -> [BH, d, T]."""
     _need_cuda(q, k, v)
     BH, d, T = q.shape
-    qc, rq = _codes_token_major_from_bct(_f32c(q), aquant.q, prescale)
-    kc, rk = _codes_token_major_from_bct(_f32c(k), aquant.k, prescale)
-    vc, rv = _codes_rows(_f32c(v).reshape(BH * d, T), aquant.v)
+    qc, rq = _codes_token_major_from_bct(q, aquant.q, prescale)
+    kc, rk = _codes_token_major_from_bct(k, aquant.k, prescale)
+    if v.dtype == torch.float32 and not v.is_contiguous() and v.stride(2) == 1 and v.stride(1) == T and v.stride(0) >= d * T:
+        # v is a [BH, d, T] slice of the qkv tensor: quantize its rows in place (groups of d rows, stride(0) apart)
+        aqv = ActQuant(aquant.v[0], aquant.v[1], aquant.v[2])
+        vc, rv = act_quant_rows(v.as_strided((BH * d, T), (T, 1)), aqv, want_rowsum=True, row_group=d, group_stride=v.stride(0))
+    else:
+        vc, rv = _codes_rows(_f32c(v).reshape(BH * d, T), aquant.v)
     out = torch.empty((BH, d, T), dtype=torch.float32, device=q.device)
     return qattn(qc, kc, vc.reshape(BH, d, -1), rq, rk, rv.reshape(BH, d), 1, d, T, aquant, sm_scale, out, (d * T, 0, 1, T))
 

@@ -79,13 +79,14 @@ int edadm_lp_loss_bwd(const float* pred, const float* tgt, int64_t n, float p, f
  * code (zero padding of F.conv2d on dequantised values == code zp), padded channels hold 0.
  * split != 0: channels >= split use the second quantizer (quant_layer.py:415-419).
  * chsum (nullable): int32 [B][H+2pad][W+2pad] per-pixel sum of codes (for 8-bit weight zero-points).
- * prescale: x is multiplied by it (fp32) before quantization (the q*scale of QuantQKMatMul, quant_block.py:130). */
+ * prescale: x is multiplied by it (fp32) before quantization (the q*scale of QuantQKMatMul, quant_block.py:130).
+ * x_batch_stride (0 = dense) / row_group + group_stride (0 = dense): read q, k, v views of one qkv tensor in place. */
 int edadm_act_quant_nhwc(const float* x, uint8_t* q, int32_t* chsum, int B, int C, int H, int W, int Cp, int pad,
                          const float* delta0, const float* zp0, int n_levels0, int split, const float* delta1,
-                         const float* zp1, int n_levels1, float prescale, void* stream);
+                         const float* zp1, int n_levels1, float prescale, int64_t x_batch_stride, void* stream);
 int edadm_act_quant_rows(const float* x, uint8_t* q, int32_t* rowsum, int64_t M, int K, int Kp, const float* delta0,
                          const float* zp0, int n_levels0, int split, const float* delta1, const float* zp1,
-                         int n_levels1, float prescale, void* stream);
+                         int n_levels1, float prescale, int row_group, int64_t group_stride, void* stream);
 /* f1: GroupNorm (+ scale-shift conditioning) + SiLU + quantize as one producer.  edadm_gn_fold reduces x [B][C][HW] to the
  * per-(sample, channel) affine a = rstd*gamma*(1+scale), s = (beta - mean*rstd*gamma)*(1+scale) + shift (scale/shift
  * nullable); edadm_norm_act_quant_nhwc is edadm_act_quant_nhwc applied to silu(a*x + s).  Replaces the GroupNorm32 / SiLU
