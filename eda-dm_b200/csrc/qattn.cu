@@ -76,7 +76,8 @@ struct __align__(8) AttnBarriers {
   uint32_t tmem_base;
 };
 
-constexpr int ATT_SMEM_BYTES = 1024 + QK_STAGES * 2 * ATT_TILE_BYTES + V_STAGES * V_TILE_BYTES + 2 * ATT_TILE_BYTES + 256;
+constexpr int ATT_MAX_KEYS = 4096;               // per-key zero-point terms of a whole (batch, head) stay in shared memory
+constexpr int ATT_SMEM_BYTES = 1024 + QK_STAGES * 2 * ATT_TILE_BYTES + V_STAGES * V_TILE_BYTES + 2 * ATT_TILE_BYTES + 256 + ATT_MAX_KEYS * 4;
 
 // SMALL_V: |raw - zq*rk| < 2^22 (head dim <= 64), so int -> float goes through the exact magic-number add instead of I2F.
 // The softmax is bound by the 16-op/clk XU pipe (ex2, I2F, F2I); with the conversions moved to the ALU/FMA pipes only the
@@ -92,8 +93,8 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   uint8_t* smem_v = smem_k + QK_STAGES * ATT_TILE_BYTES;
   uint8_t* smem_p = smem_v + V_STAGES * V_TILE_BYTES;
   AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem_p + 2 * ATT_TILE_BYTES);
+  int* colint = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [s_tiles*128]: bias - zq*rk[s]
 
-  __shared__ __align__(16) int colint[2][ATT_S];          // zq * (code sum of key s) for the S tile in each TMEM buffer
   __shared__ float stat_m[SM_PARTS][ATT_M], stat_l[SM_PARTS][ATT_M];
   __shared__ int stat_rp[SM_PARTS][ATT_M];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -212,24 +213,29 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     const int col_base = part * SM_COLS;
     const float rc_a = (float)row_const * alpha, rc_a2 = (float)row_const * alpha2;   // row constant folded into the FMA
 
+    for (int s = st; s < p.s_tiles * ATT_S; s += 32 * SM_WARPS)
+      colint[s] = (SMALL_V ? MAGIC_I : 0) - (s < p.Tk ? zq * __ldg(rk + s) : 0);
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+
     float m = -INFINITY, l = 0.f;     // m in units of x = S*alpha (natural domain), l = sum 2^((x-m)*log2e)
     int g = 0;
     // ---- pass 1: row max and sum ----
     for (int j = 0; j < p.s_tiles; ++j, ++g) {
       const int sb = g & 1;
-      if (st < ATT_S) { const int s = j * ATT_S + st; colint[sb][st] = (SMALL_V ? MAGIC_I : 0) - (s < p.Tk ? zq * __ldg(rk + s) : 0); }
       mbar_wait(&bars->s_full[sb], (uint32_t)((g >> 1) & 1));
       tc_fence_after();
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      uint32_t raws[SM_COLS / 16][16];
+#pragma unroll
+      for (int cc = 0; cc < SM_COLS / 16; ++cc)      // both TMEM loads in flight before the first is consumed
+        if (j * ATT_S + col_base + cc * 16 < p.Tk) tmem_ld16(lane_addr + (uint32_t)sb * ATT_S + col_base + cc * 16, raws[cc]);
+      tmem_ld_wait();
 #pragma unroll
       for (int cc = 0; cc < SM_COLS / 16; ++cc) {
         const int c0 = col_base + cc * 16;
         const int s0 = j * ATT_S + c0;
         if (s0 < p.Tk) {
-          uint32_t raw[16];
-          tmem_ld16(lane_addr + (uint32_t)sb * ATT_S + c0, raw);
-          tmem_ld_wait();
-          const int4* cv = reinterpret_cast<const int4*>(&colint[sb][c0]);
+          uint32_t (&raw)[16] = raws[cc];
+          const int4* cv = reinterpret_cast<const int4*>(&colint[s0]);
           int v[16];
           if (s0 + 16 <= p.Tk) {
             // full chunk: integer max first (2 instructions / score), then one FMA + ex2 + add per score
@@ -252,7 +258,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             float cmax = -INFINITY;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              v[i] = (int)raw[i] + colint[sb][c0 + i];
+              v[i] = (int)raw[i] + colint[s0 + i];
               if (s0 + i < p.Tk) cmax = fmaxf(cmax, fmaf(biased_to_float<SMALL_V>(v[i]), alpha, rc_a));
             }
             const float m_new = fmaxf(m, cmax);
@@ -294,11 +300,14 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     int rp = 0;
     for (int j = 0; j < p.s_tiles; ++j, ++g) {
       const int sb = g & 1, pb = j & 1;
-      if (st < ATT_S) { const int s = j * ATT_S + st; colint[sb][st] = (SMALL_V ? MAGIC_I : 0) - (s < p.Tk ? zq * __ldg(rk + s) : 0); }
       mbar_wait(&bars->s_full[sb], (uint32_t)((g >> 1) & 1));
-      mbar_wait(&bars->p_empty[pb], (uint32_t)(((j >> 1) & 1) ^ 1));
       tc_fence_after();
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      uint32_t raws[SM_COLS / 16][16];
+#pragma unroll
+      for (int cc = 0; cc < SM_COLS / 16; ++cc)
+        if (j * ATT_S + col_base + cc * 16 < p.Tk) tmem_ld16(lane_addr + (uint32_t)sb * ATT_S + col_base + cc * 16, raws[cc]);
+      tmem_ld_wait();
+      mbar_wait(&bars->p_empty[pb], (uint32_t)(((j >> 1) & 1) ^ 1));
       uint8_t* prow = smem_p + pb * ATT_TILE_BYTES + r * 128;
 #pragma unroll
       for (int cc = 0; cc < SM_COLS / 16; ++cc) {
@@ -306,10 +315,8 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         const int s0 = j * ATT_S + c0;
         uint32_t packed[4] = {0, 0, 0, 0};
         if (s0 < p.Tk) {
-          uint32_t raw[16];
-          tmem_ld16(lane_addr + (uint32_t)sb * ATT_S + c0, raw);
-          tmem_ld_wait();
-          const int4* cv = reinterpret_cast<const int4*>(&colint[sb][c0]);
+          uint32_t (&raw)[16] = raws[cc];
+          const int4* cv = reinterpret_cast<const int4*>(&colint[s0]);
           if (fast_codes && s0 + 16 <= p.Tk) {
             // full chunk, 8-bit codes: FMA + ex2 + mul + cvt.rni per score, saturating pack 2 codes / instruction
 #pragma unroll
@@ -326,7 +333,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float x = biased_to_float<SMALL_V>((int)raw[i] + colint[sb][c0 + i]);
+              const float x = biased_to_float<SMALL_V>((int)raw[i] + colint[s0 + i]);
               const float e = ex2_approx(fmaf(x, alpha2, cexp2));
               uint32_t code = (uint32_t)fminf(fmaxf(rintf(e * kq) + zpq, 0.f), qmax);
               code = (s0 + i < p.Tk) ? code : 0u;
@@ -397,6 +404,7 @@ extern "C" int edadm_qattn_fwd(const uint8_t* qc, const uint8_t* kc, const uint8
       p_levels < 2 || p_levels > 256)
     return fail(EDADM_ERR_ARG, "qattn_fwd: bad sizes BH=%d heads=%d Tq=%d Tk=%d d=%d dp=%d Tkp=%d", BH, heads, Tq, Tk, d, dp, Tkp);
   if (BH > 65535) return fail(EDADM_ERR_UNSUPPORTED, "qattn_fwd: more than 65535 (batch x heads) per launch");
+  if (Tk > ATT_MAX_KEYS) return fail(EDADM_ERR_UNSUPPORTED, "qattn_fwd: more than %d keys per (batch, head)", ATT_MAX_KEYS);
   if ((((uintptr_t)qc | (uintptr_t)kc | (uintptr_t)vc) & 15)) return fail(EDADM_ERR_ARG, "qattn_fwd: operands must be 16-byte aligned");
 
   AttnParams p;
