@@ -154,7 +154,11 @@ def _ref_int_conv(codes_a, za, wcodes, zw, stride=1, padding=0):
     return F.conv2d(a, w, None, stride=stride, padding=padding)
 
 
-@pytest.mark.parametrize("B,C,H,W,pad", [(2, 64, 16, 16, 1), (3, 20, 8, 8, 1), (1, 3, 32, 32, 1), (2, 130, 4, 4, 0)])
+@pytest.mark.parametrize("B,C,H,W,pad", [(2, 64, 16, 16, 1), (3, 20, 8, 8, 1), (1, 3, 32, 32, 1), (2, 130, 4, 4, 0),
+                                         # large enough for the TMA-staged producer: full tiles, ragged channel tile,
+                                         # ragged pixel tile (HW % 32 != 0), narrow heads (CT = 32 / 64)
+                                         (8, 256, 32, 32, 1), (6, 200, 32, 32, 1), (40, 128, 6, 10, 1), (64, 24, 32, 32, 0),
+                                         (24, 64, 24, 24, 1)])
 def test_act_quant_nhwc_codes(cuda, B, C, H, W, pad):
     from edadm import ops
     g = torch.Generator().manual_seed(6)
@@ -169,6 +173,30 @@ def test_act_quant_nhwc_codes(cuda, B, C, H, W, pad):
     if pad:
         assert bool((q[:, 0, :, :C] == int(z.item())).all()) and bool((q[:, :, -1, :C] == int(z.item())).all())
     assert torch.equal(chsum.cpu().long(), q.long().sum(-1))
+
+
+def test_act_quant_nhwc_tma_split_and_strided(cuda):
+    """TMA-staged producer: split quantizers (quant_layer.py:415-419), prescale, and a batch-strided source view"""
+    from edadm import ops
+    g = torch.Generator().manual_seed(61)
+    B, C, H, W, split = 8, 192, 32, 32, 128
+    x = torch.randn(B, C, H, W, generator=g) * 1.2
+    x[:, split:] *= 3.0
+    d0, z0 = _act_params(x[:, :split])
+    d1, z1 = _act_params(x[:, split:])
+    aq = ops.ActQuant(d0.to(cuda), z0.to(cuda), 256, split, d1.to(cuda), z1.to(cuda), 256)
+    q, chsum = ops.act_quant_nhwc(x.to(cuda), aq, 1, want_chsum=True)
+    ref = torch.cat([O.uaq_codes(x[:, :split], d0, z0, 256), O.uaq_codes(x[:, split:], d1, z1, 256)], 1).permute(0, 2, 3, 1)
+    q = q.cpu()
+    assert torch.equal(q[:, 1:-1, 1:-1, :C].float(), ref)
+    assert torch.equal(chsum.cpu().long(), q.long().sum(-1))
+    # q / k / v style view: 3 tensors interleaved along channels, read in place with prescale
+    big = torch.randn(B, 3 * C, H, W, generator=g)
+    view = big.to(cuda)[:, C:2 * C]
+    d, z = _act_params(big[:, C:2 * C] * 0.25)
+    qv, _ = ops.act_quant_nhwc(view, ops.ActQuant(d.to(cuda), z.to(cuda), 256, prescale=0.25), 0)
+    refv = O.uaq_codes(big[:, C:2 * C] * 0.25, d, z, 256).permute(0, 2, 3, 1)
+    assert torch.equal(qv.cpu()[..., :C].float(), refv)
 
 
 @pytest.mark.parametrize("M,K", [(200, 128), (64, 77), (4096, 320), (1, 512)])
