@@ -12,7 +12,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 # per-file extras: the quantizer files must reproduce torch's separate mul/add roundings
 EXTRA = {"elementwise.cu": ["-fmad=false"], "pack.cu": ["-fmad=false"]}
-SOURCES = ["common.cu", "elementwise.cu", "pack.cu", "qgemm_sm100.cu", "qattn.cu"]
+SOURCES = ["common.cu", "elementwise.cu", "pack.cu", "qgemm_sm100.cu", "qattn.cu", "conv_small.cu"]
 
 
 def _newest(paths):

@@ -44,6 +44,7 @@ struct GemmParams {
   // epilogue
   int out_hw;               // pixels per image of the OUTPUT layout (1 => row-major [M][N])
   int accumulate, silu;
+  const float* residual;   // optional fp32 tensor laid out like `out`, added after bias / accumulate / SiLU
   const float* delta_a;     // device scalars (nn.Parameter storage): no host sync on the path
   const float* zp_a;
   const float* delta_w;     // [N]
@@ -68,10 +69,10 @@ constexpr int ROW_STAGE_LD = 36;                                   // floats per
 constexpr int ROW_STAGE_BYTES = EPI_WARPS * 32 * ROW_STAGE_LD * 4;  // one 32x32 fp32 tile per epilogue warp
 
 // one 16-column chunk of the epilogue for one output row: int32 zero-point fold, fp32 scale + bias, store
-template <bool GENERIC>
+template <bool GENERIC, bool RES>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[16], int c0, int n_valid, int rs, const float* epi_scale,
                                                const int* epi_zterm, const int* epi_cw, const float* epi_bias, float* dst,
-                                               long long col_stride, bool accumulate, bool silu) {
+                                               const float (&t)[16], long long col_stride, bool accumulate, bool silu) {
   if (!GENERIC) {
     // all 16 columns valid, no rowsum term, plain store
     const int4* zt = reinterpret_cast<const int4*>(epi_zterm + c0);
@@ -86,7 +87,17 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[16], int c0, 
         v.y = fmaf((float)((int)r[4 * q + 1] + z.y), s.y, b.y);
         v.z = fmaf((float)((int)r[4 * q + 2] + z.z), s.z, b.z);
         v.w = fmaf((float)((int)r[4 * q + 3] + z.w), s.w, b.w);
+        if (RES) { v.x += t[4 * q + 0]; v.y += t[4 * q + 1]; v.z += t[4 * q + 2]; v.w += t[4 * q + 3]; }
         *reinterpret_cast<float4*>(dst + 4 * q) = v;
+      }
+    } else if (RES) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int4 z = zt[q]; const float4 s = sc[q]; const float4 b = bi[q];
+        dst[0] = fmaf((float)((int)r[4 * q + 0] + z.x), s.x, b.x) + t[4 * q + 0]; dst += col_stride;
+        dst[0] = fmaf((float)((int)r[4 * q + 1] + z.y), s.y, b.y) + t[4 * q + 1]; dst += col_stride;
+        dst[0] = fmaf((float)((int)r[4 * q + 2] + z.z), s.z, b.z) + t[4 * q + 2]; dst += col_stride;
+        dst[0] = fmaf((float)((int)r[4 * q + 3] + z.w), s.w, b.w) + t[4 * q + 3]; dst += col_stride;
       }
     } else {
 #pragma unroll
@@ -99,6 +110,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[16], int c0, 
       }
     }
   } else {
+#pragma unroll
     for (int j = 0; j < 16; ++j) {
       if (j < n_valid) {
         const float iv = (float)((int)r[j] + epi_cw[c0 + j] * rs + epi_zterm[c0 + j]);
@@ -106,10 +118,18 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[16], int c0, 
         float* d = dst + (long long)j * col_stride;
         if (accumulate) v += *d;
         if (silu) v = v / (1.f + __expf(-v));
+        if (RES) v += t[j];
         *d = v;
       }
     }
   }
+}
+
+// residual values of one 16-column chunk of one output row (issued well ahead of their use: the loads overlap the
+// MMA wait and the previous chunk's stores instead of sitting on the epilogue's critical path)
+__device__ __forceinline__ void load_residual(float (&t)[16], const float* res, long long col_stride, int n_valid) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) t[j] = (j < n_valid) ? __ldg(res + (long long)j * col_stride) : 0.f;
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -211,7 +231,7 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int za = (int)__ldg(p.zp_a);
     // float4 row stores need 16-byte aligned rows
     const bool generic_all = p.cw != nullptr || p.accumulate || p.silu ||
-                             (p.out_hw == 1 && ((p.N & 3) || (reinterpret_cast<uintptr_t>(p.out) & 15)));
+                             (p.out_hw == 1 && ((p.N & 3) || (reinterpret_cast<uintptr_t>(p.out) & 15) || (reinterpret_cast<uintptr_t>(p.residual) & 15)));
     const long long col_stride = p.out_hw;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -233,11 +253,12 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const long long img = row_ok ? m / p.out_hw : 0;
       const long long pix = row_ok ? m - img * p.out_hw : 0;
       float* out_row = p.out + img * (long long)p.N * p.out_hw + pix + (long long)n0 * p.out_hw;
+      const float* res_row = p.residual ? p.residual + (out_row - p.out) : nullptr;
 
-      mbar_wait(&bars->tmem_full[acc], acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BLOCK_N;
       if (p.row_staging) {
+        mbar_wait(&bars->tmem_full[acc], acc_phase);
+        tc_fence_after();
         // row-major output: 32-column chunks; values go through a per-warp 32x32 smem tile so that every store
         // instruction writes four complete 128-byte row segments instead of 32 scattered 16-byte pieces
         float* tile_s = row_stage + (warp - 2) * 32 * ROW_STAGE_LD;
@@ -267,7 +288,11 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int rr = i * 4 + (lane >> 3);
             const int mm = m_base + rr;
             if (mm < p.M && ncol < p.N) {
-              const float4 v = *reinterpret_cast<const float4*>(tile_s + rr * ROW_STAGE_LD + cq);
+              float4 v = *reinterpret_cast<const float4*>(tile_s + rr * ROW_STAGE_LD + cq);
+              if (p.residual) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.residual + (long long)mm * p.N + ncol));
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+              }
               *reinterpret_cast<float4*>(p.out + (long long)mm * p.N + ncol) = v;
             }
           }
@@ -275,25 +300,48 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
       } else {
       uint32_t r0[16], r1[16];
+      float t0[16], t1[16];
       int c0 = half * 16;
+      const bool has_res = res_row != nullptr && row_ok;
+      if (has_res && c0 < p.block_n) load_residual(t0, res_row + (long long)c0 * col_stride, col_stride, p.N - (n0 + c0));
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
       if (c0 < p.block_n) { tmem_ld16(taddr + c0, r0); }
       tmem_ld_wait();
-      // software pipeline: the TMEM load of the next chunk is in flight while this one is converted and stored
+      // software pipeline: the TMEM load (and residual load) of the next chunk is in flight while this one is converted and stored
       for (; c0 < p.block_n; c0 += 64) {
         const int c1 = c0 + 32;
-        if (c1 < p.block_n) tmem_ld16(taddr + c1, r1);
+        if (c1 < p.block_n) {
+          tmem_ld16(taddr + c1, r1);
+          if (has_res) load_residual(t1, res_row + (long long)c1 * col_stride, col_stride, p.N - (n0 + c1));
+        }
         if (row_ok) {
           const int nv = p.N - (n0 + c0);
-          if (!generic_all && nv >= 16) epilogue_chunk<false>(r0, c0, 16, rs, epi_scale, epi_zterm, epi_cw, epi_bias, out_row + (long long)c0 * col_stride, col_stride, false, false);
-          else epilogue_chunk<true>(r0, c0, nv, rs, epi_scale, epi_zterm, epi_cw, epi_bias, out_row + (long long)c0 * col_stride, col_stride, p.accumulate, p.silu);
+          float* dptr = out_row + (long long)c0 * col_stride;
+          if (has_res) {
+            if (!generic_all && nv >= 16) epilogue_chunk<false, true>(r0, c0, 16, rs, epi_scale, epi_zterm, epi_cw, epi_bias, dptr, t0, col_stride, false, false);
+            else epilogue_chunk<true, true>(r0, c0, nv, rs, epi_scale, epi_zterm, epi_cw, epi_bias, dptr, t0, col_stride, p.accumulate, p.silu);
+          } else {
+            if (!generic_all && nv >= 16) epilogue_chunk<false, false>(r0, c0, 16, rs, epi_scale, epi_zterm, epi_cw, epi_bias, dptr, t0, col_stride, false, false);
+            else epilogue_chunk<true, false>(r0, c0, nv, rs, epi_scale, epi_zterm, epi_cw, epi_bias, dptr, t0, col_stride, p.accumulate, p.silu);
+          }
         }
         tmem_ld_wait();
         const int c2 = c0 + 64;
-        if (c2 < p.block_n) tmem_ld16(taddr + c2, r0);
+        if (c2 < p.block_n) {
+          tmem_ld16(taddr + c2, r0);
+          if (has_res) load_residual(t0, res_row + (long long)c2 * col_stride, col_stride, p.N - (n0 + c2));
+        }
         if (c1 < p.block_n && row_ok) {
           const int nv = p.N - (n0 + c1);
-          if (!generic_all && nv >= 16) epilogue_chunk<false>(r1, c1, 16, rs, epi_scale, epi_zterm, epi_cw, epi_bias, out_row + (long long)c1 * col_stride, col_stride, false, false);
-          else epilogue_chunk<true>(r1, c1, nv, rs, epi_scale, epi_zterm, epi_cw, epi_bias, out_row + (long long)c1 * col_stride, col_stride, p.accumulate, p.silu);
+          float* dptr = out_row + (long long)c1 * col_stride;
+          if (has_res) {
+            if (!generic_all && nv >= 16) epilogue_chunk<false, true>(r1, c1, 16, rs, epi_scale, epi_zterm, epi_cw, epi_bias, dptr, t1, col_stride, false, false);
+            else epilogue_chunk<true, true>(r1, c1, nv, rs, epi_scale, epi_zterm, epi_cw, epi_bias, dptr, t1, col_stride, p.accumulate, p.silu);
+          } else {
+            if (!generic_all && nv >= 16) epilogue_chunk<false, false>(r1, c1, 16, rs, epi_scale, epi_zterm, epi_cw, epi_bias, dptr, t1, col_stride, false, false);
+            else epilogue_chunk<true, false>(r1, c1, nv, rs, epi_scale, epi_zterm, epi_cw, epi_bias, dptr, t1, col_stride, p.accumulate, p.silu);
+          }
         }
         tmem_ld_wait();
       }
@@ -333,7 +381,7 @@ using namespace edadm;
 extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const int8_t* wq,
                               int N, int Np, int R, int S, int Cp_w, const float* delta_a, const float* zp_a,
                               const float* delta_w, const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum,
-                              const float* bias, float* out, int out_hw, int accumulate, int silu, void* stream) {
+                              const float* bias, const float* residual, float* out, int out_hw, int accumulate, int silu, void* stream) {
   if (!q || !wq || !delta_a || !zp_a || !delta_w || !wsum_eff || !out) return fail(EDADM_ERR_ARG, "qgemm_i8: null pointer");
   if (cw && !rowsum) return fail(EDADM_ERR_ARG, "qgemm_i8: cw given without rowsum");
   if (B < 1 || Hp < R || Wp < S || R < 1 || S < 1 || N < 1 || (Cp_act & 15) || (Cp_w & 15) || Cp_w < 16 || a_c_offset < 0 ||
@@ -397,13 +445,13 @@ extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_ac
   p.block_n = block_n; p.n_tiles = n_tiles; p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
   p.b_stage_bytes = (block_n * BLOCK_K + 1023) & ~1023;
   // row-major outputs (linear layers) are staged through smem; needs whole float4s per row and no rowsum / accumulate / SiLU
-  p.row_staging = (out_hw == 1 && !cw && !accumulate && !silu && (N % 4) == 0 && (block_n % 32) == 0 &&
+  p.row_staging = (out_hw == 1 && !cw && !accumulate && !silu && (N % 4) == 0 && (block_n % 32) == 0 && ((reinterpret_cast<uintptr_t>(residual) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 1 : 0;
   const int fixed = SMEM_FIXED + (p.row_staging ? ROW_STAGE_BYTES : 0);
   p.stages = (SMEM_LIMIT - fixed) / (A_STAGE_BYTES + p.b_stage_bytes);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   const int smem_bytes = fixed + p.stages * (A_STAGE_BYTES + p.b_stage_bytes);
-  p.out_hw = out_hw; p.accumulate = accumulate; p.silu = silu;
+  p.out_hw = out_hw; p.accumulate = accumulate; p.silu = silu; p.residual = residual;
   p.delta_a = delta_a; p.zp_a = zp_a; p.delta_w = delta_w; p.wsum_eff = wsum_eff; p.cw = cw; p.rowsum = rowsum;
   p.bias = bias; p.out = out;
 

@@ -423,8 +423,12 @@ gemm_profile = None   # bench.py sets this to a list to get (start_event, end_ev
 
 
 def qgemm_i8(q, pw: PackedWeight, delta_a, zp_a, out, out_hw, bias=None, rowsum=None, a_c_offset=0,
-             accumulate=False, silu=False, filter_rs=None):
-    """Launch the tcgen05 GEMM.  q: [B,Hp,Wp,Cp] u8 codes (or [M,Kp] for a flat GEMM)."""
+             accumulate=False, silu=False, filter_rs=None, residual=None):
+    """Launch the tcgen05 GEMM.  q: [B,Hp,Wp,Cp] u8 codes (or [M,Kp] for a flat GEMM).  residual (fp32, contiguous, laid
+    out like `out`) is added in the epilogue: the `x + h` of the residual / attention blocks without a separate pass."""
+    if residual is not None:
+        if residual.dtype != torch.float32 or not residual.is_contiguous() or residual.numel() != out.numel():
+            raise EdadmError("qgemm_i8: residual must be a contiguous fp32 tensor of the output's size")
     if q.dim() == 2:
         B, Hp, Wp, Cp_act = 1, 1, q.shape[0], q.shape[1]
     else:
@@ -442,11 +446,37 @@ def qgemm_i8(q, pw: PackedWeight, delta_a, zp_a, out, out_hw, bias=None, rowsum=
     lib.qgemm_i8(q.data_ptr(), B, Hp, Wp, Cp_act, int(a_c_offset), pw.wq.data_ptr(), pw.N, pw.Np, R, S,
                  pw.wq.shape[2] if filter_rs is None else pw.wq.shape[1] * pw.wq.shape[2] // (R * S),
                  da.data_ptr(), za.data_ptr(), pw.delta_w.data_ptr(), pw.wsum_eff.data_ptr(), _ptr(cw), _ptr(rowsum),
-                 _ptr(bias), out.data_ptr(), int(out_hw), 1 if accumulate else 0, 1 if silu else 0, _stream())
+                 _ptr(bias), _ptr(residual), out.data_ptr(), int(out_hw), 1 if accumulate else 0, 1 if silu else 0, _stream())
     if prof is not None:
         ev1.record()
         m = B * (Hp - R + 1) * (Wp - S + 1)
         prof.append((ev0, ev1, m * pw.N * pw.C * pw.R * pw.S))
+    return out
+
+
+def conv3x3_small_n_ok(x, weight, kwargs):
+    """True when `F.conv2d(x, weight, **kwargs)` is the narrow output-layer case edadm_conv3x3_small_n covers."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and weight.dim() == 4):
+        return False
+    if weight.shape[0] > 4 or tuple(weight.shape[2:]) != (3, 3) or x.shape[0] > 65535 or weight.shape[1] * weight.shape[0] > 3600:
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
+        return False
+    kw = kwargs or {}
+    one = lambda v, d: all(int(e) == d for e in (v if isinstance(v, (tuple, list)) else (v,)))
+    return (one(kw.get('stride', 1), 1) and not isinstance(kw.get('padding', 0), str) and one(kw.get('padding', 0), 1)
+            and one(kw.get('dilation', 1), 1) and kw.get('groups', 1) == 1)
+
+
+def conv3x3_small_n(x, weight, bias=None):
+    """fp32 3x3 / stride 1 / pad 1 convolution to <= 4 output channels (the UNet output layer)."""
+    _need_cuda(x)
+    x, weight = _f32c(x), _f32c(weight.detach())
+    B, C, H, W = x.shape
+    N = weight.shape[0]
+    out = torch.empty((B, N, H, W), dtype=torch.float32, device=x.device)
+    b = None if bias is None else _f32c(bias.detach())
+    lib.conv3x3_small_n(x.data_ptr(), weight.data_ptr(), _ptr(b), out.data_ptr(), B, C, H, W, N, _stream())
     return out
 
 

@@ -82,6 +82,14 @@ def _prenorm_ok(conv, block):
     return isinstance(conv, QuantModule) and (not block.training or p_drop == 0)
 
 
+def _conv_plus(conv, residual, call):
+    """`residual + call()` where `call` runs the QuantModule `conv`; the add moves into the GEMM epilogue unless a hook
+    observes the conv's own output (calibration caches, FBR taps)."""
+    if isinstance(conv, QuantModule) and not conv._forward_hooks:
+        return call(residual=residual)
+    return residual + call()
+
+
 class BaseQuantBlock(nn.Module):
     """Common state of all quantized blocks (reference quant_block.py:20-43)."""
 
@@ -146,14 +154,15 @@ def _quant_resblock_forward(blk, x, emb, split=0):
     emb_out = blk.emb_layers(emb).type(h.dtype)
     while emb_out.dim() < h.dim():
         emb_out = emb_out[..., None]
+    if split and not isinstance(blk.skip_connection, nn.Identity):
+        sx = blk.skip_connection(x, split=split)
+    else:
+        sx = blk.skip_connection(x)
     if blk.use_scale_shift_norm:
         scale, shift = th.chunk(emb_out, 2, dim=1)
-        h = out_conv.forward_prenorm(h, blk.out_layers[0], scale=scale, shift=shift)
-    else:
-        h = out_conv.forward_prenorm(h + emb_out, blk.out_layers[0])
-    if split and not isinstance(blk.skip_connection, nn.Identity):
-        return blk.skip_connection(x, split=split) + h
-    return blk.skip_connection(x) + h
+        return _conv_plus(out_conv, sx, lambda **kw: out_conv.forward_prenorm(h, blk.out_layers[0], scale=scale, shift=shift, **kw))
+    hin = h + emb_out
+    return _conv_plus(out_conv, sx, lambda **kw: out_conv.forward_prenorm(hin, blk.out_layers[0], **kw))
 
 
 # ---- LDM attention: the two matmuls -----------------------------------------------------------------------
@@ -211,8 +220,12 @@ class QuantAttentionBlock(BaseQuantBlock):
     def _forward(self, x):
         b, c, *spatial = x.shape
         x = x.reshape(b, c, -1)
-        h = self.proj_out(self.attention(self.qkv(self.norm(x))))
-        return (x + h).reshape(b, c, *spatial)
+        if isinstance(self.qkv, QuantModule):
+            qkv = self.qkv.forward_prenorm(x, self.norm, silu=False)     # GroupNorm folded into the qkv producer
+        else:
+            qkv = self.qkv(self.norm(x))
+        a = self.attention(qkv)
+        return _conv_plus(self.proj_out, x, lambda **kw: self.proj_out(a, **kw)).reshape(b, c, *spatial)
 
     def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
         self.use_weight_quant = weight_quant
@@ -302,7 +315,9 @@ class QuantResnetBlock(BaseQuantBlock):
         if _prenorm_ok(self.conv1, self) and _prenorm_ok(self.conv2, self):
             h = self.conv1.forward_prenorm(x, self.norm1, act_fn=nonlinearity)
             h = h + self.temb_proj(nonlinearity(temb))[:, :, None, None]
-            h = self.conv2.forward_prenorm(h, self.norm2, act_fn=nonlinearity)
+            if self.in_channels != self.out_channels:
+                x = self.conv_shortcut(x) if self.use_conv_shortcut else self.nin_shortcut(x, split=self.split)
+            return _conv_plus(self.conv2, x, lambda **kw: self.conv2.forward_prenorm(h, self.norm2, act_fn=nonlinearity, **kw))
         else:
             h = self.conv1(nonlinearity(self.norm1(x)))
             h = h + self.temb_proj(nonlinearity(temb))[:, :, None, None]
@@ -337,7 +352,8 @@ class QuantAttnBlock(BaseQuantBlock):
             qf = q.reshape(b, c, h * w).permute(0, 2, 1)
             w_ = th.softmax(th.bmm(qf, k.reshape(b, c, h * w)) * scale, dim=2)
             out = th.bmm(v.reshape(b, c, h * w), w_.permute(0, 2, 1))
-        return x + self.proj_out(out.reshape(b, c, h, w))
+        out = out.reshape(b, c, h, w)
+        return _conv_plus(self.proj_out, x, lambda **kw: self.proj_out(out, **kw))
 
 
 def get_specials(quant_act=False):

@@ -359,14 +359,16 @@ class QuantModule(nn.Module):
         self._packed = (key, packs)
         return packs
 
-    def forward_prenorm(self, x, norm, silu: bool = True, scale=None, shift=None, split: int = 0, act_fn=F.silu):
+    def forward_prenorm(self, x, norm, silu: bool = True, scale=None, shift=None, split: int = 0, act_fn=F.silu,
+                        residual=None):
         """`self(silu(norm(x) [* (1 + scale) + shift]))` for a GroupNorm `norm` in front of this conv.  On the integer
         path GroupNorm + conditioning + SiLU + activation quantization run as ONE producer pass (edadm_gn_fold +
         edadm_norm_act_quant_nhwc); otherwise it is computed module by module like the reference does."""
         if split != 0 and self.split == 0:
             self.split = split
             self.set_split()
-        fusable = (backend.fuse_norm and isinstance(norm, nn.GroupNorm) and self.fwd_func is F.conv2d and x.dim() == 4
+        shape_ok = (self.fwd_func is F.conv2d and x.dim() == 4) or (self.fwd_func is F.conv1d and x.dim() == 3)
+        fusable = (backend.fuse_norm and isinstance(norm, nn.GroupNorm) and shape_ok
                    and self._integer_path_ok(x) and not self._forward_hooks and not self._forward_pre_hooks
                    and not norm._forward_hooks)
         if not fusable:
@@ -375,12 +377,22 @@ class QuantModule(nn.Module):
                 h = h * (1 + scale) + shift
             if silu:
                 h = act_fn(h)      # the block's own formulation of swish (x*sigmoid(x) in the DDIM UNet, nn.SiLU in LDM)
-            return self(h, split=split) if split else self(h)
+            return self(h, split=split, residual=residual)
         self.last_path = 'int8'
         a, s = ops.gn_fold(x, norm.weight, norm.bias, norm.num_groups, norm.eps, scale, shift)
-        return self.activation_function(self._forward_int8(x, affine=(a, s, silu)))
+        return self._finish(self._forward_int8(x, affine=(a, s, silu), residual=self._epilogue_residual(residual)), residual)
 
-    def _forward_int8(self, input, affine=None):
+    def _epilogue_residual(self, residual):
+        """`residual` if the GEMM epilogue may add it (nothing but a StraightThrough sits between conv and add)."""
+        return residual if isinstance(self.activation_function, StraightThrough) else None
+
+    def _finish(self, out, residual):
+        out = self.activation_function(out)
+        if residual is not None and self._epilogue_residual(residual) is None:
+            out = residual + out
+        return out
+
+    def _forward_int8(self, input, affine=None, residual=None):
         """Exact integer GEMM: out = dA*dW[n]*sum (qa-za)(qw-zw) + bias  == the reference's fp32 conv of the
         dequantised tensors (quant_layer.py:414-434) without its per-product rounding."""
         packs = self._packed_weights()
@@ -399,8 +411,10 @@ class QuantModule(nn.Module):
             x2 = input.reshape(-1, input.shape[-1])
             q, rowsum = ops.act_quant_rows(x2, aq, want_rowsum=needs_rowsum)
             out = torch.empty((x2.shape[0], N), dtype=torch.float32, device=input.device)
+            if residual is not None:
+                residual = residual.reshape(-1, N).contiguous()
             if x2.shape[0] > 0:
-                self._gemm_chain(q, packs, aqs, out, 1, bias, rowsum)
+                self._gemm_chain(q, packs, aqs, out, 1, bias, rowsum, residual)
             return out.reshape(*lead, N)
         x4 = input.unsqueeze(2) if self.fwd_func is F.conv1d else input
         B, C, H, W = x4.shape
@@ -418,24 +432,30 @@ class QuantModule(nn.Module):
             q, chsum = ops.act_quant_nhwc(x4, aq, pad, want_chsum=needs_rowsum)
         rowsum = ops.conv_rowsum(chsum, Ho, Wo, R, S, stride) if needs_rowsum else None
         out = torch.empty((B, N, Ho, Wo), dtype=torch.float32, device=input.device)
+        if residual is not None:
+            residual = residual.contiguous()
         if stride == 1 and _implicit_tiling_ok(B, Ho, Wo):
-            self._gemm_chain(q, packs, aqs, out, Ho * Wo, bias, rowsum)
+            self._gemm_chain(q, packs, aqs, out, Ho * Wo, bias, rowsum, residual)
         else:
             if self.split:
                 raise EdadmError("split shortcut on a strided / irregular conv is not supported on the integer path")
             a = ops.im2col_u8(q, Ho, Wo, R, S, stride)
-            ops.qgemm_i8(a, pw0, aqs[0].delta, aqs[0].zero_point, out, Ho * Wo, bias=bias, rowsum=rowsum, filter_rs=(1, 1))
+            ops.qgemm_i8(a, pw0, aqs[0].delta, aqs[0].zero_point, out, Ho * Wo, bias=bias, rowsum=rowsum, filter_rs=(1, 1),
+                         residual=residual)
         return out.squeeze(2) if self.fwd_func is F.conv1d else out
 
-    def _gemm_chain(self, q, packs, aqs, out, out_hw, bias, rowsum):
+    def _gemm_chain(self, q, packs, aqs, out, out_hw, bias, rowsum, residual=None):
         c_off = 0
+        last = len(packs) - 1
         for i, (pw, aqz) in enumerate(zip(packs, aqs)):
             ops.qgemm_i8(q, pw, aqz.delta, aqz.zero_point, out, out_hw, bias=bias if i == 0 else None, rowsum=rowsum,
-                         a_c_offset=c_off, accumulate=i > 0)
+                         a_c_offset=c_off, accumulate=i > 0, residual=residual if i == last else None)
             c_off += pw.C
 
     # ---- forward -------------------------------------------------------------------------------------
-    def forward(self, input: torch.Tensor, split: int = 0):
+    def forward(self, input: torch.Tensor, split: int = 0, residual=None):
+        """`residual` (optional, not in the reference signature): a tensor of the output's shape that is added to the
+        result -- `conv(x) + residual` -- inside the GEMM epilogue on the integer path, as a plain add elsewhere."""
         if split != 0 and self.split != 0:
             assert split == self.split
         elif split != 0:
@@ -445,7 +465,7 @@ class QuantModule(nn.Module):
 
         if self._integer_path_ok(input):
             self.last_path = 'int8'
-            return self.activation_function(self._forward_int8(input))
+            return self._finish(self._forward_int8(input, residual=self._epilogue_residual(residual)), residual)
 
         if not self.disable_act_quant and self.use_act_quant:
             if self.split != 0:
@@ -464,8 +484,8 @@ class QuantModule(nn.Module):
             weight = self.org_weight
             bias = self.org_bias
         self.last_path = 'fake' if (self.use_weight_quant or self.use_act_quant) else 'fp'
-        out = _library_fwd(self.fwd_func, input, weight, bias, self.fwd_kwargs)
-        return self.activation_function(out)
+        out = self.activation_function(_library_fwd(self.fwd_func, input, weight, bias, self.fwd_kwargs))
+        return out if residual is None else residual + out
 
 
 def _implicit_tiling_ok(B, Ho, Wo):
@@ -479,7 +499,10 @@ def _implicit_tiling_ok(B, Ho, Wo):
 
 
 def _library_fwd(fn, input, weight, bias, kwargs):
-    """fp32 conv / linear of the calibration + FP paths (cuDNN / cuBLAS), TF32 off unless opted in."""
+    """fp32 conv / linear of the calibration + FP paths (cuDNN / cuBLAS), TF32 off unless opted in.  The narrow output
+    layer (<= 4 channels, its input is never quantized) takes the dedicated stencil kernel when no gradient is needed."""
+    if fn is F.conv2d and ops.conv3x3_small_n_ok(input, weight, kwargs):
+        return ops.conv3x3_small_n(input, weight, bias)
     if not input.is_cuda or backend.allow_tf32:
         return fn(input, weight, bias, **kwargs)
     prev_c, prev_m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32

@@ -157,8 +157,16 @@ class AttentionBlock(nn.Module):
     def forward(self, x):
         b, c, *spatial = x.shape
         x = x.reshape(b, c, -1)
-        h = self.proj_out(self.attention(self.qkv(self.norm(x))))
-        return (x + h).reshape(b, c, *spatial)
+        # quantized modules (qdiff.QuantModule) take GroupNorm into their activation producer and the residual into
+        # their epilogue; plain nn.Conv1d runs module by module
+        if hasattr(self.qkv, 'forward_prenorm'):
+            qkv = self.qkv.forward_prenorm(x, self.norm, silu=False)
+        else:
+            qkv = self.qkv(self.norm(x))
+        h = self.attention(qkv)
+        if hasattr(self.proj_out, 'forward_prenorm') and not self.proj_out._forward_hooks:
+            return self.proj_out(h, residual=x).reshape(b, c, *spatial)
+        return (x + self.proj_out(h)).reshape(b, c, *spatial)
 
 
 class GEGLU(nn.Module):

@@ -113,11 +113,20 @@ int edadm_pack_weight(const float* w, const float* alpha, const float* delta, co
  * use_weight_quant and use_act_quant are on.  Stride-1 implicit GEMM over the halo-padded NHWC codes
  * (Ho = Hp-R+1, Wo = Wp-S+1); a 2-D GEMM is B=1,Hp=1,Wp=M,R=S=1; strided convs go through
  * edadm_im2col_u8 first.  out fp32 is written as [M/out_hw][N][out_hw] (NCHW; out_hw=1 => [M][N]):
- *   out = delta_a*delta_w[n]*(acc + cw[n]*rowsum[m] - zp_a*wsum_eff[n]) + bias[n]  (+= out if accumulate) */
+ *   out = delta_a*delta_w[n]*(acc + cw[n]*rowsum[m] - zp_a*wsum_eff[n]) + bias[n]  (+= out if accumulate)
+ * then SiLU if `silu`, then + residual (nullable; fp32 laid out like out, must not alias out) -- the `x + h` / `skip_connection(x) + h` of
+ * the residual and attention blocks (quant_block.py:116, :193) folded into the store.                              */
 int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const int8_t* wq, int N, int Np,
                    int R, int S, int Cp_w, const float* delta_a, const float* zp_a, const float* delta_w,
-                   const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum, const float* bias, float* out,
-                   int out_hw, int accumulate, int silu, void* stream);
+                   const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum, const float* bias,
+                   const float* residual, float* out, int out_hw, int accumulate, int silu, void* stream);
+
+/* fp32 3x3 convolution (stride 1, zero padding 1) with N <= 4 output channels: the UNet's output layer, whose input the
+ * reference leaves un-quantized (qdiff/quant_model.py `disable_network_output_quantization`), so it runs as
+ * fp32 activations x fake-quantized 8-bit weights (quant_layer.py:421-434 with disable_act_quant).  x [B][C][H][W],
+ * w [N][C][3][3] (already fake-quantized), bias [N] or NULL, out [B][N][H][W].                                      */
+int edadm_conv3x3_small_n(const float* x, const float* w, const float* bias, float* out, int B, int C, int H, int W, int N,
+                          void* stream);
 
 /* ---- K5: fused quantized attention (tcgen05 kind::i8 for Q.K^T and P.V, softmax + P quantization on chip) ----
  * Replaces the bmm/einsum - softmax - fake-quant chain of QuantAttnBlock.forward (qdiff/quant_block.py:431-445),

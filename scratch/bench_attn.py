@@ -7,7 +7,9 @@ dev=torch.device('cuda:0')
 def aq():
     mk=lambda d,z:(torch.tensor([d],device=dev),torch.tensor([z],device=dev),256)
     return ops.AttnQuant(mk(0.03,128.),mk(0.03,128.),mk(0.03,128.),mk(1/255.,0.))
-for (BH,d,T) in [(800,24,1024),(800,48,256),(128,384,1024),(128,576,256)]:
+import os
+SH=[(800,24,1024)] if os.environ.get('ONE') else [(800,24,1024),(800,48,256),(128,384,1024),(128,576,256)]
+for (BH,d,T) in SH:
     q,k,v=(torch.randn(BH,d,T,device=dev) for _ in range(3))
     A=aq()
     from edadm.ops import _codes_token_major_from_bct,_codes_rows,_f32c

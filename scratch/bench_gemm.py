@@ -46,8 +46,19 @@ for name,B,C,H,N,k in SHAPES:
     us=e0.elapsed_time(e1)*1e3/reps
     tops=2*M*N*K/us/1e6
     line=f"{name:28s} M={M:7d} N={N:5d} K={K:6d}  {us:8.1f} us  {tops:7.1f} TOP/s"
+    ress=[torch.randn_like(outs[0]) for _ in range(nbuf)]
+    for i in range(3): ops.qgemm_i8(qs[i%nbuf],pw,d,z,outs[i%nbuf],hw,residual=ress[i%nbuf])
+    torch.cuda.synchronize(); e0.record()
+    for i in range(reps): ops.qgemm_i8(qs[i%nbuf],pw,d,z,outs[i%nbuf],hw,residual=ress[i%nbuf])
+    e1.record(); torch.cuda.synchronize()
+    us3=e0.elapsed_time(e1)*1e3/reps
+    e0.record()
+    for i in range(reps): torch.add(outs[i%nbuf],ress[i%nbuf],out=outs[(i+1)%nbuf])
+    e1.record(); torch.cuda.synchronize()
+    line+=f"  +res {us3:7.1f} us (add alone {e0.elapsed_time(e1)*1e3/reps:6.1f})"
     # library yardstick: torch._int_mm on the im2col'd problem size
     try:
+        if os.environ.get("NOLIB"): raise RuntimeError("skipped")
         a=torch.randint(-128,127,(M,K),device=dev,dtype=torch.int8); b=torch.randint(-8,7,(K,N),device=dev,dtype=torch.int8)
         for i in range(2): torch._int_mm(a,b)
         torch.cuda.synchronize(); e0.record()

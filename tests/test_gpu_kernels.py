@@ -288,6 +288,33 @@ def test_qgemm_linear(cuda, M, K, N, bits):
     assert _rel_l2(out, ref) < 1e-5
 
 
+@pytest.mark.parametrize("shape,N,k,bits", [((2, 128, 16, 16), 128, 3, 4), ((4, 64, 8, 8), 100, 3, 4), ((2, 64, 16, 16), 96, 3, 8),
+                                            ((300, 320), 320, 0, 4), ((77, 768), 98, 0, 4), ((200, 128), 64, 0, 8)])
+def test_qgemm_residual_epilogue(cuda, shape, N, k, bits):
+    """`conv(x) + residual` fused into the epilogue == the separate fp32 add, bit for bit (quant_block.py:116,192)"""
+    from edadm import ops
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(*shape, generator=g)
+    conv = len(shape) == 4
+    w = torch.randn(N, shape[1], k, k, generator=g) * 0.05 if conv else torch.randn(N, shape[1], generator=g) * 0.05
+    bias = torch.randn(N, generator=g).to(cuda)
+    d_a, z_a = _act_params(x)
+    d_w, z_w, _ = O.init_scale(w, bits, channel_wise=True)
+    pw = ops.pack_weight(w.to(cuda), d_w.to(cuda), z_w.to(cuda), 2 ** bits)
+    aq = ops.ActQuant(d_a.to(cuda), z_a.to(cuda), 256)
+    if conv:
+        q, chsum = ops.act_quant_nhwc(x.to(cuda), aq, k // 2, want_chsum=pw.needs_rowsum)
+        rs = ops.conv_rowsum(chsum, shape[2], shape[3], k, k, 1) if pw.needs_rowsum else None
+        oshape, out_hw = (shape[0], N, shape[2], shape[3]), shape[2] * shape[3]
+    else:
+        q, rs = ops.act_quant_rows(x.to(cuda), aq, want_rowsum=pw.needs_rowsum)
+        oshape, out_hw = (shape[0], N), 1
+    res = torch.randn(*oshape, generator=g).to(cuda)
+    plain = ops.qgemm_i8(q, pw, aq.delta0, aq.zp0, torch.empty(oshape, device=cuda), out_hw, bias=bias, rowsum=rs)
+    fused = ops.qgemm_i8(q, pw, aq.delta0, aq.zp0, torch.empty(oshape, device=cuda), out_hw, bias=bias, rowsum=rs, residual=res)
+    assert torch.equal(fused, plain + res)
+
+
 @pytest.mark.parametrize("B,C,H,N,k,bits", [(2, 128, 16, 128, 3, 4), (1, 224, 64, 224, 3, 4), (4, 64, 8, 96, 3, 4),
                                             (8, 256, 4, 256, 3, 4), (2, 3, 32, 128, 3, 8), (2, 128, 32, 3, 3, 8),
                                             (2, 192, 16, 384, 1, 4), (32, 32, 2, 48, 3, 4)])
@@ -367,7 +394,23 @@ def test_qattn_cross_layout(cuda, B, heads, d, Tq, Tk):
 
 
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,C,H,scale_shift", [(3, 64, 16, False), (2, 192, 8, True), (2, 96, 4, False)])
+@pytest.mark.parametrize("B,C,H,N", [(2, 192, 32, 3), (3, 64, 13, 4), (1, 30, 40, 1), (2, 128, 8, 2)])
+def test_conv3x3_small_n(cuda, B, C, H, N):
+    """output-layer stencil (fp32 x fake-quantized W8) vs the exact fp64 convolution; fp32 summation order only"""
+    from edadm import ops
+    g = torch.Generator().manual_seed(44)
+    x = torch.randn(B, C, H, H + 3, generator=g)
+    w = torch.randn(N, C, 3, 3, generator=g) * 0.05
+    bias = torch.randn(N, generator=g)
+    out = ops.conv3x3_small_n(x.to(cuda), w.to(cuda), bias.to(cuda)).cpu()
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1).float()
+    assert _rel_l2(out, ref) < 1e-6
+    assert ops.conv3x3_small_n_ok(x.to(cuda), w.to(cuda), dict(stride=(1, 1), padding=(1, 1), dilation=(1, 1), groups=1))
+    assert not ops.conv3x3_small_n_ok(x.to(cuda), w.to(cuda), dict(stride=(2, 2), padding=(1, 1), dilation=(1, 1), groups=1))
+
+
+@pytest.mark.parametrize("B,C,H,scale_shift", [(3, 64, 16, False), (2, 192, 8, True), (2, 96, 4, False), (2, 768, 4, True),
+                                               (2, 192, 32, False), (1, 64, 64, False)])
 def test_groupnorm_silu_quant_producer(cuda, B, C, H, scale_shift):
     """GroupNorm (+ scale-shift) + SiLU + quantize in one pass vs the module-by-module path: the codes agree except where
     silu(gn(x))/delta lands within an ulp of a .5 boundary (different-order fp32 arithmetic in GroupNorm itself)."""
