@@ -362,13 +362,22 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
 }
 
-// choose the N tile: the multiple of 16 (<=256) that covers N in the fewest tiles with the least padding
-static int pick_block_n(int N) {
-  const int tiles = (N + MAX_BLOCK_N - 1) / MAX_BLOCK_N;
-  int bn = (N + tiles - 1) / tiles;
-  bn = (bn + 15) & ~15;
-  if (bn < 16) bn = 16;
-  return bn;
+// choose the N tile (multiple of `step`, <= 256).  A persistent CTA needs  waves x k_iters x t(bn)  with
+// waves = ceil(m_tiles * ceil(N / bn) / SMs) and a per-k-iteration time that grows with the bytes staged per iteration
+// (128 activation rows + bn weight rows, plus a fixed issue / latency part worth ~64 rows).  Wide layers with many M tiles
+// end up with the fewest, widest tiles; the small-M layers deep in the UNet and the embedding linears get narrow tiles so
+// that all SMs take part instead of a dozen.
+static int pick_block_n(int N, int m_tiles, int sms, int step) {
+  int best = 0;
+  long long best_cost = 0;
+  for (int bn = step; bn <= MAX_BLOCK_N; bn += step) {
+    const long long tiles = (long long)m_tiles * ((N + bn - 1) / bn);
+    const long long waves = (tiles + sms - 1) / sms;
+    const long long cost = waves * (bn + 192);
+    if (best == 0 || cost <= best_cost) { best = bn; best_cost = cost; }
+    if (bn >= N) break;           // wider tiles only add padding
+  }
+  return best;
 }
 
 }  // namespace edadm
@@ -377,7 +386,7 @@ using namespace edadm;
 
 // Activation codes q: [B][Hp][Wp][Cp_act] u8 (halo included), filter R x S, stride 1:  Ho = Hp-R+1, Wo = Wp-S+1.
 // A 2-D GEMM ([M][Kp] rows) is the special case B=1, Hp=1, Wp=M, R=S=1.
-// Weights wq: [Np][R*S][Cp_w] s8 with Np >= round_up(N, block_n) rows allocated (pack_weight pads with zeros).
+// Weights wq: [Np][R*S][Cp_w] s8 with Np >= N rows allocated (rows past Np are zero-filled by TMA).
 extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const int8_t* wq,
                               int N, int Np, int R, int S, int Cp_w, const float* delta_a, const float* zp_a,
                               const float* delta_w, const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum,
@@ -414,9 +423,11 @@ extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_ac
     }
   }
 
-  const int block_n = pick_block_n(N);
+  if (Np < N) return fail(EDADM_ERR_ARG, "qgemm_i8: weight rows Np=%d < N=%d", Np, N);
+  const int m_tiles_all = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  // row-major outputs are staged in 32-column pieces; weight rows past Np are zero-filled by TMA
+  const int block_n = pick_block_n(N, m_tiles_all, sm_count(), out_hw == 1 ? 32 : 16);
   const int n_tiles = (N + block_n - 1) / block_n;
-  if (Np < n_tiles * block_n) return fail(EDADM_ERR_ARG, "qgemm_i8: weight rows Np=%d < %d needed by the N tiling", Np, n_tiles * block_n);
 
   CUtensorMap map_a, map_b;
   {

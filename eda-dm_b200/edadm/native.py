@@ -30,7 +30,7 @@ _SIGNATURES = {
     "edadm_lp_loss_bwd": (c_int, [P, P, c_int64, c_float, c_float, P, P, P]),
     "edadm_act_quant_nhwc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P, c_int, c_float, c_int64, P]),
     "edadm_act_quant_rows": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, c_int, c_int, P, P, c_int, c_float, c_int, c_int64, P]),
-    "edadm_gn_fold": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P, P, P]),
+    "edadm_gn_fold": (c_int, [P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_float, P, P, P]),
     "edadm_norm_act_quant_nhwc": (c_int, [P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P, c_int, P]),
     "edadm_im2col_u8": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "edadm_conv_rowsum": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),

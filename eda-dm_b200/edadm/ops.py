@@ -352,6 +352,17 @@ def act_quant_nhwc(x, aq: ActQuant, pad: int, want_chsum=False):
     return q, chsum
 
 
+def _cond_rows(scale, shift, B, C):
+    """scale / shift [B, C, 1...] as (tensor, tensor, row stride); the two `th.chunk` halves of one embedding are used in place."""
+    if scale is None:
+        return None, None, 0
+    sc, sh = scale.detach().reshape(B, C), shift.detach().reshape(B, C)
+    if (sc.dtype == torch.float32 and sh.dtype == torch.float32 and sc.stride(1) == 1 and sh.stride(1) == 1
+            and sc.stride(0) == sh.stride(0) and sc.stride(0) >= C):
+        return sc, sh, sc.stride(0)
+    return _f32c(sc), _f32c(sh), C
+
+
 def gn_fold(x, gamma, beta, groups, eps, scale=None, shift=None):
     """GroupNorm statistics of x [B,C,...] folded into per-(sample, channel) affine (a, s), both [B, C]."""
     _need_cuda(x)
@@ -362,10 +373,9 @@ def gn_fold(x, gamma, beta, groups, eps, scale=None, shift=None):
     s = torch.empty((B, C), dtype=torch.float32, device=x.device)
     g = None if gamma is None else _f32c(gamma.detach())
     b = None if beta is None else _f32c(beta.detach())
-    sc = None if scale is None else _f32c(scale.detach()).reshape(B, C)
-    sh = None if shift is None else _f32c(shift.detach()).reshape(B, C)
-    lib.gn_fold(x.data_ptr(), _ptr(g), _ptr(b), _ptr(sc), _ptr(sh), B, C, HW, int(groups), float(eps), a.data_ptr(), s.data_ptr(),
-                _stream())
+    sc, sh, cond_stride = _cond_rows(scale, shift, B, C)
+    lib.gn_fold(x.data_ptr(), _ptr(g), _ptr(b), _ptr(sc), _ptr(sh), cond_stride, B, C, HW, int(groups), float(eps),
+                a.data_ptr(), s.data_ptr(), _stream())
     return a, s
 
 

@@ -89,10 +89,11 @@ int edadm_act_quant_rows(const float* x, uint8_t* q, int32_t* rowsum, int64_t M,
                          int n_levels1, float prescale, int row_group, int64_t group_stride, void* stream);
 /* f1: GroupNorm (+ scale-shift conditioning) + SiLU + quantize as one producer.  edadm_gn_fold reduces x [B][C][HW] to the
  * per-(sample, channel) affine a = rstd*gamma*(1+scale), s = (beta - mean*rstd*gamma)*(1+scale) + shift (scale/shift
- * nullable); edadm_norm_act_quant_nhwc is edadm_act_quant_nhwc applied to silu(a*x + s).  Replaces the GroupNorm32 / SiLU
+ * nullable; row b of scale / shift starts at b*cond_stride, 0 = C, so the two halves of one [B][2C] embedding are
+ * read in place); edadm_norm_act_quant_nhwc is edadm_act_quant_nhwc applied to silu(a*x + s).  Replaces the GroupNorm32 / SiLU
  * modules in front of a QuantModule (openaimodel.py:201-205,225-232; ddim/models/diffusion.py:120-130) on the integer path. */
-int edadm_gn_fold(const float* x, const float* gamma, const float* beta, const float* scale, const float* shift, int B, int C,
-                  int HW, int G, float eps, float* a_out, float* s_out, void* stream);
+int edadm_gn_fold(const float* x, const float* gamma, const float* beta, const float* scale, const float* shift,
+                  int64_t cond_stride, int B, int C, int HW, int G, float eps, float* a_out, float* s_out, void* stream);
 int edadm_norm_act_quant_nhwc(const float* x, const float* aff_a, const float* aff_s, int silu, uint8_t* q, int32_t* chsum,
                               int B, int C, int H, int W, int Cp, int pad, const float* delta0, const float* zp0,
                               int n_levels0, int split, const float* delta1, const float* zp1, int n_levels1, void* stream);
