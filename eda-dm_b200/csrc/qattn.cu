@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
              const __grid_constant__ CUtensorMap map_v, AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer (LDS/STS)
   uint8_t* smem_q = smem;
   uint8_t* smem_k = smem_q + QK_STAGES * ATT_TILE_BYTES;
   uint8_t* smem_v = smem_k + QK_STAGES * ATT_TILE_BYTES;
@@ -229,6 +229,30 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       for (int cc = 0; cc < SM_COLS / 16; ++cc)      // both TMEM loads in flight before the first is consumed
         if (j * ATT_S + col_base + cc * 16 < p.Tk) tmem_ld16(lane_addr + (uint32_t)sb * ATT_S + col_base + cc * 16, raws[cc]);
       tmem_ld_wait();
+      if ((j + 1) * ATT_S <= p.Tk) {
+        // full tile (the common case): all 32 columns of this thread at once, no per-chunk bounds logic, one rescale
+        const int4* cv = reinterpret_cast<const int4*>(&colint[j * ATT_S + col_base]);
+        int v[SM_COLS];
+        int vmax = INT_MIN;
+#pragma unroll
+        for (int q4 = 0; q4 < SM_COLS / 4; ++q4) {
+          const int4 c4 = cv[q4];
+          const uint32_t* raw = &raws[q4 >> 2][(q4 & 3) * 4];
+          v[4 * q4 + 0] = (int)raw[0] + c4.x; v[4 * q4 + 1] = (int)raw[1] + c4.y;
+          v[4 * q4 + 2] = (int)raw[2] + c4.z; v[4 * q4 + 3] = (int)raw[3] + c4.w;
+          vmax = max(max(max(vmax, v[4 * q4 + 0]), max(v[4 * q4 + 1], v[4 * q4 + 2])), v[4 * q4 + 3]);
+        }
+        const float m_new = fmaxf(m, fmaf(biased_to_float<SMALL_V>(vmax), alpha, rc_a));
+        const float cexp = rc_a2 - m_new * 1.4426950408889634f;
+        float add0 = 0.f, add1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < SM_COLS; i += 2) {
+          add0 += ex2_approx(fmaf(biased_to_float<SMALL_V>(v[i]), alpha2, cexp));
+          add1 += ex2_approx(fmaf(biased_to_float<SMALL_V>(v[i + 1]), alpha2, cexp));
+        }
+        l = l * ex2_approx((m - m_new) * 1.4426950408889634f) + (add0 + add1);
+        m = m_new;
+      } else {
 #pragma unroll
       for (int cc = 0; cc < SM_COLS / 16; ++cc) {
         const int c0 = col_base + cc * 16;
@@ -271,6 +295,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
@@ -309,6 +334,28 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       tmem_ld_wait();
       mbar_wait(&bars->p_empty[pb], (uint32_t)(((j >> 1) & 1) ^ 1));
       uint8_t* prow = smem_p + pb * ATT_TILE_BYTES + r * 128;
+      if (fast_codes && (j + 1) * ATT_S <= p.Tk) {
+        // full tile, 8-bit codes: FMA + ex2 + mul + magic-round per score, saturating pack, no bounds logic
+        const int4* cv = reinterpret_cast<const int4*>(&colint[j * ATT_S + col_base]);
+#pragma unroll
+        for (int cc = 0; cc < SM_COLS / 16; ++cc) {
+          uint32_t packed[4];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int4 c4 = cv[cc * 4 + q4];
+            const uint32_t* raw = &raws[cc][q4 * 4];
+            const int k0 = rint_magic(ex2_approx(fmaf(biased_to_float<SMALL_V>((int)raw[0] + c4.x), alpha2, cexp2)) * kq) + zp_i;
+            const int k1 = rint_magic(ex2_approx(fmaf(biased_to_float<SMALL_V>((int)raw[1] + c4.y), alpha2, cexp2)) * kq) + zp_i;
+            const int k2 = rint_magic(ex2_approx(fmaf(biased_to_float<SMALL_V>((int)raw[2] + c4.z), alpha2, cexp2)) * kq) + zp_i;
+            const int k3 = rint_magic(ex2_approx(fmaf(biased_to_float<SMALL_V>((int)raw[3] + c4.w), alpha2, cexp2)) * kq) + zp_i;
+            const uint32_t w = pack_sat_u8(k1, k0, pack_sat_u8(k3, k2, 0u));
+            packed[q4] = w;
+            rp = (int)__dp4a(w, 0x01010101u, (unsigned)rp);
+          }
+          const int chunk = (col_base >> 4) + cc;
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+      } else {
 #pragma unroll
       for (int cc = 0; cc < SM_COLS / 16; ++cc) {
         const int c0 = col_base + cc * 16;
@@ -344,6 +391,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         }
         const int chunk = c0 >> 4;  // one 16-byte chunk per 16 columns, XOR-swizzled by the row (SWIZZLE_128B)
         *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      }
       }
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
