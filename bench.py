@@ -333,8 +333,16 @@ def main():
     peaks, peak_src = measured_peaks()
     int8_peak = 2.0 * peaks["bf16_tflops"]      # dense int8 = 2x bf16 on B200; no int8 entry in MEASURED_PEAKS.json
     achieved = 2.0 * gemm_macs / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    # DRAM bytes per qgemm launch from the committed ncu capture of the same eager step (profiles/, church workload only)
+    traffic = None
+    try:
+        if args.workload == "church" and args.batch in (0, 100):
+            with open(os.path.join(ROOT, "profiles", "launches_r01_church_b100_summary.json")) as f:
+                traffic = json.load(f)["kernels"]["edadm::qgemm_i8_kernel"]["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "tensor", "kernel": "qgemm_i8_kernel (tcgen05 kind::i8)", "achieved": achieved, "peak": int8_peak,
-                "unit": "TOP/s", "frac": achieved / int8_peak, "traffic": None,
+                "unit": "TOP/s", "frac": achieved / int8_peak, "traffic": traffic,
                 "peak_source": f"2 x bf16 burst {peaks['bf16_tflops']} TF/s, {peak_src}",
                 "launches_per_step": n_gemm, "avg_launch_us": 1e3 * gemm_ms / max(1, n_gemm),
                 "share_of_eager_step": gemm_ms / eager_ms if eager_ms else None,

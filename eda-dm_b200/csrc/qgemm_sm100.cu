@@ -135,7 +135,7 @@ __device__ __forceinline__ void load_residual(float (&t)[16], const float* res, 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer (LDS/STS, not generic LD/ST)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.stages * A_STAGE_BYTES;
   float* epi_scale = reinterpret_cast<float*>(smem_b + p.stages * p.b_stage_bytes);
