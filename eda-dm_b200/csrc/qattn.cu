@@ -123,75 +123,92 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
+  // TMA producer and MMA issuer: the whole warp runs the loop (uniform control flow, descriptors in uniform registers), one
+  // elected lane issues -- see the note in qgemm_sm100.cu.
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int vs = 0; uint32_t vphase = 0;
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int j = 0; j < p.s_tiles; ++j) {
-          for (int kc = 0; kc < p.k_chunks; ++kc) {
-            mbar_wait(&bars->qk_empty[stage], phase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    int vs = 0; uint32_t vphase = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int j = 0; j < p.s_tiles; ++j) {
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&bars->qk_empty[stage], phase ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(&bars->qk_full[stage], 2 * ATT_TILE_BYTES);
             tma_load_3d(smem_q + stage * ATT_TILE_BYTES, &map_q, &bars->qk_full[stage], kc * ATT_KB, q0, bh);
             tma_load_3d(smem_k + stage * ATT_TILE_BYTES, &map_k, &bars->qk_full[stage], kc * ATT_KB, j * ATT_S, bh);
-            if (++stage == QK_STAGES) { stage = 0; phase ^= 1; }
           }
-          if (pass == 1) {
-            mbar_wait(&bars->v_empty[vs], vphase ^ 1);
+          __syncwarp();
+          if (++stage == QK_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (pass == 1) {
+          mbar_wait(&bars->v_empty[vs], vphase ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(&bars->v_full[vs], (uint32_t)p.d_chunk * ATT_KB);
             tma_load_3d(smem_v + vs * V_TILE_BYTES, &map_v, &bars->v_full[vs], j * ATT_S, dc * p.d_chunk, bh);
-            if (++vs == V_STAGES) { vs = 0; vphase ^= 1; }
           }
+          __syncwarp();
+          if (++vs == V_STAGES) { vs = 0; vphase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_i8(ATT_S, 0, 0);
-      const uint32_t idesc_o = make_idesc_i8(p.d_chunk, 0, 0);
-      const uint32_t tmem_o = tmem_base + 256;
-      int stage = 0; uint32_t phase = 0;
-      int vs = 0; uint32_t vphase = 0;
-      auto issue_pv = [&](int jj) {
-        const int pb = jj & 1;
-        mbar_wait(&bars->p_full[pb], (uint32_t)((jj >> 1) & 1));
-        mbar_wait(&bars->v_full[vs], vphase);
-        tc_fence_after();
-        const uint64_t adesc = make_smem_desc(smem_u32(smem_p + pb * ATT_TILE_BYTES));
-        const uint64_t bdesc = make_smem_desc(smem_u32(smem_v + vs * V_TILE_BYTES));
-        for (int k = 0; k < ATT_S / UMMA_K; ++k)
-          umma_i8(tmem_o, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)), idesc_o, (jj | k) ? 1u : 0u);
+    const uint32_t idesc_s = make_idesc_i8(ATT_S, 0, 0);
+    const uint32_t idesc_o = make_idesc_i8(p.d_chunk, 0, 0);
+    const uint32_t tmem_o = tmem_base + 256;
+    const uint32_t q_base = smem_u32(smem_q), k_base = smem_u32(smem_k), v_base = smem_u32(smem_v), p_base = smem_u32(smem_p);
+    int stage = 0; uint32_t phase = 0;
+    int vs = 0; uint32_t vphase = 0;
+    auto issue_pv = [&](int jj) {
+      const int pb = jj & 1;
+      mbar_wait(&bars->p_full[pb], (uint32_t)((jj >> 1) & 1));
+      mbar_wait(&bars->v_full[vs], vphase);
+      tc_fence_after();
+      const uint64_t adesc = make_smem_desc(p_base + pb * ATT_TILE_BYTES);
+      const uint64_t bdesc = make_smem_desc(v_base + vs * V_TILE_BYTES);
+      if (elect_one()) {
+        umma_i8(tmem_o, adesc, bdesc, idesc_o, jj ? 1u : 0u);
+        umma_i8(tmem_o, adesc + 2, bdesc + 2, idesc_o, 1u);
+        umma_i8(tmem_o, adesc + 4, bdesc + 4, idesc_o, 1u);
+        umma_i8(tmem_o, adesc + 6, bdesc + 6, idesc_o, 1u);
         umma_commit(&bars->v_empty[vs]);
         umma_commit(&bars->p_empty[pb]);
-        if (++vs == V_STAGES) { vs = 0; vphase ^= 1; }
-      };
-      int g = 0;
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int j = 0; j < p.s_tiles; ++j, ++g) {
-          const int sb = g & 1;
-          mbar_wait(&bars->s_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));
-          tc_fence_after();
-          const uint32_t tmem_s = tmem_base + (uint32_t)sb * ATT_S;
-          for (int kc = 0; kc < p.k_chunks; ++kc) {
-            const int nmma = (kc == p.k_chunks - 1) ? p.k_last_mmas : ATT_KB / UMMA_K;
-            mbar_wait(&bars->qk_full[stage], phase);
-            tc_fence_after();
-            const uint64_t adesc = make_smem_desc(smem_u32(smem_q + stage * ATT_TILE_BYTES));
-            const uint64_t bdesc = make_smem_desc(smem_u32(smem_k + stage * ATT_TILE_BYTES));
-            for (int k = 0; k < nmma; ++k)
-              umma_i8(tmem_s, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)), idesc_s, (kc | k) ? 1u : 0u);
-            umma_commit(&bars->qk_empty[stage]);
-            if (++stage == QK_STAGES) { stage = 0; phase ^= 1; }
-          }
-          umma_commit(&bars->s_full[sb]);
-          if (pass == 1 && j > 0) issue_pv(j - 1);
-        }
       }
-      issue_pv(p.s_tiles - 1);
-      umma_commit(&bars->o_full);
+      __syncwarp();
+      if (++vs == V_STAGES) { vs = 0; vphase ^= 1; }
+    };
+    int g = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int j = 0; j < p.s_tiles; ++j, ++g) {
+        const int sb = g & 1;
+        mbar_wait(&bars->s_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t tmem_s = tmem_base + (uint32_t)sb * ATT_S;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          const int nmma = (kc == p.k_chunks - 1) ? p.k_last_mmas : ATT_KB / UMMA_K;
+          mbar_wait(&bars->qk_full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(q_base + stage * ATT_TILE_BYTES);
+          const uint64_t bdesc = make_smem_desc(k_base + stage * ATT_TILE_BYTES);
+          if (elect_one()) {
+            umma_i8(tmem_s, adesc, bdesc, idesc_s, kc ? 1u : 0u);
+            if (nmma > 1) umma_i8(tmem_s, adesc + 2, bdesc + 2, idesc_s, 1u);
+            if (nmma > 2) umma_i8(tmem_s, adesc + 4, bdesc + 4, idesc_s, 1u);
+            if (nmma > 3) umma_i8(tmem_s, adesc + 6, bdesc + 6, idesc_s, 1u);
+            umma_commit(&bars->qk_empty[stage]);
+          }
+          __syncwarp();
+          if (++stage == QK_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(&bars->s_full[sb]);
+        __syncwarp();
+        if (pass == 1 && j > 0) issue_pv(j - 1);
+      }
     }
+    issue_pv(p.s_tiles - 1);
+    if (elect_one()) umma_commit(&bars->o_full);
+    __syncwarp();
   } else {
     // ===================== softmax + epilogue (warps 2..17) =====================
     // Four threads per query row: warps w, w+4, w+8, w+12 share a TMEM lane quarter and split every 128-key tile into

@@ -27,7 +27,9 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 8;
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;   // TMA warp, MMA warp, 8 epilogue warps
+constexpr int UNPACK_WARPS = 4;     // W4 path: nibble-packed weight tiles -> s8 UMMA operand tiles in shared memory
+constexpr int U_STAGES = 3;         // ring of unpacked B tiles
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32 + UNPACK_WARPS * 32;   // TMA warp, MMA warp, 8 epilogue warps, 4 unpack warps
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct GemmParams {
@@ -40,6 +42,9 @@ struct GemmParams {
   int Wo, HoWo;             // output row length and pixels per image (2-D GEMM: Wo = HoWo = 2^30)
   int block_n, n_tiles, m_tiles;
   int stages, b_stage_bytes;
+  int w4;                   // 1: B arrives as 4-bit codes (two per byte, [Np][taps][Cp/2]) and is unpacked to s8 in shared memory
+  int u_stage_bytes;        // bytes of one unpacked B tile (block_n x 128, rounded to 1024)
+  const int32_t* zoff;      // [N] per-row offset subtracted from the 4-bit codes while unpacking (the weight zero-point)
   int row_staging;          // 1: row-major output staged through shared memory for 128-byte coalesced row stores
   // epilogue
   int out_hw;               // pixels per image of the OUTPUT layout (1 => row-major [M][N])
@@ -60,11 +65,13 @@ struct __align__(8) PipeBarriers {
   uint64_t empty[MAX_STAGES];
   uint64_t tmem_full[ACC_STAGES];
   uint64_t tmem_empty[ACC_STAGES];
+  uint64_t ufull[U_STAGES];    // unpacked B tile ready (UNPACK_WARPS arrivals)
+  uint64_t uempty[U_STAGES];   // unpacked B tile consumed by the MMAs (tcgen05.commit)
   uint32_t tmem_base;
 };
 
 constexpr int EPI_VEC_BYTES = MAX_BLOCK_N * 4 * 4;  // scale, zterm, cw, bias per column
-constexpr int SMEM_FIXED = 1024 /*align slack*/ + EPI_VEC_BYTES + 256 /*barriers*/;
+constexpr int SMEM_FIXED = 1024 /*align slack*/ + EPI_VEC_BYTES + 1024 /*barriers*/;
 constexpr int ROW_STAGE_LD = 36;                                   // floats per staged row (32 + pad, 16-byte aligned)
 constexpr int ROW_STAGE_BYTES = EPI_WARPS * 32 * ROW_STAGE_LD * 4;  // one 32x32 fp32 tile per epilogue warp
 
@@ -143,20 +150,22 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   int* epi_cw = epi_zterm + MAX_BLOCK_N;
   float* epi_bias = reinterpret_cast<float*>(epi_cw + MAX_BLOCK_N);
   PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(epi_bias + MAX_BLOCK_N);
-  float* row_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // only when p.row_staging
+  float* row_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);   // only when p.row_staging
+  uint8_t* smem_u = reinterpret_cast<uint8_t*>(row_stage) + (p.row_staging ? ROW_STAGE_BYTES : 0);   // only when p.w4 (1024-aligned by construction)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
   const int k_iters = p.taps * p.k_chunks;
   const int stages = p.stages;
-  const uint32_t stage_tx = A_STAGE_BYTES + (uint32_t)p.block_n * BLOCK_K;
+  const uint32_t stage_tx = A_STAGE_BYTES + (uint32_t)p.block_n * (p.w4 ? BLOCK_K / 2 : BLOCK_K);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int i = 0; i < stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], EPI_WARPS); }
+    for (int i = 0; i < U_STAGES; ++i) { mbar_init(&bars->ufull[i], UNPACK_WARPS); mbar_init(&bars->uempty[i], 1); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -169,56 +178,131 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
+  // The producer and the MMA issuer run their loops with the WHOLE warp (uniform control flow, loop state and operand
+  // descriptors in uniform registers) and issue through one elected lane.  Running them inside `if (lane == 0)` makes every
+  // operand "divergent" for the compiler, which then wraps each UTMALDG / UTCIMMA in an ELECT + R2UR + BRA.U.ANY loop: the
+  // single issuing thread needed ~380 cycles per MMA where the tensor pipe needs 134 (N=192, scratch/mma_peak.py).
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
-        const int m0 = m_blk * BLOCK_M;
-        const int b0 = m0 / p.HoWo;
-        const int rem = m0 - b0 * p.HoWo;
-        const int oh0 = rem / p.Wo, ow0 = rem - oh0 * p.Wo;
-        const int n0 = n_blk * p.block_n;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int kh = tap / p.S, kw = tap - kh * p.S;
-          for (int kc = 0; kc < p.k_chunks; ++kc) {
-            mbar_wait(&bars->empty[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
+      const int m0 = m_blk * BLOCK_M;
+      const int b0 = m0 / p.HoWo;
+      const int rem = m0 - b0 * p.HoWo;
+      const int oh0 = rem / p.Wo, ow0 = rem - oh0 * p.Wo;
+      const int n0 = n_blk * p.block_n;
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const int kh = tap / p.S, kw = tap - kh * p.S;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(&bars->full[stage], stage_tx);
             tma_load_4d(smem_a + stage * A_STAGE_BYTES, &map_a, &bars->full[stage], p.a_c_offset + kc * BLOCK_K, ow0 + kw, oh0 + kh, b0);
-            tma_load_3d(smem_b + stage * p.b_stage_bytes, &map_b, &bars->full[stage], kc * BLOCK_K, tap, n0);
-            if (++stage == stages) { stage = 0; phase ^= 1; }
+            tma_load_3d(smem_b + stage * p.b_stage_bytes, &map_b, &bars->full[stage], p.w4 ? kc * (BLOCK_K / 2) : kc * BLOCK_K, tap, n0);
           }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_i8(p.block_n, /*A u8*/ 0, /*B s8*/ 1);
+    const uint32_t idesc = make_idesc_i8(p.block_n, /*A u8*/ 0, /*B s8*/ 1);
+    const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b), u_base = smem_u32(smem_u);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int us = 0;
+    uint32_t uphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BLOCK_N;
+      int kc = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        const int nmma = (kc == p.k_chunks - 1) ? p.k_last_mmas : BLOCK_K / UMMA_K;
+        if (++kc == p.k_chunks) kc = 0;
+        mbar_wait(&bars->full[stage], phase);
+        if (p.w4) mbar_wait(&bars->ufull[us], uphase);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(a_base + stage * A_STAGE_BYTES);
+        const uint64_t bdesc = make_smem_desc(p.w4 ? u_base + us * p.u_stage_bytes : b_base + stage * p.b_stage_bytes);
+        if (elect_one()) {
+          umma_i8(tmem_d, adesc, bdesc, idesc, it ? 1u : 0u);
+          if (nmma > 1) umma_i8(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
+          if (nmma > 2) umma_i8(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
+          if (nmma > 3) umma_i8(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+          umma_commit(&bars->empty[stage]);     // A tile and (packed) B tile of this stage are free again
+          if (p.w4) umma_commit(&bars->uempty[us]);
+        }
+        __syncwarp();
+        if (p.w4 && ++us == U_STAGES) { us = 0; uphase ^= 1; }
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&bars->tmem_full[acc]);
+      __syncwarp();
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 2 + EPI_WARPS) {
+    // ===================== W4 unpack (warps 10..13) =====================
+    // The packed tile of a stage holds block_n rows of 64 bytes = 128 four-bit codes; inside every 32-bit word the low
+    // nibbles are codes 0..3 and the high nibbles codes 4..7 of that word's 8 codes (edadm_pack_weight_w4), so one AND
+    // and one shift+AND split a word into two words of byte codes.  code - zoff[n] per byte without borrows between
+    // bytes: (code + (0x80 - zoff)) ^ 0x80.  Rows are written in the 128B-swizzled K-major layout the UMMA descriptor
+    // expects (16-byte chunk index XOR (row & 7)), exactly what TMA would have produced for s8 weights.
+    if (p.w4) {
+      const int ut = threadIdx.x - (64 + EPI_WARPS * 32);     // 0..127
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      int us = 0;
+      uint32_t uphase = 0;
+      const int chunks = p.block_n * 4;                       // 16-byte packed chunks per tile
+      constexpr int UT = UNPACK_WARPS * 32;
+      constexpr int MAXC = MAX_BLOCK_N * 4 / UT;              // chunks per thread and K step (8)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BLOCK_N;
+        const int n0 = (tile % p.n_tiles) * p.block_n;
+        // this thread always handles the same rows of a tile: row = ut/4 + 32*j -> per-row constants live in registers
+        uint32_t kz[MAXC];
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) {
+          const int n = n0 + (ut >> 2) + (UT / 4) * j;
+          const int z = (j * UT + ut < chunks && n < p.N) ? __ldg(p.zoff + n) : 0;
+          kz[j] = 0x80808080u - 0x01010101u * (uint32_t)z;
+        }
         for (int it = 0; it < k_iters; ++it) {
-          const int kc = it % p.k_chunks;
-          const int nmma = (kc == p.k_chunks - 1) ? p.k_last_mmas : BLOCK_K / UMMA_K;
-          mbar_wait(&bars->full[stage], phase);
-          tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
-          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * p.b_stage_bytes));
-          for (int k = 0; k < nmma; ++k)
-            umma_i8(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)), idesc, (it | k) ? 1u : 0u);
-          umma_commit(&bars->empty[stage]);
+          mbar_wait_spin(&bars->full[stage], phase);
+          const uint8_t* src = smem_b + stage * p.b_stage_bytes + ut * 16;
+          uint4 pk[MAXC];
+#pragma unroll
+          for (int j = 0; j < MAXC; ++j)
+            if (j * UT + ut < chunks) pk[j] = *reinterpret_cast<const uint4*>(src + j * UT * 16);
+          mbar_wait_spin(&bars->uempty[us], uphase ^ 1);
+          uint8_t* dst = smem_u + us * p.u_stage_bytes + (ut >> 2) * 128;
+          const int c = ut & 3, sw = (ut >> 2) & 7;           // (row & 7) is the same for all of this thread's rows
+          const int off0 = ((2 * c) ^ sw) << 4, off1 = ((2 * c + 1) ^ sw) << 4;
+#pragma unroll
+          for (int j = 0; j < MAXC; ++j) {
+            if (j * UT + ut < chunks) {
+              const uint32_t k = kz[j];
+              uint4 o0, o1;
+              o0.x = ((pk[j].x & 0x0F0F0F0Fu) + k) ^ 0x80808080u; o0.y = (((pk[j].x >> 4) & 0x0F0F0F0Fu) + k) ^ 0x80808080u;
+              o0.z = ((pk[j].y & 0x0F0F0F0Fu) + k) ^ 0x80808080u; o0.w = (((pk[j].y >> 4) & 0x0F0F0F0Fu) + k) ^ 0x80808080u;
+              o1.x = ((pk[j].z & 0x0F0F0F0Fu) + k) ^ 0x80808080u; o1.y = (((pk[j].z >> 4) & 0x0F0F0F0Fu) + k) ^ 0x80808080u;
+              o1.z = ((pk[j].w & 0x0F0F0F0Fu) + k) ^ 0x80808080u; o1.w = (((pk[j].w >> 4) & 0x0F0F0F0Fu) + k) ^ 0x80808080u;
+              uint8_t* row = dst + j * (UT / 4) * 128;
+              *reinterpret_cast<uint4*>(row + off0) = o0;
+              *reinterpret_cast<uint4*>(row + off1) = o1;
+            }
+          }
+          fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->ufull[us]);
+          if (++us == U_STAGES) { us = 0; uphase ^= 1; }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&bars->tmem_full[acc]);
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -387,16 +471,17 @@ using namespace edadm;
 // Activation codes q: [B][Hp][Wp][Cp_act] u8 (halo included), filter R x S, stride 1:  Ho = Hp-R+1, Wo = Wp-S+1.
 // A 2-D GEMM ([M][Kp] rows) is the special case B=1, Hp=1, Wp=M, R=S=1.
 // Weights wq: [Np][R*S][Cp_w] s8 with Np >= N rows allocated (rows past Np are zero-filled by TMA).
-extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const int8_t* wq,
-                              int N, int Np, int R, int S, int Cp_w, const float* delta_a, const float* zp_a,
-                              const float* delta_w, const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum,
-                              const float* bias, const float* residual, float* out, int out_hw, int accumulate, int silu, void* stream) {
+static int launch_qgemm(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const void* wq, int w4,
+                        const int32_t* zoff, int N, int Np, int R, int S, int Cp_w, const float* delta_a, const float* zp_a,
+                        const float* delta_w, const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum,
+                        const float* bias, const float* residual, float* out, int out_hw, int accumulate, int silu, void* stream) {
   if (!q || !wq || !delta_a || !zp_a || !delta_w || !wsum_eff || !out) return fail(EDADM_ERR_ARG, "qgemm_i8: null pointer");
   if (cw && !rowsum) return fail(EDADM_ERR_ARG, "qgemm_i8: cw given without rowsum");
   if (B < 1 || Hp < R || Wp < S || R < 1 || S < 1 || N < 1 || (Cp_act & 15) || (Cp_w & 15) || Cp_w < 16 || a_c_offset < 0 ||
       a_c_offset + 16 > Cp_act + 15)
     return fail(EDADM_ERR_ARG, "qgemm_i8: bad geometry B=%d Hp=%d Wp=%d Cp_act=%d Cp_w=%d R=%d S=%d N=%d", B, Hp, Wp, Cp_act, Cp_w, R, S, N);
   if ((((uintptr_t)q) & 15) || (((uintptr_t)wq) & 15)) return fail(EDADM_ERR_ARG, "qgemm_i8: operands must be 16-byte aligned");
+  if (w4 && (!zoff || (Cp_w & 31))) return fail(EDADM_ERR_ARG, "qgemm_w4a8: packed weights need zoff and a channel pitch that is a multiple of 32 (got %d)", Cp_w);
   const int Ho = Hp - R + 1, Wo = Wp - S + 1;
   const long long M = (long long)B * Ho * Wo;
   if (M > 0x7fffffffLL) return fail(EDADM_ERR_UNSUPPORTED, "qgemm_i8: M too large");
@@ -437,7 +522,13 @@ extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_ac
     int rc = encode_map(&map_a, q, 4, dims, strides, box, "activations");
     if (rc) return rc;
   }
-  {
+  if (w4) {   // two codes per byte, plain (unswizzled) 64-byte rows; the unpack warps produce the swizzled s8 tile
+    cuuint64_t dims[3] = {(cuuint64_t)(Cp_w / 2), (cuuint64_t)(R * S), (cuuint64_t)Np};
+    cuuint64_t strides[2] = {(cuuint64_t)(Cp_w / 2), (cuuint64_t)R * S * (Cp_w / 2)};
+    cuuint32_t box[3] = {(cuuint32_t)(BLOCK_K / 2), 1u, (cuuint32_t)block_n};
+    int rc = encode_map(&map_b, wq, 3, dims, strides, box, "packed weights", CU_TENSOR_MAP_DATA_TYPE_UINT8, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  } else {
     cuuint64_t dims[3] = {(cuuint64_t)Cp_w, (cuuint64_t)(R * S), (cuuint64_t)Np};
     cuuint64_t strides[2] = {(cuuint64_t)Cp_w, (cuuint64_t)R * S * Cp_w};
     cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, 1u, (cuuint32_t)block_n};
@@ -454,11 +545,13 @@ extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_ac
   p.Wo = flat ? (1 << 30) : Wo;
   p.HoWo = flat ? (1 << 30) : Ho * Wo;
   p.block_n = block_n; p.n_tiles = n_tiles; p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
-  p.b_stage_bytes = (block_n * BLOCK_K + 1023) & ~1023;
+  p.w4 = w4; p.zoff = zoff;
+  p.b_stage_bytes = (block_n * (w4 ? BLOCK_K / 2 : BLOCK_K) + 1023) & ~1023;
+  p.u_stage_bytes = (block_n * BLOCK_K + 1023) & ~1023;
   // row-major outputs (linear layers) are staged through smem; needs whole float4s per row and no rowsum / accumulate / SiLU
   p.row_staging = (out_hw == 1 && !cw && !accumulate && !silu && (N % 4) == 0 && (block_n % 32) == 0 && ((reinterpret_cast<uintptr_t>(residual) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 1 : 0;
-  const int fixed = SMEM_FIXED + (p.row_staging ? ROW_STAGE_BYTES : 0);
+  const int fixed = SMEM_FIXED + (p.row_staging ? ROW_STAGE_BYTES : 0) + (w4 ? U_STAGES * p.u_stage_bytes : 0);
   p.stages = (SMEM_LIMIT - fixed) / (A_STAGE_BYTES + p.b_stage_bytes);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   const int smem_bytes = fixed + p.stages * (A_STAGE_BYTES + p.b_stage_bytes);
@@ -476,4 +569,24 @@ extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_ac
   const int grid = tiles < sm_count() ? tiles : sm_count();
   qgemm_i8_kernel<<<grid, GEMM_THREADS, smem_bytes, (cudaStream_t)stream>>>(map_a, map_b, p);
   return check_launch("qgemm_i8");
+}
+
+extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const int8_t* wq,
+                              int N, int Np, int R, int S, int Cp_w, const float* delta_a, const float* zp_a,
+                              const float* delta_w, const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum,
+                              const float* bias, const float* residual, float* out, int out_hw, int accumulate, int silu, void* stream) {
+  return launch_qgemm(q, B, Hp, Wp, Cp_act, a_c_offset, wq, 0, nullptr, N, Np, R, S, Cp_w, delta_a, zp_a, delta_w, wsum_eff, cw,
+                      rowsum, bias, residual, out, out_hw, accumulate, silu, stream);
+}
+
+// Same GEMM with the weights stored as 4-bit codes, two per byte: wq4 [Np][R*S][Cp_w/2] (Cp_w % 32 == 0; inside each 32-bit
+// word the low nibbles hold codes 0..3 and the high nibbles codes 4..7 of the word's 8 channels, see edadm_pack_weight_w4).
+// The kernel unpacks every tile to s8 (code - zoff[n]) in shared memory before the MMA; wsum_eff must be sum_k (code - zoff).
+extern "C" int edadm_qgemm_w4a8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const uint8_t* wq4,
+                                const int32_t* zoff, int N, int Np, int R, int S, int Cp_w, const float* delta_a,
+                                const float* zp_a, const float* delta_w, const int32_t* wsum_eff, const float* bias,
+                                const float* residual, float* out, int out_hw, int accumulate, int silu, void* stream) {
+  if (!zoff) return fail(EDADM_ERR_ARG, "qgemm_w4a8: null zoff");
+  return launch_qgemm(q, B, Hp, Wp, Cp_act, a_c_offset, wq4, 1, zoff, N, Np, R, S, Cp_w, delta_a, zp_a, delta_w, wsum_eff, nullptr,
+                      nullptr, bias, residual, out, out_hw, accumulate, silu, stream);
 }

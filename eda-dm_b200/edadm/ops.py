@@ -270,14 +270,21 @@ def gemm_padded_n(n: int) -> int:
 class PackedWeight:
     """Integer weight codes of one QuantModule K-range in the layout the GEMM consumes."""
 
-    __slots__ = ("wq", "wsum_eff", "cw", "delta_w", "N", "Np", "R", "S", "C", "Cp", "needs_rowsum", "codes")
+    __slots__ = ("wq", "wsum_eff", "cw", "delta_w", "N", "Np", "R", "S", "C", "Cp", "needs_rowsum", "codes", "w4", "zoff")
 
     def nbytes(self):
         return self.wq.numel()
 
 
-def pack_weight(w, delta, zero_point, n_levels, alpha=None, c_begin=0, c_end=None, want_codes=False) -> PackedWeight:
-    """w: [N, C, R, S] / [N, C, T] / [N, C] fp32 -> PackedWeight for channels [c_begin, c_end)."""
+# Keep <= 4-bit weight codes nibble-packed (two per byte, half the weight bytes in HBM / L2) and let the GEMM unpack them in
+# shared memory (edadm_pack_weight_w4 + edadm_qgemm_w4a8).  Bit-identical to the s8 layout; off by default because the
+# unpack stage currently costs more than the halved weight traffic saves (church 32x32 conv: 79 us vs 56 us, round 1).
+w4_storage = False
+
+
+def pack_weight(w, delta, zero_point, n_levels, alpha=None, c_begin=0, c_end=None, want_codes=False, w4=None) -> PackedWeight:
+    """w: [N, C, R, S] / [N, C, T] / [N, C] fp32 -> PackedWeight for channels [c_begin, c_end).
+    w4 (default: `w4_storage` when n_levels <= 16): store 4-bit codes two per byte, [Np][R*S][Cp/2] with Cp % 32 == 0."""
     _need_cuda(w)
     w = _f32c(w.detach())
     N, Ctot = w.shape[0], w.shape[1]
@@ -289,7 +296,8 @@ def pack_weight(w, delta, zero_point, n_levels, alpha=None, c_begin=0, c_end=Non
         R, S = 1, 1
     c_end = Ctot if c_end is None else c_end
     Cr = c_end - c_begin
-    Cp = _round_up(Cr, 16)
+    use_w4 = (w4_storage if w4 is None else bool(w4)) and n_levels <= 16
+    Cp = _round_up(Cr, 32 if use_w4 else 16)
     Np = gemm_padded_n(N)
     d = _qparam(delta, w.device)
     z = _qparam(zero_point, w.device)
@@ -298,6 +306,23 @@ def pack_weight(w, delta, zero_point, n_levels, alpha=None, c_begin=0, c_end=Non
     if z.numel() == 1:
         z = z.expand(N).contiguous()
     pw = PackedWeight()
+    pw.w4, pw.zoff = use_w4, None
+    if use_w4:
+        pw.wq = torch.empty((Np, R * S, Cp // 2), dtype=torch.uint8, device=w.device)
+        wsum = torch.empty(Np, dtype=torch.int32, device=w.device)
+        pw.zoff = torch.empty(Np, dtype=torch.int32, device=w.device)
+        pw.cw = None
+        pw.codes = torch.empty((N, Cr, R, S), dtype=torch.uint8, device=w.device) if want_codes else None
+        a = None if alpha is None else _f32c(alpha.detach())
+        lib.pack_weight_w4(w.data_ptr(), _ptr(a), d.data_ptr(), z.data_ptr(), N, Ctot, R, S, c_begin, c_end, Cp, Np,
+                           int(n_levels), pw.wq.data_ptr(), _ptr(pw.codes), wsum.data_ptr(), pw.zoff.data_ptr(), _stream())
+        pw.wsum_eff = wsum
+        pw.needs_rowsum = False
+        dw = torch.zeros(Np, dtype=torch.float32, device=w.device)
+        dw[:N] = d
+        pw.delta_w = dw
+        pw.N, pw.Np, pw.R, pw.S, pw.C, pw.Cp = N, Np, R, S, Cr, Cp
+        return pw
     pw.wq = torch.empty((Np, R * S, Cp), dtype=torch.int8, device=w.device)
     wsum = torch.empty(Np, dtype=torch.int32, device=w.device)
     pw.cw = torch.empty(Np, dtype=torch.int32, device=w.device)
@@ -335,12 +360,12 @@ def _batch_strided(x):
     return _f32c(x), 0
 
 
-def act_quant_nhwc(x, aq: ActQuant, pad: int, want_chsum=False):
-    """x fp32 [B,C,H,W] -> u8 codes [B,H+2p,W+2p,Cp] (halo = zero-point code)."""
+def act_quant_nhwc(x, aq: ActQuant, pad: int, want_chsum=False, cp: int = 0):
+    """x fp32 [B,C,H,W] -> u8 codes [B,H+2p,W+2p,Cp] (halo = zero-point code); Cp = cp or C rounded up to 16."""
     _need_cuda(x)
     x, bstride = _batch_strided(x)
     B, C, H, W = x.shape
-    Cp = _round_up(C, 16)
+    Cp = max(_round_up(C, 16), int(cp))
     q = torch.empty((B, H + 2 * pad, W + 2 * pad, Cp), dtype=torch.uint8, device=x.device)
     chsum = torch.empty((B, H + 2 * pad, W + 2 * pad), dtype=torch.int32, device=x.device) if want_chsum else None
     dev = x.device
@@ -379,12 +404,12 @@ def gn_fold(x, gamma, beta, groups, eps, scale=None, shift=None):
     return a, s
 
 
-def norm_act_quant_nhwc(x, aff_a, aff_s, silu, aq: ActQuant, pad: int, want_chsum=False):
+def norm_act_quant_nhwc(x, aff_a, aff_s, silu, aq: ActQuant, pad: int, want_chsum=False, cp: int = 0):
     """silu(a*x+s) -> u8 codes [B,H+2p,W+2p,Cp] in one pass (GroupNorm + SiLU + activation quantizer)."""
     _need_cuda(x)
     x = _f32c(x)
     B, C, H, W = x.shape
-    Cp = _round_up(C, 16)
+    Cp = max(_round_up(C, 16), int(cp))
     q = torch.empty((B, H + 2 * pad, W + 2 * pad, Cp), dtype=torch.uint8, device=x.device)
     chsum = torch.empty((B, H + 2 * pad, W + 2 * pad), dtype=torch.int32, device=x.device) if want_chsum else None
     dev = x.device
@@ -453,10 +478,17 @@ def qgemm_i8(q, pw: PackedWeight, delta_a, zp_a, out, out_hw, bias=None, rowsum=
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    lib.qgemm_i8(q.data_ptr(), B, Hp, Wp, Cp_act, int(a_c_offset), pw.wq.data_ptr(), pw.N, pw.Np, R, S,
-                 pw.wq.shape[2] if filter_rs is None else pw.wq.shape[1] * pw.wq.shape[2] // (R * S),
-                 da.data_ptr(), za.data_ptr(), pw.delta_w.data_ptr(), pw.wsum_eff.data_ptr(), _ptr(cw), _ptr(rowsum),
-                 _ptr(bias), _ptr(residual), out.data_ptr(), int(out_hw), 1 if accumulate else 0, 1 if silu else 0, _stream())
+    if pw.w4:
+        # 4-bit codes, two per byte; an explicit-im2col GEMM (filter_rs) sees the taps as extra channels (pitch stays % 32)
+        cp_w = pw.Cp if filter_rs is None else pw.wq.shape[1] * pw.Cp // (R * S)
+        lib.qgemm_w4a8(q.data_ptr(), B, Hp, Wp, Cp_act, int(a_c_offset), pw.wq.data_ptr(), pw.zoff.data_ptr(), pw.N, pw.Np,
+                       R, S, cp_w, da.data_ptr(), za.data_ptr(), pw.delta_w.data_ptr(), pw.wsum_eff.data_ptr(), _ptr(bias),
+                       _ptr(residual), out.data_ptr(), int(out_hw), 1 if accumulate else 0, 1 if silu else 0, _stream())
+    else:
+        lib.qgemm_i8(q.data_ptr(), B, Hp, Wp, Cp_act, int(a_c_offset), pw.wq.data_ptr(), pw.N, pw.Np, R, S,
+                     pw.wq.shape[2] if filter_rs is None else pw.wq.shape[1] * pw.wq.shape[2] // (R * S),
+                     da.data_ptr(), za.data_ptr(), pw.delta_w.data_ptr(), pw.wsum_eff.data_ptr(), _ptr(cw), _ptr(rowsum),
+                     _ptr(bias), _ptr(residual), out.data_ptr(), int(out_hw), 1 if accumulate else 0, 1 if silu else 0, _stream())
     if prof is not None:
         ev1.record()
         m = B * (Hp - R + 1) * (Wp - S + 1)

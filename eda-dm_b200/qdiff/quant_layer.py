@@ -30,6 +30,7 @@ class _Backend:
     allow_tf32 = False       # library conv/matmul of the calibration path in strict fp32
     integer_path = True      # use the tcgen05 int8 GEMM whenever it applies
     fuse_norm = True         # GroupNorm + SiLU + activation quantizer as one producer pass on the integer path
+    # (4-bit weight storage with in-smem unpack: `edadm.ops.w4_storage`)
     recon_cuda_graph = True  # capture the reconstruction iteration in one CUDA graph after 3 eager iterations
     qdrop_inkernel_rng = False  # False: QDrop masks come from torch.rand_like (the reference's stream, graph-safe);
                                 # True: drawn inside the kernel (Philox4x32, no extra memory pass)
@@ -426,10 +427,11 @@ class QuantModule(nn.Module):
             raise EdadmError("conv1d with padding is not supported on the integer path")
         Ho = (H + 2 * pad_h - R) // stride + 1
         Wo = (W + 2 * pad - S) // stride + 1
+        cp_act = pw0.Cp if len(packs) == 1 else 0     # nibble-packed weights pad channels to 32: keep the im2col K aligned
         if affine is not None:
-            q, chsum = ops.norm_act_quant_nhwc(x4, affine[0], affine[1], affine[2], aq, pad, want_chsum=needs_rowsum)
+            q, chsum = ops.norm_act_quant_nhwc(x4, affine[0], affine[1], affine[2], aq, pad, want_chsum=needs_rowsum, cp=cp_act)
         else:
-            q, chsum = ops.act_quant_nhwc(x4, aq, pad, want_chsum=needs_rowsum)
+            q, chsum = ops.act_quant_nhwc(x4, aq, pad, want_chsum=needs_rowsum, cp=cp_act)
         rowsum = ops.conv_rowsum(chsum, Ho, Wo, R, S, stride) if needs_rowsum else None
         out = torch.empty((B, N, Ho, Wo), dtype=torch.float32, device=input.device)
         if residual is not None:

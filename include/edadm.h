@@ -122,6 +122,18 @@ int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_
                    const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum, const float* bias,
                    const float* residual, float* out, int out_hw, int accumulate, int silu, void* stream);
 
+/* W4 storage: the same GEMM with the weights kept as 4-bit codes, two per byte -- wq4 u8 [Np][R*S][Cp/2] (Cp % 32 == 0; inside
+ * each 32-bit word byte j = code[c0+j] | code[c0+4+j] << 4), zoff[n] = zp[n] -- and unpacked to s8 (code - zoff[n]) in
+ * shared memory by dedicated warps of the GEMM kernel, tile by tile, ahead of the tensor-core MMA.  Replaces the same
+ * call site as edadm_qgemm_i8 (quant_layer.py:434) for n_bits <= 4 weight quantizers.                                */
+int edadm_pack_weight_w4(const float* w, const float* alpha, const float* delta, const float* zp, int N, int Ctot, int R,
+                         int S, int c_begin, int c_end, int Cp, int Np, int n_levels, uint8_t* wq4, uint8_t* codes,
+                         int32_t* wsum, int32_t* zoff, void* stream);
+int edadm_qgemm_w4a8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const uint8_t* wq4,
+                     const int32_t* zoff, int N, int Np, int R, int S, int Cp_w, const float* delta_a, const float* zp_a,
+                     const float* delta_w, const int32_t* wsum_eff, const float* bias, const float* residual, float* out,
+                     int out_hw, int accumulate, int silu, void* stream);
+
 /* fp32 3x3 convolution (stride 1, zero padding 1) with N <= 4 output channels: the UNet's output layer, whose input the
  * reference leaves un-quantized (qdiff/quant_model.py `disable_network_output_quantization`), so it runs as
  * fp32 activations x fake-quantized 8-bit weights (quant_layer.py:421-434 with disable_act_quant).  x [B][C][H][W],

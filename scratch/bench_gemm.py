@@ -4,6 +4,7 @@ ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0]=[ROOT, os.path.join(ROOT,'eda-dm_b200')]
 import torch
 from edadm import ops
+ops.w4_storage = bool(int(os.environ.get('W4','1')))
 dev=torch.device('cuda:0')
 # (name, B, C, H, N, k)  conv with pad=k//2 ; k=0 -> linear with M=B
 SHAPES=[("church 32x32 c192 3x3",100,192,32,192,3),("church 16x16 c384 3x3",100,384,16,384,3),("church 8x8 c384 3x3",100,384,8,384,3),

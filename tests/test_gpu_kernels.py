@@ -218,9 +218,22 @@ def test_pack_weight_codes(cuda, n_bits):
     w = torch.randn(40, 24, 3, 3, generator=g) * 0.07
     d, z, _ = O.init_scale(w, n_bits, channel_wise=True)
     L = 2 ** n_bits
-    pw = ops.pack_weight(w.to(cuda), d.to(cuda), z.to(cuda), L, want_codes=True)
+    pw = ops.pack_weight(w.to(cuda), d.to(cuda), z.to(cuda), L, want_codes=True, w4=False)
     ref = O.uaq_codes(w, d, z, L)
     assert torch.equal(pw.codes.cpu().float(), ref)
+    if n_bits == 4:
+        # nibble-packed storage: [Np][taps][Cp/2], byte j of every 4-byte word = code[c0+j] | code[c0+4+j] << 4
+        p4 = ops.pack_weight(w.to(cuda), d.to(cuda), z.to(cuda), L, want_codes=True, w4=True)
+        assert p4.w4 and p4.Cp == 32 and p4.wq.dtype == torch.uint8 and tuple(p4.wq.shape) == (p4.Np, 9, 16)
+        assert torch.equal(p4.codes.cpu().float(), ref)
+        b = p4.wq.cpu()[:40].reshape(40, 9, 4, 4).long()                      # [n][tap][word][byte]
+        lo, hi = b & 15, b >> 4
+        un = torch.stack([lo, hi], dim=3).reshape(40, 9, 32)                    # word -> codes c0..c0+3, c0+4..c0+7
+        codes_nc = ref.reshape(40, 24, 9).permute(0, 2, 1).long()               # [n][tap][c]
+        assert torch.equal(un[..., :24], codes_nc)
+        assert torch.equal(un[..., 24:], z.reshape(40, 1, 1).long().expand(40, 9, 8))   # padding == zero-point code
+        assert torch.equal(p4.zoff.cpu()[:40].long(), z.reshape(-1).long())
+        assert torch.equal(p4.wsum_eff.cpu()[:40].long(), (codes_nc - z.reshape(40, 1, 1).long()).sum((1, 2)))
     zoff = z.reshape(-1) if L <= 128 else torch.full((40,), 128.0)
     wq = pw.wq.cpu()[:40].reshape(40, 3, 3, -1)[..., :24].permute(0, 3, 1, 2).float()
     assert torch.equal(wq, ref - zoff.reshape(-1, 1, 1, 1))
@@ -286,6 +299,33 @@ def test_qgemm_linear(cuda, M, K, N, bits):
     assert _rel_l2(out, exact) < 1e-6
     # vs the reference fp32 fake-quant forward (north_star tolerance 1e-3; fp32 summation order only)
     assert _rel_l2(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("shape,N,k", [((2, 128, 16, 16), 128, 3), ((4, 48, 8, 8), 100, 3), ((2, 200, 16, 16), 96, 1),
+                                       ((300, 320), 320, 0), ((77, 720), 98, 0), ((16, 80, 32, 32), 256, 3)])
+def test_qgemm_w4_storage_matches_s8(cuda, shape, N, k):
+    """weights kept as 4-bit codes (two per byte) and unpacked in shared memory == the same GEMM on s8 codes, bit for bit"""
+    from edadm import ops
+    g = torch.Generator().manual_seed(35)
+    x = torch.randn(*shape, generator=g)
+    conv = len(shape) == 4
+    w = torch.randn(N, shape[1], k, k, generator=g) * 0.05 if conv else torch.randn(N, shape[1], generator=g) * 0.05
+    bias = torch.randn(N, generator=g).to(cuda)
+    d_a, z_a = _act_params(x)
+    d_w, z_w, _ = O.init_scale(w, 4, channel_wise=True)
+    aq = ops.ActQuant(d_a.to(cuda), z_a.to(cuda), 256)
+    outs = []
+    for w4 in (False, True):
+        pw = ops.pack_weight(w.to(cuda), d_w.to(cuda), z_w.to(cuda), 16, w4=w4)
+        assert pw.w4 == w4
+        if conv:
+            q, _ = ops.act_quant_nhwc(x.to(cuda), aq, k // 2, cp=pw.Cp)
+            oshape, out_hw = (shape[0], N, shape[2], shape[3]), shape[2] * shape[3]
+        else:
+            q, _ = ops.act_quant_rows(x.to(cuda), aq)
+            oshape, out_hw = (shape[0], N), 1
+        outs.append(ops.qgemm_i8(q, pw, aq.delta0, aq.zp0, torch.empty(oshape, device=cuda), out_hw, bias=bias))
+    assert torch.equal(outs[0], outs[1])
 
 
 @pytest.mark.parametrize("shape,N,k,bits", [((2, 128, 16, 16), 128, 3, 4), ((4, 64, 8, 8), 100, 3, 4), ((2, 64, 16, 16), 96, 3, 8),
