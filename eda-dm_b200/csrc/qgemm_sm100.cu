@@ -29,7 +29,8 @@ constexpr int TMEM_COLS = 512;
 constexpr int EPI_WARPS = 8;
 constexpr int UNPACK_WARPS = 4;     // W4 path: nibble-packed weight tiles -> s8 UMMA operand tiles in shared memory
 constexpr int U_STAGES = 3;         // ring of unpacked B tiles
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32 + UNPACK_WARPS * 32;   // TMA warp, MMA warp, 8 epilogue warps, 4 unpack warps
+constexpr int GEMM_THREADS_S8 = 64 + EPI_WARPS * 32;                         // TMA warp, MMA warp, 8 epilogue warps
+constexpr int GEMM_THREADS_W4 = GEMM_THREADS_S8 + UNPACK_WARPS * 32;         // + 4 unpack warps (W4 storage)
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct GemmParams {
@@ -139,7 +140,9 @@ __device__ __forceinline__ void load_residual(float (&t)[16], const float* res, 
   for (int j = 0; j < 16; ++j) t[j] = (j < n_valid) ? __ldg(res + (long long)j * col_stride) : 0.f;
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// W4 = false: s8 weight tiles straight from TMA, 320 threads (the epilogue keeps its registers); W4 = true: + unpack warps.
+template <bool W4>
+__global__ void __launch_bounds__(W4 ? GEMM_THREADS_W4 : GEMM_THREADS_S8, 1)
 qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer (LDS/STS, not generic LD/ST)
@@ -151,14 +154,14 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   float* epi_bias = reinterpret_cast<float*>(epi_cw + MAX_BLOCK_N);
   PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(epi_bias + MAX_BLOCK_N);
   float* row_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);   // only when p.row_staging
-  uint8_t* smem_u = reinterpret_cast<uint8_t*>(row_stage) + (p.row_staging ? ROW_STAGE_BYTES : 0);   // only when p.w4 (1024-aligned by construction)
+  uint8_t* smem_u = reinterpret_cast<uint8_t*>(row_stage) + (p.row_staging ? ROW_STAGE_BYTES : 0);   // only when W4 (1024-aligned by construction)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
   const int k_iters = p.taps * p.k_chunks;
   const int stages = p.stages;
-  const uint32_t stage_tx = A_STAGE_BYTES + (uint32_t)p.block_n * (p.w4 ? BLOCK_K / 2 : BLOCK_K);
+  const uint32_t stage_tx = A_STAGE_BYTES + (uint32_t)p.block_n * (W4 ? BLOCK_K / 2 : BLOCK_K);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -200,7 +203,7 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           if (elect_one()) {
             mbar_expect_tx(&bars->full[stage], stage_tx);
             tma_load_4d(smem_a + stage * A_STAGE_BYTES, &map_a, &bars->full[stage], p.a_c_offset + kc * BLOCK_K, ow0 + kw, oh0 + kh, b0);
-            tma_load_3d(smem_b + stage * p.b_stage_bytes, &map_b, &bars->full[stage], p.w4 ? kc * (BLOCK_K / 2) : kc * BLOCK_K, tap, n0);
+            tma_load_3d(smem_b + stage * p.b_stage_bytes, &map_b, &bars->full[stage], W4 ? kc * (BLOCK_K / 2) : kc * BLOCK_K, tap, n0);
           }
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -226,20 +229,20 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int nmma = (kc == p.k_chunks - 1) ? p.k_last_mmas : BLOCK_K / UMMA_K;
         if (++kc == p.k_chunks) kc = 0;
         mbar_wait(&bars->full[stage], phase);
-        if (p.w4) mbar_wait(&bars->ufull[us], uphase);
+        if (W4) mbar_wait(&bars->ufull[us], uphase);
         tc_fence_after();
         const uint64_t adesc = make_smem_desc(a_base + stage * A_STAGE_BYTES);
-        const uint64_t bdesc = make_smem_desc(p.w4 ? u_base + us * p.u_stage_bytes : b_base + stage * p.b_stage_bytes);
+        const uint64_t bdesc = make_smem_desc(W4 ? u_base + us * p.u_stage_bytes : b_base + stage * p.b_stage_bytes);
         if (elect_one()) {
           umma_i8(tmem_d, adesc, bdesc, idesc, it ? 1u : 0u);
           if (nmma > 1) umma_i8(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
           if (nmma > 2) umma_i8(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
           if (nmma > 3) umma_i8(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
           umma_commit(&bars->empty[stage]);     // A tile and (packed) B tile of this stage are free again
-          if (p.w4) umma_commit(&bars->uempty[us]);
+          if (W4) umma_commit(&bars->uempty[us]);
         }
         __syncwarp();
-        if (p.w4 && ++us == U_STAGES) { us = 0; uphase ^= 1; }
+        if (W4 && ++us == U_STAGES) { us = 0; uphase ^= 1; }
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
       if (elect_one()) umma_commit(&bars->tmem_full[acc]);
@@ -253,7 +256,7 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // and one shift+AND split a word into two words of byte codes.  code - zoff[n] per byte without borrows between
     // bytes: (code + (0x80 - zoff)) ^ 0x80.  Rows are written in the 128B-swizzled K-major layout the UMMA descriptor
     // expects (16-byte chunk index XOR (row & 7)), exactly what TMA would have produced for s8 weights.
-    if (p.w4) {
+    if (W4) {
       const int ut = threadIdx.x - (64 + EPI_WARPS * 32);     // 0..127
       int stage = 0;
       uint32_t phase = 0;
@@ -341,14 +344,27 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BLOCK_N;
       if (p.row_staging) {
-        mbar_wait(&bars->tmem_full[acc], acc_phase);
-        tc_fence_after();
         // row-major output: 32-column chunks; values go through a per-warp 32x32 smem tile so that every store
-        // instruction writes four complete 128-byte row segments instead of 32 scattered 16-byte pieces
+        // instruction writes four complete 128-byte row segments instead of 32 scattered 16-byte pieces.  The residual
+        // (if any) of a chunk is requested before its TMEM load and conversion, the first chunk's before the accumulator
+        // is even ready.
         float* tile_s = row_stage + (warp - 2) * 32 * ROW_STAGE_LD;
         const int m_base = m_blk * BLOCK_M + quarter * 32;
-        for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
+        const int cq = (lane & 7) * 4;                 // 8 lanes x float4 = one 128-byte row segment
+        float4 tres[8];
+        auto load_res = [&](float4 (&t)[8], int c0) {
+          const int ncol = n0 + c0 + cq;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int mm = m_base + i * 4 + (lane >> 3);
+            t[i] = (mm < p.M && ncol < p.N) ? __ldg(reinterpret_cast<const float4*>(p.residual + (long long)mm * p.N + ncol))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        const bool has_res = p.residual != nullptr;
+        auto do_chunk = [&](int c0, bool res_loaded) {
           uint32_t r[32];
+          if (has_res && !res_loaded) load_res(tres, c0);        // requested ahead of the TMEM load + conversion
           tmem_ld32(taddr + c0, r);
           tmem_ld_wait();
           const int4* zt = reinterpret_cast<const int4*>(epi_zterm + c0);
@@ -365,7 +381,6 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             *reinterpret_cast<float4*>(tile_s + lane * ROW_STAGE_LD + 4 * q) = v;
           }
           __syncwarp();
-          const int cq = (lane & 7) * 4;                 // 8 lanes x float4 = one 128-byte row segment
           const int ncol = n0 + c0 + cq;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -373,15 +388,16 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int mm = m_base + rr;
             if (mm < p.M && ncol < p.N) {
               float4 v = *reinterpret_cast<const float4*>(tile_s + rr * ROW_STAGE_LD + cq);
-              if (p.residual) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(p.residual + (long long)mm * p.N + ncol));
-                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-              }
+              if (has_res) { v.x += tres[i].x; v.y += tres[i].y; v.z += tres[i].z; v.w += tres[i].w; }
               *reinterpret_cast<float4*>(p.out + (long long)mm * p.N + ncol) = v;
             }
           }
           __syncwarp();
-        }
+        };
+        if (has_res && half * 32 < p.block_n) load_res(tres, half * 32);      // first chunk: before the accumulator is ready
+        mbar_wait(&bars->tmem_full[acc], acc_phase);
+        tc_fence_after();
+        for (int c0 = half * 32; c0 < p.block_n; c0 += 64) do_chunk(c0, c0 == half * 32);
       } else {
       uint32_t r0[16], r1[16];
       float t0[16], t1[16];
@@ -561,13 +577,15 @@ static int launch_qgemm(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(qgemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(qgemm_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(qgemm_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return fail(EDADM_ERR_CUDA, "qgemm_i8: cannot opt in to %d B shared memory: %s", SMEM_LIMIT, cudaGetErrorString(e));
     attr_set = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  qgemm_i8_kernel<<<grid, GEMM_THREADS, smem_bytes, (cudaStream_t)stream>>>(map_a, map_b, p);
+  if (w4) qgemm_i8_kernel<true><<<grid, GEMM_THREADS_W4, smem_bytes, (cudaStream_t)stream>>>(map_a, map_b, p);
+  else qgemm_i8_kernel<false><<<grid, GEMM_THREADS_S8, smem_bytes, (cudaStream_t)stream>>>(map_a, map_b, p);
   return check_launch("qgemm_i8");
 }
 

@@ -440,6 +440,36 @@ def act_quant_rows(x2d, aq: ActQuant, want_rowsum=False, row_group=0, group_stri
     return q, rowsum
 
 
+def layernorm_quant_rows(x, norm_weight, norm_bias, eps, aq: ActQuant, want_rowsum=False):
+    """LayerNorm over the last dim of x [..., K] + activation quantizer -> u8 codes [M, Kp] (one pass)."""
+    _need_cuda(x)
+    x2 = _f32c(x.reshape(-1, x.shape[-1]))
+    M, K = x2.shape
+    Kp = _round_up(K, 16)
+    q = torch.empty((M, Kp), dtype=torch.uint8, device=x.device)
+    rowsum = torch.empty(M, dtype=torch.int32, device=x.device) if want_rowsum else None
+    g = None if norm_weight is None else _f32c(norm_weight.detach())
+    b = None if norm_bias is None else _f32c(norm_bias.detach())
+    d0, z0 = _qparam(aq.delta0, x.device), _qparam(aq.zp0, x.device)
+    lib.layernorm_quant_rows(x2.data_ptr(), _ptr(g), _ptr(b), float(eps), q.data_ptr(), _ptr(rowsum), M, K, Kp, d0.data_ptr(),
+                             z0.data_ptr(), aq.levels0, _stream())
+    return q, rowsum
+
+
+def geglu_quant_rows(h, aq: ActQuant, want_rowsum=False):
+    """h [..., 2K] (GEGLU.proj output) -> u8 codes [M, Kp] of h[..., :K] * gelu(h[..., K:]) (one pass)."""
+    _need_cuda(h)
+    h2 = _f32c(h.reshape(-1, h.shape[-1]))
+    M, K2 = h2.shape
+    K = K2 // 2
+    Kp = _round_up(K, 16)
+    q = torch.empty((M, Kp), dtype=torch.uint8, device=h.device)
+    rowsum = torch.empty(M, dtype=torch.int32, device=h.device) if want_rowsum else None
+    d0, z0 = _qparam(aq.delta0, h.device), _qparam(aq.zp0, h.device)
+    lib.geglu_quant_rows(h2.data_ptr(), q.data_ptr(), _ptr(rowsum), M, K, Kp, d0.data_ptr(), z0.data_ptr(), aq.levels0, _stream())
+    return q, rowsum
+
+
 def im2col_u8(q, Ho, Wo, R, S, stride):
     B, Hp, Wp, Cp = q.shape
     a = torch.empty((B * Ho * Wo, R * S * Cp), dtype=torch.uint8, device=q.device)

@@ -87,7 +87,7 @@ def _conv_plus(conv, residual, call):
     observes the conv's own output (calibration caches, FBR taps)."""
     if isinstance(conv, QuantModule) and not conv._forward_hooks:
         return call(residual=residual)
-    return residual + call()
+    return call() + residual
 
 
 class BaseQuantBlock(nn.Module):
@@ -238,22 +238,60 @@ class QuantAttentionBlock(BaseQuantBlock):
 
 
 # ---- transformer block (ImageNet / Stable Diffusion) -------------------------------------------------------
-def cross_attn_forward(self, x, context=None, mask=None):
-    """Replacement `CrossAttention.forward` with quantized q, k, v and softmax (reference quant_block.py:204-235)."""
+def cross_attn_forward(self, x, context=None, mask=None, norm=None, residual=None):
+    """Replacement `CrossAttention.forward` with quantized q, k, v and softmax (reference quant_block.py:204-235).
+    norm / residual (optional, used by QuantBasicTransformerBlock): compute `attn(norm(x), context) + residual` with the
+    LayerNorm folded into the q/k/v activation producers and the add into to_out's GEMM epilogue when nothing observes the
+    intermediate tensors; otherwise module by module."""
     h = self.heads
-    q = self.to_q(x)
-    context = x if context is None else context
-    k, v = self.to_k(context), self.to_v(context)
-    q, k, v = (_zoo_ldm._heads_split(t, h) for t in (q, k, v))
     if mask is not None:
         raise NotImplementedError("attention masks are not used by any EDA-DM configuration")
+    self_attn = context is None
+    if norm is not None:
+        mods = (self.to_q, self.to_k, self.to_v) if self_attn else (self.to_q,)
+        if all(isinstance(m, QuantModule) and m.prenorm_fusable(x, norm) for m in mods):
+            q = self.to_q.forward_prenorm(x, norm, silu=False)
+            if self_attn:
+                k, v = self.to_k.forward_prenorm(x, norm, silu=False), self.to_v.forward_prenorm(x, norm, silu=False)
+            else:
+                k, v = self.to_k(context), self.to_v(context)
+        else:
+            xn = norm(x)
+            ctx = xn if self_attn else context
+            q, k, v = self.to_q(xn), self.to_k(ctx), self.to_v(ctx)
+    else:
+        ctx = x if self_attn else context
+        q, k, v = self.to_q(x), self.to_k(ctx), self.to_v(ctx)
+    q, k, v = (_zoo_ldm._heads_split(t, h) for t in (q, k, v))
     if self.use_act_quant:
         out = qattn.quantized_attention_bnd(q, k, v, h, self.scale, self.act_quantizer_q, self.act_quantizer_k,
                                             self.act_quantizer_v, self.act_quantizer_w)
     else:
         attn = (th.einsum('bid,bjd->bij', q, k) * self.scale).softmax(dim=-1)
         out = _zoo_ldm._heads_merge(th.einsum('bij,bjd->bid', attn, v), h)
-    return self.to_out(out)
+    if residual is None:
+        return self.to_out(out)
+    lin, rest = self.to_out[0], self.to_out[1:]
+    drop_active = any(isinstance(m, nn.Dropout) and m.p > 0 and m.training for m in rest)
+    if drop_active:
+        return self.to_out(out) + residual
+    return _conv_plus(lin, residual, lambda **kw: lin(out, **kw))
+
+
+def _ff_forward(ff, x, norm):
+    """`ff(norm(x)) + x` of BasicTransformerBlock (ldm/modules/attention.py:  FeedForward = [GEGLU | Linear+GELU], Dropout,
+    Linear) with LayerNorm, the GEGLU gate and the residual folded into the two linears' producers / epilogue."""
+    first, drop, last = ff.net[0], ff.net[1], ff.net[2]
+    drop_active = isinstance(drop, nn.Dropout) and drop.p > 0 and drop.training
+    geglu = hasattr(first, 'proj')
+    lin_in = first.proj if geglu else first[0]
+    if drop_active or not isinstance(lin_in, QuantModule) or not isinstance(last, QuantModule):
+        return ff(norm(x)) + x
+    h = lin_in.forward_prenorm(x, norm, silu=False)
+    if geglu:
+        return _conv_plus(last, x, lambda **kw: last.forward_geglu(h, **kw))
+    hh = first[1](h)
+    return _conv_plus(last, x, lambda **kw: last(hh, **kw))
 
 
 class QuantBasicTransformerBlock(BaseQuantBlock):
@@ -280,9 +318,11 @@ class QuantBasicTransformerBlock(BaseQuantBlock):
         if context is None:
             assert len(x) == 2
             x, context = x
-        x = self.attn1(self.norm1(x)) + x
-        x = self.attn2(self.norm2(x), context=context) + x
-        return self.ff(self.norm3(x)) + x
+        # same dataflow as the reference (quant_block.py:254-262): x = attn1(norm1(x)) + x; x = attn2(norm2(x), ctx) + x;
+        # x = ff(norm3(x)) + x -- LayerNorms, GEGLU gate and residual adds ride on the neighbouring QuantModules
+        x = self.attn1(x, norm=self.norm1, residual=x)
+        x = self.attn2(x, context=context, norm=self.norm2, residual=x)
+        return _ff_forward(self.ff, x, self.norm3)
 
     def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
         self.attn1.use_act_quant = act_quant

@@ -360,28 +360,68 @@ class QuantModule(nn.Module):
         self._packed = (key, packs)
         return packs
 
+    def prenorm_fusable(self, x, norm) -> bool:
+        """True when `self(norm(x))` can run as one normalise + quantize producer on the integer path: GroupNorm in front of a
+        conv, LayerNorm in front of a linear; no hook may observe the normalised tensor or this module's input."""
+        if isinstance(norm, nn.GroupNorm):
+            shape_ok = (self.fwd_func is F.conv2d and x.dim() == 4) or (self.fwd_func is F.conv1d and x.dim() == 3)
+        elif isinstance(norm, nn.LayerNorm):
+            shape_ok = (self.fwd_func is F.linear and len(norm.normalized_shape) == 1 and
+                        norm.normalized_shape[0] == x.shape[-1] and self.split == 0)
+        else:
+            return False
+        return bool(backend.fuse_norm and shape_ok and self._integer_path_ok(x) and not self._forward_hooks
+                    and not self._forward_pre_hooks and not norm._forward_hooks)
+
     def forward_prenorm(self, x, norm, silu: bool = True, scale=None, shift=None, split: int = 0, act_fn=F.silu,
-                        residual=None):
-        """`self(silu(norm(x) [* (1 + scale) + shift]))` for a GroupNorm `norm` in front of this conv.  On the integer
-        path GroupNorm + conditioning + SiLU + activation quantization run as ONE producer pass (edadm_gn_fold +
-        edadm_norm_act_quant_nhwc); otherwise it is computed module by module like the reference does."""
+                        residual=None, tokens_out: bool = False):
+        """`self(silu(norm(x) [* (1 + scale) + shift]))` for a GroupNorm in front of this conv (or a LayerNorm in front of this
+        linear).  On the integer path normalisation + conditioning + SiLU + activation quantization run as ONE producer
+        pass (edadm_gn_fold + edadm_norm_act_quant_nhwc, or edadm_layernorm_quant_rows); otherwise it is computed module
+        by module like the reference does.  tokens_out (1x1 conv only): return [B, H*W, N] (the `b c h w -> b (h w) c`
+        rearrangement of SpatialTransformer.forward) straight from the GEMM instead of NCHW."""
         if split != 0 and self.split == 0:
             self.split = split
             self.set_split()
-        shape_ok = (self.fwd_func is F.conv2d and x.dim() == 4) or (self.fwd_func is F.conv1d and x.dim() == 3)
-        fusable = (backend.fuse_norm and isinstance(norm, nn.GroupNorm) and shape_ok
-                   and self._integer_path_ok(x) and not self._forward_hooks and not self._forward_pre_hooks
-                   and not norm._forward_hooks)
-        if not fusable:
+        if not self.prenorm_fusable(x, norm):
             h = norm(x)
             if scale is not None:
                 h = h * (1 + scale) + shift
             if silu:
                 h = act_fn(h)      # the block's own formulation of swish (x*sigmoid(x) in the DDIM UNet, nn.SiLU in LDM)
-            return self(h, split=split, residual=residual)
+            out = self(h, split=split, residual=residual)
+            return out.flatten(2).permute(0, 2, 1) if tokens_out else out
         self.last_path = 'int8'
+        if isinstance(norm, nn.LayerNorm):
+            assert scale is None and not silu
+            return self._finish(self._forward_int8(x, rows=('layernorm', norm), residual=self._epilogue_residual(residual)), residual)
         a, s = ops.gn_fold(x, norm.weight, norm.bias, norm.num_groups, norm.eps, scale, shift)
-        return self._finish(self._forward_int8(x, affine=(a, s, silu), residual=self._epilogue_residual(residual)), residual)
+        return self._finish(self._forward_int8(x, affine=(a, s, silu), residual=self._epilogue_residual(residual),
+                                               tokens_out=tokens_out), residual)
+
+    def forward_geglu(self, h, residual=None):
+        """`self(a * gelu(g))` with (a, g) = h.chunk(2, -1): the GEGLU gate (ldm/modules/attention.py GEGLU.forward) folded
+        into this linear's activation producer (edadm_geglu_quant_rows) on the integer path."""
+        fusable = (backend.fuse_norm and self.fwd_func is F.linear and self.split == 0 and self._integer_path_ok(h)
+                   and not self._forward_hooks and not self._forward_pre_hooks and h.shape[-1] == 2 * self.weight.shape[1])
+        if not fusable:
+            a, g = h.chunk(2, dim=-1)
+            return self(a * F.gelu(g), residual=residual)
+        self.last_path = 'int8'
+        return self._finish(self._forward_int8(h, rows=('geglu',), residual=self._epilogue_residual(residual)), residual)
+
+    def forward_from_tokens(self, y, hw, residual=None):
+        """This 1x1 conv applied to tokens y [B, H*W, C] (the `b (h w) c -> b c h w` + proj_out of SpatialTransformer.forward):
+        token rows ARE the NHWC layout the GEMM consumes, so no transpose pass is needed on the integer path."""
+        H, W = hw
+        B, T, C = y.shape
+        ok = (self.fwd_func is F.conv2d and tuple(self.weight.shape[2:]) == (1, 1) and self.split == 0 and T == H * W
+              and self._integer_path_ok(y) and not self._forward_hooks and not self._forward_pre_hooks
+              and int(self.fwd_kwargs['padding'][0]) == 0 and int(self.fwd_kwargs['stride'][0]) == 1)
+        if not ok:
+            return self(y.permute(0, 2, 1).reshape(B, C, H, W), residual=residual)
+        self.last_path = 'int8'
+        return self._finish(self._forward_int8(y, rows=('tokens', H, W), residual=self._epilogue_residual(residual)), residual)
 
     def _epilogue_residual(self, residual):
         """`residual` if the GEMM epilogue may add it (nothing but a StraightThrough sits between conv and add)."""
@@ -390,10 +430,10 @@ class QuantModule(nn.Module):
     def _finish(self, out, residual):
         out = self.activation_function(out)
         if residual is not None and self._epilogue_residual(residual) is None:
-            out = residual + out
+            out = out + residual
         return out
 
-    def _forward_int8(self, input, affine=None, residual=None):
+    def _forward_int8(self, input, affine=None, residual=None, rows=None, tokens_out=False):
         """Exact integer GEMM: out = dA*dW[n]*sum (qa-za)(qw-zw) + bias  == the reference's fp32 conv of the
         dequantised tensors (quant_layer.py:414-434) without its per-product rounding."""
         packs = self._packed_weights()
@@ -407,14 +447,28 @@ class QuantModule(nn.Module):
         bias = None if self.bias is None else self.bias.detach()
         pw0 = packs[0]
         N = pw0.N
+        if rows is not None and rows[0] == 'tokens':
+            # 1x1 conv over tokens [B, T, C]: rows of codes == NHWC codes; output NCHW (+ residual) straight from the GEMM
+            _, H, W = rows
+            B = input.shape[0]
+            q, rowsum = ops.act_quant_rows(input.reshape(-1, input.shape[-1]), aq, want_rowsum=needs_rowsum)
+            out = torch.empty((B, N, H, W), dtype=torch.float32, device=input.device)
+            if residual is not None:
+                residual = residual.contiguous()
+            self._gemm_chain(q, packs, aqs, out, H * W, bias, rowsum, residual)     # flat GEMM, NCHW store (out_hw = H*W)
+            return out
         if self.fwd_func is F.linear:
             lead = input.shape[:-1]
-            x2 = input.reshape(-1, input.shape[-1])
-            q, rowsum = ops.act_quant_rows(x2, aq, want_rowsum=needs_rowsum)
-            out = torch.empty((x2.shape[0], N), dtype=torch.float32, device=input.device)
+            if rows is None:
+                q, rowsum = ops.act_quant_rows(input.reshape(-1, input.shape[-1]), aq, want_rowsum=needs_rowsum)
+            elif rows[0] == 'layernorm':
+                q, rowsum = ops.layernorm_quant_rows(input, rows[1].weight, rows[1].bias, rows[1].eps, aq, want_rowsum=needs_rowsum)
+            else:   # 'geglu'
+                q, rowsum = ops.geglu_quant_rows(input, aq, want_rowsum=needs_rowsum)
+            out = torch.empty((q.shape[0], N), dtype=torch.float32, device=input.device)
             if residual is not None:
                 residual = residual.reshape(-1, N).contiguous()
-            if x2.shape[0] > 0:
+            if q.shape[0] > 0:
                 self._gemm_chain(q, packs, aqs, out, 1, bias, rowsum, residual)
             return out.reshape(*lead, N)
         x4 = input.unsqueeze(2) if self.fwd_func is F.conv1d else input
@@ -433,6 +487,10 @@ class QuantModule(nn.Module):
         else:
             q, chsum = ops.act_quant_nhwc(x4, aq, pad, want_chsum=needs_rowsum, cp=cp_act)
         rowsum = ops.conv_rowsum(chsum, Ho, Wo, R, S, stride) if needs_rowsum else None
+        if tokens_out and R == 1 and S == 1 and stride == 1 and pad == 0 and residual is None and not self.split:
+            out = torch.empty((B, Ho * Wo, N), dtype=torch.float32, device=input.device)     # row-major [B*T][N] == tokens
+            self._gemm_chain(q.reshape(-1, q.shape[-1]), packs, aqs, out, 1, bias, rowsum, None)
+            return out
         out = torch.empty((B, N, Ho, Wo), dtype=torch.float32, device=input.device)
         if residual is not None:
             residual = residual.contiguous()
@@ -444,7 +502,8 @@ class QuantModule(nn.Module):
             a = ops.im2col_u8(q, Ho, Wo, R, S, stride)
             ops.qgemm_i8(a, pw0, aqs[0].delta, aqs[0].zero_point, out, Ho * Wo, bias=bias, rowsum=rowsum, filter_rs=(1, 1),
                          residual=residual)
-        return out.squeeze(2) if self.fwd_func is F.conv1d else out
+        out = out.squeeze(2) if self.fwd_func is F.conv1d else out
+        return out.flatten(2).permute(0, 2, 1) if tokens_out else out
 
     def _gemm_chain(self, q, packs, aqs, out, out_hw, bias, rowsum, residual=None):
         c_off = 0
@@ -487,7 +546,7 @@ class QuantModule(nn.Module):
             bias = self.org_bias
         self.last_path = 'fake' if (self.use_weight_quant or self.use_act_quant) else 'fp'
         out = self.activation_function(_library_fwd(self.fwd_func, input, weight, bias, self.fwd_kwargs))
-        return out if residual is None else residual + out
+        return out if residual is None else out + residual
 
 
 def _implicit_tiling_ok(B, Ho, Wo):

@@ -246,9 +246,16 @@ class SpatialTransformer(nn.Module):
 
     def forward(self, x, context=None):
         b, c, h, w = x.shape
-        y = self.proj_in(self.norm(x)).reshape(b, -1, h * w).permute(0, 2, 1)
+        # quantized 1x1 convs (qdiff.QuantModule) emit / consume the token layout directly and take the GroupNorm and the
+        # residual with them; plain nn.Conv2d runs module by module
+        if hasattr(self.proj_in, 'forward_prenorm'):
+            y = self.proj_in.forward_prenorm(x, self.norm, silu=False, tokens_out=True)
+        else:
+            y = self.proj_in(self.norm(x)).reshape(b, -1, h * w).permute(0, 2, 1)
         for blk in self.transformer_blocks:
             y = blk(y, context)
+        if hasattr(self.proj_out, 'forward_from_tokens') and not self.proj_out._forward_hooks:
+            return self.proj_out.forward_from_tokens(y, (h, w), residual=x)
         y = y.permute(0, 2, 1).reshape(b, -1, h, w)
         return self.proj_out(y) + x
 

@@ -97,6 +97,14 @@ int edadm_gn_fold(const float* x, const float* gamma, const float* beta, const f
 int edadm_norm_act_quant_nhwc(const float* x, const float* aff_a, const float* aff_s, int silu, uint8_t* q, int32_t* chsum,
                               int B, int C, int H, int W, int Cp, int pad, const float* delta0, const float* zp0,
                               int n_levels0, int split, const float* delta1, const float* zp1, int n_levels1, void* stream);
+/* Transformer-block producers (ldm/modules/attention.py BasicTransformerBlock as rewritten by quant_block.py:237-262):
+ * edadm_layernorm_quant_rows = nn.LayerNorm (norm1/2/3) + the activation quantizer of the linear behind it, one pass;
+ * edadm_geglu_quant_rows = GEGLU's `x * F.gelu(gate)` (attention.py GEGLU.forward) + the activation quantizer of
+ * FeedForward.net[2].  h is GEGLU.proj's output [M][2K]; q [M][Kp] u8; rowsum nullable.                             */
+int edadm_layernorm_quant_rows(const float* x, const float* gamma, const float* beta, float eps, uint8_t* q, int32_t* rowsum,
+                               int64_t M, int K, int Kp, const float* delta, const float* zp, int n_levels, void* stream);
+int edadm_geglu_quant_rows(const float* h, uint8_t* q, int32_t* rowsum, int64_t M, int K, int Kp, const float* delta,
+                           const float* zp, int n_levels, void* stream);
 int edadm_im2col_u8(const uint8_t* q, uint8_t* a, int B, int Hp, int Wp, int Cp, int Ho, int Wo, int R, int S,
                     int stride, void* stream);
 int edadm_conv_rowsum(const int32_t* chsum, int32_t* rowsum, int B, int Hp, int Wp, int Ho, int Wo, int R, int S,

@@ -477,3 +477,83 @@ def test_groupnorm_silu_quant_producer(cuda, B, C, H, scale_shift):
     diff = (codes - ref_codes).abs()
     assert float(diff.max()) <= 1.0                                   # never more than one code step
     assert float((diff > 0).float().mean()) < 2e-3                    # and only at rounding boundaries
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,K", [(300, 384), (64, 96), (1000, 1536), (33, 50)])
+def test_layernorm_quant_rows(cuda, M, K):
+    """LayerNorm + activation quantizer in one pass vs nn.LayerNorm followed by the quantizer (rounding-boundary flips only)"""
+    from edadm import ops
+    g = torch.Generator().manual_seed(51)
+    x = torch.randn(M, K, generator=g) * 2 + 0.3
+    ln = torch.nn.LayerNorm(K)
+    ln.weight.data = torch.randn(K, generator=g) * 0.3 + 1
+    ln.bias.data = torch.randn(K, generator=g) * 0.2
+    with torch.no_grad():
+        y = ln(x)
+    d, z = _act_params(y)
+    ref = O.uaq_codes(y, d, z, 256)
+    q, rs = ops.layernorm_quant_rows(x.to(cuda), ln.weight.to(cuda), ln.bias.to(cuda), ln.eps,
+                                     ops.ActQuant(d.to(cuda), z.to(cuda), 256), want_rowsum=True)
+    codes = q.cpu()[:, :K].float()
+    diff = (codes - ref).abs()
+    assert float(diff.max()) <= 1.0 and float((diff > 0).float().mean()) < 2e-3
+    assert int(q.cpu()[:, K:].sum()) == 0
+    assert torch.equal(rs.cpu().long(), q.cpu().long().sum(1))
+
+
+@pytest.mark.parametrize("M,K", [(200, 1536), (77, 96), (1024, 3072), (5, 20)])
+def test_geglu_quant_rows(cuda, M, K):
+    """GEGLU gate + quantizer in one pass == F.gelu on the device followed by the quantizer (same erf formulation)"""
+    from edadm import ops
+    g = torch.Generator().manual_seed(52)
+    h = torch.randn(M, 2 * K, generator=g) * 1.5
+    a, gate = h.to(cuda).chunk(2, dim=-1)
+    y = (a * F.gelu(gate)).cpu()
+    d, z = _act_params(y)
+    ref = O.uaq_codes(y, d, z, 256)
+    q, rs = ops.geglu_quant_rows(h.to(cuda), ops.ActQuant(d.to(cuda), z.to(cuda), 256), want_rowsum=True)
+    codes = q.cpu()[:, :K].float()
+    diff = (codes - ref).abs()
+    assert float(diff.max()) <= 1.0 and float((diff > 0).float().mean()) < 1e-4
+    assert torch.equal(rs.cpu().long(), q.cpu().long().sum(1))
+
+
+def test_transformer_block_fusions_match_unfused(cuda):
+    """QuantBasicTransformerBlock + SpatialTransformer with LayerNorm / GEGLU / residual / token-layout fusions vs the same
+    modules run one by one (backend.fuse_norm off): same integer GEMMs, only normalisation rounding differs"""
+    import copy
+    from qdiff import QuantModel, set_weight_quantize_params, set_act_quantize_params
+    from qdiff.quant_layer import backend, QuantModule
+    from unet_zoo.ldm_unet import UNetModel
+    torch.manual_seed(7)
+    model = UNetModel(image_size=16, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=1,
+                      attention_resolutions=(1, 2), channel_mult=(1, 2), num_heads=4, use_spatial_transformer=True,
+                      transformer_depth=1, context_dim=48).to(cuda).eval()
+    for p in model.parameters():
+        if p.dim() > 1 and float(p.abs().max()) == 0:
+            torch.nn.init.normal_(p, std=0.02)            # zero-initialised proj_out would hide the path
+    wq = dict(n_bits=4, symmetric=True, channel_wise=True, scale_method='mse')
+    aq = dict(n_bits=8, symmetric=True, channel_wise=False, scale_method='mse', leaf_param=True, prob=1.0)
+    qnn = QuantModel(model, wq, aq, sm_abit=8).to(cuda).eval()
+    qnn.set_first_last_layer_to_8bit()
+    qnn.disable_network_output_quantization()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(8, 4, 16, 16, generator=g).to(cuda)
+    t = torch.randint(0, 1000, (8,), generator=g).to(cuda)
+    ctx = torch.randn(8, 5, 48, generator=g).to(cuda)
+    qnn.set_quant_state(True, True)
+    with torch.no_grad():
+        set_weight_quantize_params(qnn, (x, t, ctx))
+        set_act_quantize_params(qnn, (x, t, ctx), all_attention=True)
+        backend.fuse_norm = True
+        y1 = qnn(x, t, ctx)
+        paths = {n: m.last_path for n, m in qnn.named_modules() if isinstance(m, QuantModule)}
+        backend.fuse_norm = False
+        try:
+            y0 = qnn(x, t, ctx)
+        finally:
+            backend.fuse_norm = True
+    assert sum(p == 'int8' for p in paths.values()) >= len(paths) - 2
+    assert _rel_l2(y1, y0) < 5e-2     # chaotic amplification of single code flips (DESIGN.md section 5); typically ~1e-3
+    assert torch.isfinite(y1).all()
