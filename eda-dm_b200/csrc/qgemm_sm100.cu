@@ -51,6 +51,7 @@ struct GemmParams {
   int out_hw;               // pixels per image of the OUTPUT layout (1 => row-major [M][N])
   int accumulate, silu;
   const float* residual;   // optional fp32 tensor laid out like `out`, added after bias / accumulate / SiLU
+  const float* bias_img;   // optional fp32 [images][N]: per-(image, channel) term added like a residual (timestep embedding)
   const float* delta_a;     // device scalars (nn.Parameter storage): no host sync on the path
   const float* zp_a;
   const float* delta_w;     // [N]
@@ -340,7 +341,9 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const long long img = row_ok ? m / p.out_hw : 0;
       const long long pix = row_ok ? m - img * p.out_hw : 0;
       float* out_row = p.out + img * (long long)p.N * p.out_hw + pix + (long long)n0 * p.out_hw;
-      const float* res_row = p.residual ? p.residual + (out_row - p.out) : nullptr;
+      // the per-image bias rides on the residual machinery: same prefetch, element (img, n) instead of (m, n)
+      const float* res_row = p.residual ? p.residual + (out_row - p.out) : (p.bias_img ? p.bias_img + img * (long long)p.N + n0 : nullptr);
+      const long long res_stride = p.residual ? col_stride : 1;
 
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BLOCK_N;
       if (p.row_staging) {
@@ -403,7 +406,7 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       float t0[16], t1[16];
       int c0 = half * 16;
       const bool has_res = res_row != nullptr && row_ok;
-      if (has_res && c0 < p.block_n) load_residual(t0, res_row + (long long)c0 * col_stride, col_stride, p.N - (n0 + c0));
+      if (has_res && c0 < p.block_n) load_residual(t0, res_row + (long long)c0 * res_stride, res_stride, p.N - (n0 + c0));
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       if (c0 < p.block_n) { tmem_ld16(taddr + c0, r0); }
@@ -413,7 +416,7 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int c1 = c0 + 32;
         if (c1 < p.block_n) {
           tmem_ld16(taddr + c1, r1);
-          if (has_res) load_residual(t1, res_row + (long long)c1 * col_stride, col_stride, p.N - (n0 + c1));
+          if (has_res) load_residual(t1, res_row + (long long)c1 * res_stride, res_stride, p.N - (n0 + c1));
         }
         if (row_ok) {
           const int nv = p.N - (n0 + c0);
@@ -430,7 +433,7 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int c2 = c0 + 64;
         if (c2 < p.block_n) {
           tmem_ld16(taddr + c2, r0);
-          if (has_res) load_residual(t0, res_row + (long long)c2 * col_stride, col_stride, p.N - (n0 + c2));
+          if (has_res) load_residual(t0, res_row + (long long)c2 * res_stride, res_stride, p.N - (n0 + c2));
         }
         if (c1 < p.block_n && row_ok) {
           const int nv = p.N - (n0 + c1);
@@ -490,7 +493,10 @@ using namespace edadm;
 static int launch_qgemm(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const void* wq, int w4,
                         const int32_t* zoff, int N, int Np, int R, int S, int Cp_w, const float* delta_a, const float* zp_a,
                         const float* delta_w, const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum,
-                        const float* bias, const float* residual, float* out, int out_hw, int accumulate, int silu, void* stream) {
+                        const float* bias, const float* bias_img, const float* residual, float* out, int out_hw, int accumulate,
+                        int silu, void* stream) {
+  if (bias_img && (residual || out_hw == 1))
+    return fail(EDADM_ERR_UNSUPPORTED, "qgemm_i8: bias_img needs an NCHW output (out_hw > 1) and cannot be combined with residual");
   if (!q || !wq || !delta_a || !zp_a || !delta_w || !wsum_eff || !out) return fail(EDADM_ERR_ARG, "qgemm_i8: null pointer");
   if (cw && !rowsum) return fail(EDADM_ERR_ARG, "qgemm_i8: cw given without rowsum");
   if (B < 1 || Hp < R || Wp < S || R < 1 || S < 1 || N < 1 || (Cp_act & 15) || (Cp_w & 15) || Cp_w < 16 || a_c_offset < 0 ||
@@ -571,7 +577,7 @@ static int launch_qgemm(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int
   p.stages = (SMEM_LIMIT - fixed) / (A_STAGE_BYTES + p.b_stage_bytes);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   const int smem_bytes = fixed + p.stages * (A_STAGE_BYTES + p.b_stage_bytes);
-  p.out_hw = out_hw; p.accumulate = accumulate; p.silu = silu; p.residual = residual;
+  p.out_hw = out_hw; p.accumulate = accumulate; p.silu = silu; p.residual = residual; p.bias_img = bias_img;
   p.delta_a = delta_a; p.zp_a = zp_a; p.delta_w = delta_w; p.wsum_eff = wsum_eff; p.cw = cw; p.rowsum = rowsum;
   p.bias = bias; p.out = out;
 
@@ -592,9 +598,10 @@ static int launch_qgemm(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int
 extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const int8_t* wq,
                               int N, int Np, int R, int S, int Cp_w, const float* delta_a, const float* zp_a,
                               const float* delta_w, const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum,
-                              const float* bias, const float* residual, float* out, int out_hw, int accumulate, int silu, void* stream) {
+                              const float* bias, const float* bias_img, const float* residual, float* out, int out_hw,
+                              int accumulate, int silu, void* stream) {
   return launch_qgemm(q, B, Hp, Wp, Cp_act, a_c_offset, wq, 0, nullptr, N, Np, R, S, Cp_w, delta_a, zp_a, delta_w, wsum_eff, cw,
-                      rowsum, bias, residual, out, out_hw, accumulate, silu, stream);
+                      rowsum, bias, bias_img, residual, out, out_hw, accumulate, silu, stream);
 }
 
 // Same GEMM with the weights stored as 4-bit codes, two per byte: wq4 [Np][R*S][Cp_w/2] (Cp_w % 32 == 0; inside each 32-bit
@@ -603,8 +610,9 @@ extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_ac
 extern "C" int edadm_qgemm_w4a8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const uint8_t* wq4,
                                 const int32_t* zoff, int N, int Np, int R, int S, int Cp_w, const float* delta_a,
                                 const float* zp_a, const float* delta_w, const int32_t* wsum_eff, const float* bias,
-                                const float* residual, float* out, int out_hw, int accumulate, int silu, void* stream) {
+                                const float* bias_img, const float* residual, float* out, int out_hw, int accumulate, int silu,
+                                void* stream) {
   if (!zoff) return fail(EDADM_ERR_ARG, "qgemm_w4a8: null zoff");
   return launch_qgemm(q, B, Hp, Wp, Cp_act, a_c_offset, wq4, 1, zoff, N, Np, R, S, Cp_w, delta_a, zp_a, delta_w, wsum_eff, nullptr,
-                      nullptr, bias, residual, out, out_hw, accumulate, silu, stream);
+                      nullptr, bias, bias_img, residual, out, out_hw, accumulate, silu, stream);
 }

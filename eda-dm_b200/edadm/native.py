@@ -35,11 +35,11 @@ _SIGNATURES = {
     "edadm_im2col_u8": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "edadm_conv_rowsum": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "edadm_pack_weight": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
-    "edadm_qgemm_i8": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
+    "edadm_qgemm_i8": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "edadm_layernorm_quant_rows": (c_int, [P, P, P, c_float, P, P, c_int64, c_int, c_int, P, P, c_int, P]),
     "edadm_geglu_quant_rows": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, c_int, P]),
     "edadm_pack_weight_w4": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
-    "edadm_qgemm_w4a8": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
+    "edadm_qgemm_w4a8": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "edadm_conv3x3_small_n": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
     "edadm_qattn_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int,
                                 c_float, P, c_int64, c_int64, c_int64, c_int64, P]),

@@ -488,9 +488,11 @@ gemm_profile = None   # bench.py sets this to a list to get (start_event, end_ev
 
 
 def qgemm_i8(q, pw: PackedWeight, delta_a, zp_a, out, out_hw, bias=None, rowsum=None, a_c_offset=0,
-             accumulate=False, silu=False, filter_rs=None, residual=None):
+             accumulate=False, silu=False, filter_rs=None, residual=None, bias_img=None):
     """Launch the tcgen05 GEMM.  q: [B,Hp,Wp,Cp] u8 codes (or [M,Kp] for a flat GEMM).  residual (fp32, contiguous, laid
     out like `out`) is added in the epilogue: the `x + h` of the residual / attention blocks without a separate pass."""
+    if bias_img is not None:
+        bias_img = _f32c(bias_img.detach().reshape(-1, pw.N))
     if residual is not None:
         if residual.dtype != torch.float32 or not residual.is_contiguous() or residual.numel() != out.numel():
             raise EdadmError("qgemm_i8: residual must be a contiguous fp32 tensor of the output's size")
@@ -513,12 +515,12 @@ def qgemm_i8(q, pw: PackedWeight, delta_a, zp_a, out, out_hw, bias=None, rowsum=
         cp_w = pw.Cp if filter_rs is None else pw.wq.shape[1] * pw.Cp // (R * S)
         lib.qgemm_w4a8(q.data_ptr(), B, Hp, Wp, Cp_act, int(a_c_offset), pw.wq.data_ptr(), pw.zoff.data_ptr(), pw.N, pw.Np,
                        R, S, cp_w, da.data_ptr(), za.data_ptr(), pw.delta_w.data_ptr(), pw.wsum_eff.data_ptr(), _ptr(bias),
-                       _ptr(residual), out.data_ptr(), int(out_hw), 1 if accumulate else 0, 1 if silu else 0, _stream())
+                       _ptr(bias_img), _ptr(residual), out.data_ptr(), int(out_hw), 1 if accumulate else 0, 1 if silu else 0, _stream())
     else:
         lib.qgemm_i8(q.data_ptr(), B, Hp, Wp, Cp_act, int(a_c_offset), pw.wq.data_ptr(), pw.N, pw.Np, R, S,
                      pw.wq.shape[2] if filter_rs is None else pw.wq.shape[1] * pw.wq.shape[2] // (R * S),
                      da.data_ptr(), za.data_ptr(), pw.delta_w.data_ptr(), pw.wsum_eff.data_ptr(), _ptr(cw), _ptr(rowsum),
-                     _ptr(bias), _ptr(residual), out.data_ptr(), int(out_hw), 1 if accumulate else 0, 1 if silu else 0, _stream())
+                     _ptr(bias), _ptr(bias_img), _ptr(residual), out.data_ptr(), int(out_hw), 1 if accumulate else 0, 1 if silu else 0, _stream())
     if prof is not None:
         ev1.record()
         m = B * (Hp - R + 1) * (Wp - S + 1)

@@ -145,15 +145,18 @@ def _quant_resblock_forward(blk, x, emb, split=0):
     fuse = _prenorm_ok(in_conv, blk) and _prenorm_ok(out_conv, blk)
     if not fuse:
         return _zoo_ldm.resblock_forward(blk, x, emb, split)
+    emb_out = blk.emb_layers(emb).type(x.dtype)
+    while emb_out.dim() < x.dim():
+        emb_out = emb_out[..., None]
+    # `h + emb_out` (no scale-shift conditioning) rides on in_layers' conv as a per-(image, channel) bias unless a hook
+    # observes that conv's own output
+    emb_bias = emb_out if (not blk.use_scale_shift_norm and not in_conv._forward_hooks) else None
     if blk.updown:
         h = blk.in_layers[:-1](x)
         h, x = blk.h_upd(h), blk.x_upd(x)
-        h = in_conv(h)
+        h = in_conv(h, bias_img=emb_bias) if emb_bias is not None else in_conv(h)
     else:
-        h = in_conv.forward_prenorm(x, blk.in_layers[0])
-    emb_out = blk.emb_layers(emb).type(h.dtype)
-    while emb_out.dim() < h.dim():
-        emb_out = emb_out[..., None]
+        h = in_conv.forward_prenorm(x, blk.in_layers[0], bias_img=emb_bias)
     if split and not isinstance(blk.skip_connection, nn.Identity):
         sx = blk.skip_connection(x, split=split)
     else:
@@ -161,7 +164,7 @@ def _quant_resblock_forward(blk, x, emb, split=0):
     if blk.use_scale_shift_norm:
         scale, shift = th.chunk(emb_out, 2, dim=1)
         return _conv_plus(out_conv, sx, lambda **kw: out_conv.forward_prenorm(h, blk.out_layers[0], scale=scale, shift=shift, **kw))
-    hin = h + emb_out
+    hin = h if emb_bias is not None else h + emb_out
     return _conv_plus(out_conv, sx, lambda **kw: out_conv.forward_prenorm(hin, blk.out_layers[0], **kw))
 
 
@@ -353,8 +356,11 @@ class QuantResnetBlock(BaseQuantBlock):
         if split != 0:
             self.split = split
         if _prenorm_ok(self.conv1, self) and _prenorm_ok(self.conv2, self):
-            h = self.conv1.forward_prenorm(x, self.norm1, act_fn=nonlinearity)
-            h = h + self.temb_proj(nonlinearity(temb))[:, :, None, None]
+            tb = self.temb_proj(nonlinearity(temb))[:, :, None, None]
+            if self.conv1._forward_hooks:
+                h = self.conv1.forward_prenorm(x, self.norm1, act_fn=nonlinearity) + tb
+            else:
+                h = self.conv1.forward_prenorm(x, self.norm1, act_fn=nonlinearity, bias_img=tb)
             if self.in_channels != self.out_channels:
                 x = self.conv_shortcut(x) if self.use_conv_shortcut else self.nin_shortcut(x, split=self.split)
             return _conv_plus(self.conv2, x, lambda **kw: self.conv2.forward_prenorm(h, self.norm2, act_fn=nonlinearity, **kw))

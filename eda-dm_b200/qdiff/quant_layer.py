@@ -374,7 +374,7 @@ class QuantModule(nn.Module):
                     and not self._forward_pre_hooks and not norm._forward_hooks)
 
     def forward_prenorm(self, x, norm, silu: bool = True, scale=None, shift=None, split: int = 0, act_fn=F.silu,
-                        residual=None, tokens_out: bool = False):
+                        residual=None, tokens_out: bool = False, bias_img=None):
         """`self(silu(norm(x) [* (1 + scale) + shift]))` for a GroupNorm in front of this conv (or a LayerNorm in front of this
         linear).  On the integer path normalisation + conditioning + SiLU + activation quantization run as ONE producer
         pass (edadm_gn_fold + edadm_norm_act_quant_nhwc, or edadm_layernorm_quant_rows); otherwise it is computed module
@@ -389,15 +389,17 @@ class QuantModule(nn.Module):
                 h = h * (1 + scale) + shift
             if silu:
                 h = act_fn(h)      # the block's own formulation of swish (x*sigmoid(x) in the DDIM UNet, nn.SiLU in LDM)
-            out = self(h, split=split, residual=residual)
+            out = self(h, split=split, residual=residual, bias_img=bias_img)
             return out.flatten(2).permute(0, 2, 1) if tokens_out else out
         self.last_path = 'int8'
         if isinstance(norm, nn.LayerNorm):
             assert scale is None and not silu
             return self._finish(self._forward_int8(x, rows=('layernorm', norm), residual=self._epilogue_residual(residual)), residual)
         a, s = ops.gn_fold(x, norm.weight, norm.bias, norm.num_groups, norm.eps, scale, shift)
-        return self._finish(self._forward_int8(x, affine=(a, s, silu), residual=self._epilogue_residual(residual),
-                                               tokens_out=tokens_out), residual)
+        fold = bias_img is not None and residual is None and not tokens_out and self._epilogue_residual(bias_img) is not None
+        out = self._finish(self._forward_int8(x, affine=(a, s, silu), residual=self._epilogue_residual(residual),
+                                              tokens_out=tokens_out, bias_img=bias_img if fold else None), residual)
+        return out if bias_img is None or fold else out + bias_img.reshape(out.shape[0], -1, *([1] * (out.dim() - 2)))
 
     def forward_geglu(self, h, residual=None):
         """`self(a * gelu(g))` with (a, g) = h.chunk(2, -1): the GEGLU gate (ldm/modules/attention.py GEGLU.forward) folded
@@ -433,7 +435,7 @@ class QuantModule(nn.Module):
             out = out + residual
         return out
 
-    def _forward_int8(self, input, affine=None, residual=None, rows=None, tokens_out=False):
+    def _forward_int8(self, input, affine=None, residual=None, rows=None, tokens_out=False, bias_img=None):
         """Exact integer GEMM: out = dA*dW[n]*sum (qa-za)(qw-zw) + bias  == the reference's fp32 conv of the
         dequantised tensors (quant_layer.py:414-434) without its per-product rounding."""
         packs = self._packed_weights()
@@ -495,28 +497,36 @@ class QuantModule(nn.Module):
         if residual is not None:
             residual = residual.contiguous()
         if stride == 1 and _implicit_tiling_ok(B, Ho, Wo):
-            self._gemm_chain(q, packs, aqs, out, Ho * Wo, bias, rowsum, residual)
+            self._gemm_chain(q, packs, aqs, out, Ho * Wo, bias, rowsum, residual, bias_img)
         else:
             if self.split:
                 raise EdadmError("split shortcut on a strided / irregular conv is not supported on the integer path")
             a = ops.im2col_u8(q, Ho, Wo, R, S, stride)
             ops.qgemm_i8(a, pw0, aqs[0].delta, aqs[0].zero_point, out, Ho * Wo, bias=bias, rowsum=rowsum, filter_rs=(1, 1),
-                         residual=residual)
+                         residual=residual, bias_img=bias_img)
         out = out.squeeze(2) if self.fwd_func is F.conv1d else out
         return out.flatten(2).permute(0, 2, 1) if tokens_out else out
 
-    def _gemm_chain(self, q, packs, aqs, out, out_hw, bias, rowsum, residual=None):
+    def _gemm_chain(self, q, packs, aqs, out, out_hw, bias, rowsum, residual=None, bias_img=None):
         c_off = 0
         last = len(packs) - 1
         for i, (pw, aqz) in enumerate(zip(packs, aqs)):
             ops.qgemm_i8(q, pw, aqz.delta, aqz.zero_point, out, out_hw, bias=bias if i == 0 else None, rowsum=rowsum,
-                         a_c_offset=c_off, accumulate=i > 0, residual=residual if i == last else None)
+                         a_c_offset=c_off, accumulate=i > 0, residual=residual if i == last else None,
+                         bias_img=bias_img if i == last else None)
             c_off += pw.C
 
     # ---- forward -------------------------------------------------------------------------------------
-    def forward(self, input: torch.Tensor, split: int = 0, residual=None):
+    def forward(self, input: torch.Tensor, split: int = 0, residual=None, bias_img=None):
         """`residual` (optional, not in the reference signature): a tensor of the output's shape that is added to the
-        result -- `conv(x) + residual` -- inside the GEMM epilogue on the integer path, as a plain add elsewhere."""
+        result -- `conv(x) + residual` -- inside the GEMM epilogue on the integer path, as a plain add elsewhere.
+        `bias_img` (optional, convs): [B, N(,1,1)] added per (image, channel) -- the ResBlock's `h + emb_out`."""
+        if bias_img is not None:
+            fold = (residual is None and self.fwd_func is F.conv2d and self._integer_path_ok(input)
+                    and self._epilogue_residual(bias_img) is not None)
+            if not fold:
+                out = self.forward(input, split=split, residual=residual)
+                return out + bias_img.reshape(out.shape[0], -1, *([1] * (out.dim() - 2)))
         if split != 0 and self.split != 0:
             assert split == self.split
         elif split != 0:
@@ -526,7 +536,7 @@ class QuantModule(nn.Module):
 
         if self._integer_path_ok(input):
             self.last_path = 'int8'
-            return self._finish(self._forward_int8(input, residual=self._epilogue_residual(residual)), residual)
+            return self._finish(self._forward_int8(input, residual=self._epilogue_residual(residual), bias_img=bias_img), residual)
 
         if not self.disable_act_quant and self.use_act_quant:
             if self.split != 0:

@@ -124,11 +124,13 @@ int edadm_pack_weight(const float* w, const float* alpha, const float* delta, co
  * edadm_im2col_u8 first.  out fp32 is written as [M/out_hw][N][out_hw] (NCHW; out_hw=1 => [M][N]):
  *   out = delta_a*delta_w[n]*(acc + cw[n]*rowsum[m] - zp_a*wsum_eff[n]) + bias[n]  (+= out if accumulate)
  * then SiLU if `silu`, then + residual (nullable; fp32 laid out like out, must not alias out) -- the `x + h` / `skip_connection(x) + h` of
- * the residual and attention blocks (quant_block.py:116, :193) folded into the store.                              */
+ * the residual and attention blocks (quant_block.py:116, :193) folded into the store.  bias_img (nullable, NCHW outputs
+ * only, not together with residual): fp32 [images][N] added per (image, channel) -- the `h + emb_out` of the ResBlock
+ * (quant_block.py:112-113, openaimodel.py ResBlock._forward) folded into in_layers' conv.                              */
 int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const int8_t* wq, int N, int Np,
                    int R, int S, int Cp_w, const float* delta_a, const float* zp_a, const float* delta_w,
                    const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum, const float* bias,
-                   const float* residual, float* out, int out_hw, int accumulate, int silu, void* stream);
+                   const float* bias_img, const float* residual, float* out, int out_hw, int accumulate, int silu, void* stream);
 
 /* W4 storage: the same GEMM with the weights kept as 4-bit codes, two per byte -- wq4 u8 [Np][R*S][Cp/2] (Cp % 32 == 0; inside
  * each 32-bit word byte j = code[c0+j] | code[c0+4+j] << 4), zoff[n] = zp[n] -- and unpacked to s8 (code - zoff[n]) in
@@ -139,8 +141,8 @@ int edadm_pack_weight_w4(const float* w, const float* alpha, const float* delta,
                          int32_t* wsum, int32_t* zoff, void* stream);
 int edadm_qgemm_w4a8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const uint8_t* wq4,
                      const int32_t* zoff, int N, int Np, int R, int S, int Cp_w, const float* delta_a, const float* zp_a,
-                     const float* delta_w, const int32_t* wsum_eff, const float* bias, const float* residual, float* out,
-                     int out_hw, int accumulate, int silu, void* stream);
+                     const float* delta_w, const int32_t* wsum_eff, const float* bias, const float* bias_img,
+                     const float* residual, float* out, int out_hw, int accumulate, int silu, void* stream);
 
 /* fp32 3x3 convolution (stride 1, zero padding 1) with N <= 4 output channels: the UNet's output layer, whose input the
  * reference leaves un-quantized (qdiff/quant_model.py `disable_network_output_quantization`), so it runs as

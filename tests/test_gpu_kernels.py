@@ -301,6 +301,25 @@ def test_qgemm_linear(cuda, M, K, N, bits):
     assert _rel_l2(out, ref) < 1e-5
 
 
+@pytest.mark.parametrize("B,C,H,N,k", [(3, 64, 16, 128, 3), (5, 96, 8, 100, 3), (2, 32, 32, 48, 1)])
+def test_qgemm_bias_img_epilogue(cuda, B, C, H, N, k):
+    """`conv(x) + emb[:, :, None, None]` folded into the epilogue == the separate broadcast add (quant_block.py:112-113)"""
+    from edadm import ops
+    g = torch.Generator().manual_seed(36)
+    x = torch.randn(B, C, H, H, generator=g)
+    w = torch.randn(N, C, k, k, generator=g) * 0.05
+    bias = torch.randn(N, generator=g).to(cuda)
+    emb = torch.randn(B, N, 1, 1, generator=g).to(cuda)
+    d_a, z_a = _act_params(x)
+    d_w, z_w, _ = O.init_scale(w, 4, channel_wise=True)
+    pw = ops.pack_weight(w.to(cuda), d_w.to(cuda), z_w.to(cuda), 16)
+    aq = ops.ActQuant(d_a.to(cuda), z_a.to(cuda), 256)
+    q, _ = ops.act_quant_nhwc(x.to(cuda), aq, k // 2, cp=pw.Cp)
+    plain = ops.qgemm_i8(q, pw, aq.delta0, aq.zp0, torch.empty(B, N, H, H, device=cuda), H * H, bias=bias)
+    fused = ops.qgemm_i8(q, pw, aq.delta0, aq.zp0, torch.empty(B, N, H, H, device=cuda), H * H, bias=bias, bias_img=emb)
+    assert torch.equal(fused, plain + emb)
+
+
 @pytest.mark.parametrize("shape,N,k", [((2, 128, 16, 16), 128, 3), ((4, 48, 8, 8), 100, 3), ((2, 200, 16, 16), 96, 1),
                                        ((300, 320), 320, 0), ((77, 720), 98, 0), ((16, 80, 32, 32), 256, 3)])
 def test_qgemm_w4_storage_matches_s8(cuda, shape, N, k):
