@@ -336,8 +336,9 @@ def main():
     # DRAM bytes per qgemm launch from the committed ncu capture of the same eager step (profiles/, church workload only)
     traffic = None
     try:
-        if args.workload == "church" and args.batch in (0, 100):
-            with open(os.path.join(ROOT, "profiles", "launches_r01_church_b100_summary.json")) as f:
+        wl_batch = {"church": 100, "imagenet": 128}.get(args.workload)
+        if wl_batch and args.batch in (0, wl_batch):
+            with open(os.path.join(ROOT, "profiles", f"launches_r01_{args.workload}_b{wl_batch}_summary.json")) as f:
                 traffic = json.load(f)["kernels"]["edadm::qgemm_i8_kernel"]["dram_bytes_per_launch"]
     except Exception:
         traffic = None
