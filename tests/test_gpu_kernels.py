@@ -576,3 +576,49 @@ def test_transformer_block_fusions_match_unfused(cuda):
     assert sum(p == 'int8' for p in paths.values()) >= len(paths) - 2
     assert _rel_l2(y1, y0) < 5e-2     # chaotic amplification of single code flips; typically ~1e-3
     assert torch.isfinite(y1).all()
+
+
+def _inited_module(cuda, org, sample):
+    """QuantModule around `org` with weight / activation scales searched on `sample` and the integer path armed"""
+    from qdiff.quant_layer import QuantModule
+    wq = dict(n_bits=4, symmetric=True, channel_wise=True, scale_method='mse')
+    aq = dict(n_bits=8, symmetric=True, channel_wise=False, scale_method='mse', leaf_param=True, prob=1.0)
+    qm = QuantModule(org, wq, aq).to(cuda).eval()
+    qm.set_quant_state(True, True)
+    with torch.no_grad():
+        qm(sample)                         # un-inited quantizers run their search on the first forward
+    for q in (qm.weight_quantizer, qm.act_quantizer):
+        q.set_inited(True)
+    return qm
+
+
+def test_token_layout_and_geglu_paths_are_exact(cuda):
+    """tokens_out / forward_from_tokens / forward_geglu change layouts and producers, not arithmetic: bit-identical outputs"""
+    from qdiff.quant_layer import backend
+    torch.manual_seed(11)
+    B, C, H, W, N = 4, 64, 16, 16, 96
+    x = torch.randn(B, C, H, W, device=cuda)
+    gn = torch.nn.GroupNorm(32, C, eps=1e-6).to(cuda)
+    with torch.no_grad():
+        xn = gn(x)
+        proj_in = _inited_module(cuda, torch.nn.Conv2d(C, N, 1), xn)
+        y_nchw = proj_in.forward_prenorm(x, gn, silu=False)
+        y_tok = proj_in.forward_prenorm(x, gn, silu=False, tokens_out=True)
+        assert proj_in.last_path == 'int8' and tuple(y_tok.shape) == (B, H * W, N) and y_tok.is_contiguous()
+        assert torch.equal(y_tok, y_nchw.flatten(2).permute(0, 2, 1))
+        tok = torch.randn(B, H * W, N, device=cuda)
+        proj_out = _inited_module(cuda, torch.nn.Conv2d(N, C, 1), tok.permute(0, 2, 1).reshape(B, N, H, W))
+        ref = proj_out(tok.permute(0, 2, 1).reshape(B, N, H, W).contiguous()) + x
+        got = proj_out.forward_from_tokens(tok, (H, W), residual=x)
+        assert proj_out.last_path == 'int8' and torch.equal(got, ref)
+        h = torch.randn(B, 50, 2 * 128, device=cuda) * 1.5
+        a, g = h.chunk(2, dim=-1)
+        lin = _inited_module(cuda, torch.nn.Linear(128, 64), a * F.gelu(g))
+        res = torch.randn(B, 50, 64, device=cuda)
+        fused = lin.forward_geglu(h, residual=res)
+        backend.fuse_norm = False
+        try:
+            plain = lin.forward_geglu(h, residual=res)
+        finally:
+            backend.fuse_norm = True
+        assert torch.equal(fused, plain)
