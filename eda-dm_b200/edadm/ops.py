@@ -440,6 +440,26 @@ def act_quant_rows(x2d, aq: ActQuant, want_rowsum=False, row_group=0, group_stri
     return q, rowsum
 
 
+def norm_act_pool2(x, aff_a, aff_s, silu):
+    """avg_pool2d(silu(a*x+s), 2) in one pass; x fp32 [B,C,H,W] with even H, W."""
+    _need_cuda(x)
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    out = torch.empty((B, C, H // 2, W // 2), dtype=torch.float32, device=x.device)
+    lib.norm_act_pool2(x.data_ptr(), aff_a.data_ptr(), aff_s.data_ptr(), 1 if silu else 0, out.data_ptr(), B, C, H, W, _stream())
+    return out
+
+
+def upsample2x_codes(q_lo, C, pad, aq: ActQuant):
+    """Nearest 2x upsampling of NHWC codes q_lo [B,H,W,Cp] (no halo) -> [B,2H+2p,2W+2p,Cp] with the zero-point halo ring."""
+    B, H, W, Cp = q_lo.shape
+    q_hi = torch.empty((B, 2 * H + 2 * pad, 2 * W + 2 * pad, Cp), dtype=torch.uint8, device=q_lo.device)
+    d0, z0 = _qparam(aq.delta0, q_lo.device), _qparam(aq.zp0, q_lo.device)
+    lib.upsample2x_codes(q_lo.data_ptr(), q_hi.data_ptr(), B, int(C), H, W, Cp, int(pad), d0.data_ptr(), z0.data_ptr(), aq.levels0,
+                         _stream())
+    return q_hi
+
+
 def layernorm_quant_rows(x, norm_weight, norm_bias, eps, aq: ActQuant, want_rowsum=False):
     """LayerNorm over the last dim of x [..., K] + activation quantizer -> u8 codes [M, Kp] (one pass)."""
     _need_cuda(x)

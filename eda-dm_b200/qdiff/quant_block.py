@@ -152,9 +152,9 @@ def _quant_resblock_forward(blk, x, emb, split=0):
     # observes that conv's own output
     emb_bias = emb_out if (not blk.use_scale_shift_norm and not in_conv._forward_hooks) else None
     if blk.updown:
-        h = blk.in_layers[:-1](x)
-        h, x = blk.h_upd(h), blk.x_upd(x)
-        h = in_conv(h, bias_img=emb_bias) if emb_bias is not None else in_conv(h)
+        # in_layers[:-1] (GroupNorm, SiLU) -> h_upd -> conv: normalisation, resampling and quantization as one producer chain
+        h = in_conv.forward_prenorm(x, blk.in_layers[0], resample=blk.h_upd, bias_img=emb_bias)
+        x = blk.x_upd(x)
     else:
         h = in_conv.forward_prenorm(x, blk.in_layers[0], bias_img=emb_bias)
     if split and not isinstance(blk.skip_connection, nn.Identity):

@@ -374,7 +374,7 @@ class QuantModule(nn.Module):
                     and not self._forward_pre_hooks and not norm._forward_hooks)
 
     def forward_prenorm(self, x, norm, silu: bool = True, scale=None, shift=None, split: int = 0, act_fn=F.silu,
-                        residual=None, tokens_out: bool = False, bias_img=None):
+                        residual=None, tokens_out: bool = False, bias_img=None, resample=None):
         """`self(silu(norm(x) [* (1 + scale) + shift]))` for a GroupNorm in front of this conv (or a LayerNorm in front of this
         linear).  On the integer path normalisation + conditioning + SiLU + activation quantization run as ONE producer
         pass (edadm_gn_fold + edadm_norm_act_quant_nhwc, or edadm_layernorm_quant_rows); otherwise it is computed module
@@ -389,6 +389,8 @@ class QuantModule(nn.Module):
                 h = h * (1 + scale) + shift
             if silu:
                 h = act_fn(h)      # the block's own formulation of swish (x*sigmoid(x) in the DDIM UNet, nn.SiLU in LDM)
+            if resample is not None:
+                h = resample(h)
             out = self(h, split=split, residual=residual, bias_img=bias_img)
             return out.flatten(2).permute(0, 2, 1) if tokens_out else out
         self.last_path = 'int8'
@@ -396,9 +398,31 @@ class QuantModule(nn.Module):
             assert scale is None and not silu
             return self._finish(self._forward_int8(x, rows=('layernorm', norm), residual=self._epilogue_residual(residual)), residual)
         a, s = ops.gn_fold(x, norm.weight, norm.bias, norm.num_groups, norm.eps, scale, shift)
+        codes = None
+        if resample is not None:
+            # `resample` is the block's h_upd (openaimodel.py Upsample / Downsample without conv): 2x average pooling is fused
+            # with the normalisation pass; nearest 2x upsampling commutes with the quantizer and is done on the u8 codes
+            kind = _resample_kind(resample)
+            if kind == 'down2' and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+                out = self.forward(ops.norm_act_pool2(x, a, s, silu), split=split, residual=residual, bias_img=bias_img)
+                return out
+            if kind == 'up2' and not self.split and not any(p.needs_rowsum for p in self._packed_weights()):
+                _, aqs = self._quantizers()
+                aq = ops.ActQuant(aqs[0].delta, aqs[0].zero_point, aqs[0].n_levels)
+                pw0 = self._packed_weights()[0]
+                q_lo, _ = ops.norm_act_quant_nhwc(x, a, s, silu, aq, 0, cp=pw0.Cp)
+                pad = int(self.fwd_kwargs['padding'][0])
+                codes = ops.upsample2x_codes(q_lo, x.shape[1], pad, aq)
+            else:
+                h = norm(x)
+                if scale is not None:
+                    h = h * (1 + scale) + shift
+                if silu:
+                    h = act_fn(h)
+                return self(resample(h), split=split, residual=residual, bias_img=bias_img)
         fold = bias_img is not None and residual is None and not tokens_out and self._epilogue_residual(bias_img) is not None
         out = self._finish(self._forward_int8(x, affine=(a, s, silu), residual=self._epilogue_residual(residual),
-                                              tokens_out=tokens_out, bias_img=bias_img if fold else None), residual)
+                                              tokens_out=tokens_out, bias_img=bias_img if fold else None, codes=codes), residual)
         return out if bias_img is None or fold else out + bias_img.reshape(out.shape[0], -1, *([1] * (out.dim() - 2)))
 
     def forward_geglu(self, h, residual=None):
@@ -435,7 +459,7 @@ class QuantModule(nn.Module):
             out = out + residual
         return out
 
-    def _forward_int8(self, input, affine=None, residual=None, rows=None, tokens_out=False, bias_img=None):
+    def _forward_int8(self, input, affine=None, residual=None, rows=None, tokens_out=False, bias_img=None, codes=None):
         """Exact integer GEMM: out = dA*dW[n]*sum (qa-za)(qw-zw) + bias  == the reference's fp32 conv of the
         dequantised tensors (quant_layer.py:414-434) without its per-product rounding."""
         packs = self._packed_weights()
@@ -477,6 +501,8 @@ class QuantModule(nn.Module):
         B, C, H, W = x4.shape
         R, S = pw0.R, pw0.S
         pad = int(self.fwd_kwargs['padding'][0])
+        if codes is not None:      # activation codes prepared by the caller (halo included): [B, H + 2 pad, W + 2 pad, Cp]
+            H, W = codes.shape[1] - 2 * pad, codes.shape[2] - 2 * pad
         stride = int(self.fwd_kwargs['stride'][0])
         pad_h = 0 if self.fwd_func is F.conv1d else pad
         if pad_h != pad:
@@ -484,7 +510,9 @@ class QuantModule(nn.Module):
         Ho = (H + 2 * pad_h - R) // stride + 1
         Wo = (W + 2 * pad - S) // stride + 1
         cp_act = pw0.Cp if len(packs) == 1 else 0     # nibble-packed weights pad channels to 32: keep the im2col K aligned
-        if affine is not None:
+        if codes is not None:
+            q, chsum = codes, None
+        elif affine is not None:
             q, chsum = ops.norm_act_quant_nhwc(x4, affine[0], affine[1], affine[2], aq, pad, want_chsum=needs_rowsum, cp=cp_act)
         else:
             q, chsum = ops.act_quant_nhwc(x4, aq, pad, want_chsum=needs_rowsum, cp=cp_act)
@@ -557,6 +585,18 @@ class QuantModule(nn.Module):
         self.last_path = 'fake' if (self.use_weight_quant or self.use_act_quant) else 'fp'
         out = self.activation_function(_library_fwd(self.fwd_func, input, weight, bias, self.fwd_kwargs))
         return out if residual is None else out + residual
+
+
+def _resample_kind(m):
+    """'up2' / 'down2' for the conv-less 2x resampling modules of the LDM ResBlock (zoo or reference classes), else None."""
+    op = getattr(m, 'op', None)
+    if isinstance(op, nn.AvgPool2d):
+        k, st = op.kernel_size, op.stride
+        if (k in (2, (2, 2))) and (st in (2, (2, 2))) and op.padding in (0, (0, 0)) and not op.ceil_mode:
+            return 'down2'
+    if type(m).__name__ == 'Upsample' and getattr(m, 'use_conv', True) is False and getattr(m, 'dims', 2) == 2:
+        return 'up2'
+    return None
 
 
 def _implicit_tiling_ok(B, Ho, Wo):

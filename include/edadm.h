@@ -97,6 +97,15 @@ int edadm_gn_fold(const float* x, const float* gamma, const float* beta, const f
 int edadm_norm_act_quant_nhwc(const float* x, const float* aff_a, const float* aff_s, int silu, uint8_t* q, int32_t* chsum,
                               int B, int C, int H, int W, int Cp, int pad, const float* delta0, const float* zp0,
                               int n_levels0, int split, const float* delta1, const float* zp1, int n_levels1, void* stream);
+/* Resampling ResBlocks (openaimodel.py ResBlock up=/down=: in_layers[:-1] -> h_upd -> conv, quant_block.py:93-97).
+ * edadm_norm_act_pool2: out[B][C][H/2][W/2] = avg_pool2d(silu(a*x+s), 2) in one pass (GroupNorm folded by edadm_gn_fold).
+ * edadm_upsample2x_codes: nearest 2x upsampling done on the u8 codes (it commutes with the quantizer):
+ * q_lo [B][H][W][Cp] -> q_hi [B][2H+2pad][2W+2pad][Cp] with the halo ring of edadm_act_quant_nhwc.                    */
+int edadm_norm_act_pool2(const float* x, const float* aff_a, const float* aff_s, int silu, float* out, int B, int C, int H,
+                         int W, void* stream);
+int edadm_upsample2x_codes(const uint8_t* q_lo, uint8_t* q_hi, int B, int C, int H, int W, int Cp, int pad, const float* delta,
+                           const float* zp, int n_levels, void* stream);
+
 /* Transformer-block producers (ldm/modules/attention.py BasicTransformerBlock as rewritten by quant_block.py:237-262):
  * edadm_layernorm_quant_rows = nn.LayerNorm (norm1/2/3) + the activation quantizer of the linear behind it, one pass;
  * edadm_geglu_quant_rows = GEGLU's `x * F.gelu(gate)` (attention.py GEGLU.forward) + the activation quantizer of

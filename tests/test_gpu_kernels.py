@@ -622,3 +622,25 @@ def test_token_layout_and_geglu_paths_are_exact(cuda):
         finally:
             backend.fuse_norm = True
         assert torch.equal(fused, plain)
+
+
+def test_resample_producers(cuda):
+    """resampling ResBlock chain: pooled GroupNorm+SiLU pass and nearest upsampling on codes vs the torch modules"""
+    from edadm import ops
+    g = torch.Generator().manual_seed(71)
+    B, C, H = 3, 64, 16
+    x = (torch.randn(B, C, H, H, generator=g) * 1.3).to(cuda)
+    gn = torch.nn.GroupNorm(32, C).to(cuda)
+    with torch.no_grad():
+        gn.weight.copy_(torch.randn(C, generator=g).to(cuda) * 0.3 + 1)
+        gn.bias.copy_(torch.randn(C, generator=g).to(cuda) * 0.2)
+        y = F.silu(gn(x))
+        a, s = ops.gn_fold(x, gn.weight, gn.bias, 32, gn.eps)
+        pooled = ops.norm_act_pool2(x, a, s, True)
+        assert _rel_l2(pooled.cpu(), F.avg_pool2d(y, 2).cpu()) < 1e-5
+        d, z = _act_params(y.cpu())
+        aq = ops.ActQuant(d.to(cuda), z.to(cuda), 256)
+        q_lo, _ = ops.act_quant_nhwc(y, aq, 0)
+        q_hi = ops.upsample2x_codes(q_lo, C, 1, aq)
+        ref, _ = ops.act_quant_nhwc(F.interpolate(y, scale_factor=2, mode="nearest"), aq, 1)
+        assert torch.equal(q_hi, ref)
