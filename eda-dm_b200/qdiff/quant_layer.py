@@ -32,6 +32,7 @@ class _Backend:
     fuse_norm = True         # GroupNorm + SiLU + activation quantizer as one producer pass on the integer path
     # (4-bit weight storage with in-smem unpack: `edadm.ops.w4_storage`)
     recon_cuda_graph = True  # capture the reconstruction iteration in one CUDA graph after 3 eager iterations
+    recon_overlap_fp = True  # ... with the FP forward on a forked stream (a parallel branch of the graph)
     qdrop_inkernel_rng = False  # False: QDrop masks come from torch.rand_like (the reference's stream, graph-safe);
                                 # True: drawn inside the kernel (Philox4x32, no extra memory pass)
     qdrop_seed = None        # None -> torch.initial_seed()
