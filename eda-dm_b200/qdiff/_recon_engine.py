@@ -303,9 +303,9 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
     # Warm-up iterations and the capture run on ONE non-default stream (library handles / workspaces used by the
     # autograd thread must never have been bound to the legacy stream, or capture is invalidated).
     side = torch.cuda.Stream(device=device) if use_graph else None
-    # a parallel FP branch pays off while the unit's kernels are launch/latency bound (small activations: +4 % on a church
-    # 16x16 ResBlock) and hurts once they are bandwidth bound (ImageNet 64x64 ResBlock: -23 %), hence the size gate
-    small_unit = static is not None and static[1].numel() <= (8 << 20)
+    # a parallel FP branch pays off while the unit's kernels are launch/latency bound (+4 % on a church 16x16 ResBlock) and
+    # hurts on larger units (ImageNet 32x32 ResBlock: -23 %): opt-in (backend.recon_overlap_fp) and size-gated
+    small_unit = static is not None and static[1].numel() <= (4 << 20)
     fp_stream = torch.cuda.Stream(device=device) if (use_graph and backend.recon_overlap_fp and small_unit) else None
     if side is not None:
         side.wait_stream(torch.cuda.current_stream(device))
