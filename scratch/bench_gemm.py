@@ -7,7 +7,7 @@ from edadm import ops
 ops.w4_storage = bool(int(os.environ.get('W4','1')))
 dev=torch.device('cuda:0')
 # (name, B, C, H, N, k)  conv with pad=k//2 ; k=0 -> linear with M=B
-SHAPES=[("church 32x32 c192 3x3",100,192,32,192,3),("church 16x16 c384 3x3",100,384,16,384,3),("church 8x8 c384 3x3",100,384,8,384,3),
+SHAPES=[("church up c576->192 32x32",100,576,32,192,3),("church up c384->192 32x32",100,384,32,192,3),("church up c1152->384 16x16",100,1152,16,384,3),("church 32x32 c192 3x3",100,192,32,192,3),("church 16x16 c384 3x3",100,384,16,384,3),("church 8x8 c384 3x3",100,384,8,384,3),
         ("church 4x4 c768 3x3",100,768,4,768,3),("church qkv 1x1 T1024",100,192,32,576,1),("imagenet 64x64 c192 3x3",32,192,64,192,3),
         ("imagenet 32x32 c384 3x3",32,384,32,384,3),("imagenet 16x16 c576",32,576,16,576,3),("imagenet geglu lin",32*1024,384,0,3072,0),
         ("imagenet lin 384",32*1024,384,0,384,0),("bedroom 64x64 c224",8,224,64,224,3)]
