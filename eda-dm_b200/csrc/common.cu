@@ -38,4 +38,4 @@ int sm_count() {
 }  // namespace edadm
 
 extern "C" const char* edadm_last_error(void) { return edadm::last_error_buf(); }
-extern "C" int edadm_abi_version(void) { return 3; }
+extern "C" int edadm_abi_version(void) { return 4; }

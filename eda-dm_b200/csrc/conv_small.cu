@@ -15,8 +15,9 @@ constexpr int CS_CCH = 4;                     // channels staged per step and gr
 constexpr int CS_GROUPS = 4;                  // channel groups (64 threads each)
 
 template <int NOUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv3x3_small_n_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                       const float* __restrict__ aff_a, const float* __restrict__ aff_s, int silu,
                        float* __restrict__ out, int C, int H, int W, int tiles_w) {
   extern __shared__ float cs_smem[];
   float* wsm = cs_smem;                                              // [C][NOUT][12] (9 used, 16-byte rows)
@@ -39,17 +40,48 @@ conv3x3_small_n_kernel(const float* __restrict__ x, const float* __restrict__ w,
   const int c_per_group = (C + CS_GROUPS - 1) / CS_GROUPS;
   const int cbeg = grp * c_per_group, cend = min(C, cbeg + c_per_group);
   const int steps = (c_per_group + CS_CCH - 1) / CS_CCH;             // same trip count for every group (block barriers)
+  // patch elements of one step handled by this thread (CS_CCH * CS_PH * 34 = 1360 values over 64 threads -> 22 each); the
+  // values of step s+1 are requested into registers before step s is computed, so global latency overlaps the FMAs.
+  // Optional per-(image, channel) affine + SiLU on load: the GroupNorm + SiLU in front of the output conv (edadm_gn_fold).
+  constexpr int PER_T = (CS_CCH * CS_PH * 34 + 63) / 64;
+  float stage[PER_T];
+  auto fetch = [&](int s) {
+    const int c0 = cbeg + s * CS_CCH;
+#pragma unroll
+    for (int u = 0; u < PER_T; ++u) {
+      const int i = tg + u * 64;
+      float v = 0.f;
+      if (i < CS_CCH * CS_PH * 34) {
+        const int col = i % 34, r = i / 34, row = r % CS_PH, cc = r / CS_PH;
+        const int c = c0 + cc, iy = ty0 + row - 1, ix = tx0 + col - 1;
+        if (c < cend && iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          v = __ldg(xb + ((size_t)c * H + iy) * W + ix);
+          if (aff_a) {
+            v = fmaf(v, __ldg(aff_a + (size_t)b * C + c), __ldg(aff_s + (size_t)b * C + c));
+            if (silu) v = v / (1.0f + __expf(-v));
+          }
+        }
+      }
+      stage[u] = v;
+    }
+  };
+  auto commit = [&]() {
+#pragma unroll
+    for (int u = 0; u < PER_T; ++u) {
+      const int i = tg + u * 64;
+      if (i < CS_CCH * CS_PH * 34) {
+        const int col = i % 34, r = i / 34, row = r % CS_PH, cc = r / CS_PH;
+        pg[(cc * CS_PH + row) * CS_PW + col] = stage[u];
+      }
+    }
+  };
+  fetch(0);
   for (int s = 0; s < steps; ++s) {
     const int c0 = cbeg + s * CS_CCH;
+    __syncthreads();                 // previous step's reads of the patch are done
+    commit();
     __syncthreads();
-    for (int i = tg; i < CS_CCH * CS_PH * 34; i += 64) {
-      const int col = i % 34, r = i / 34, row = r % CS_PH, cc = r / CS_PH;
-      const int c = c0 + cc, iy = ty0 + row - 1, ix = tx0 + col - 1;
-      float v = 0.f;
-      if (c < cend && iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(xb + ((size_t)c * H + iy) * W + ix);
-      pg[(cc * CS_PH + row) * CS_PW + col] = v;
-    }
-    __syncthreads();
+    if (s + 1 < steps) fetch(s + 1);
 #pragma unroll
     for (int cc = 0; cc < CS_CCH; ++cc) {
       const int c = c0 + cc;
@@ -103,10 +135,11 @@ conv3x3_small_n_kernel(const float* __restrict__ x, const float* __restrict__ w,
 using namespace edadm;
 
 // x fp32 [B][C][H][W], w fp32 [N][C][3][3] (already fake-quantized by the caller), bias fp32 [N] or null,
-// out fp32 [B][N][H][W]; stride 1, zero padding 1, N in {1..4}.
-extern "C" int edadm_conv3x3_small_n(const float* x, const float* w, const float* bias, float* out, int B, int C, int H,
-                                     int W, int N, void* stream) {
-  if (!x || !w || !out) return fail(EDADM_ERR_ARG, "conv3x3_small_n: null pointer");
+// out fp32 [B][N][H][W]; stride 1, zero padding 1, N in {1..4}.  aff_a / aff_s (nullable, [B][C]) + silu: the input is
+// silu(a*x+s), i.e. the GroupNorm + SiLU of the output head folded into the load (zero padding applies AFTER the activation).
+extern "C" int edadm_conv3x3_small_n(const float* x, const float* w, const float* bias, const float* aff_a, const float* aff_s,
+                                     int silu, float* out, int B, int C, int H, int W, int N, void* stream) {
+  if (!x || !w || !out || ((aff_a == nullptr) != (aff_s == nullptr))) return fail(EDADM_ERR_ARG, "conv3x3_small_n: null pointer");
   if (B < 0 || C < 1 || H < 1 || W < 1 || N < 1) return fail(EDADM_ERR_ARG, "conv3x3_small_n: bad sizes");
   if (N > 4) return fail(EDADM_ERR_UNSUPPORTED, "conv3x3_small_n: at most 4 output channels (got %d)", N);
   if (B == 0) return EDADM_OK;
@@ -121,7 +154,7 @@ extern "C" int edadm_conv3x3_small_n(const float* x, const float* w, const float
 #define EDADM_LAUNCH_CS(NO)                                                                                            \
   {                                                                                                                    \
     if (smem > 48 * 1024) cudaFuncSetAttribute(conv3x3_small_n_kernel<NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    conv3x3_small_n_kernel<NO><<<grid, 256, smem, s>>>(x, w, bias, out, C, H, W, tiles_w);                             \
+    conv3x3_small_n_kernel<NO><<<grid, 256, smem, s>>>(x, w, bias, aff_a, aff_s, silu, out, C, H, W, tiles_w);                             \
   }
   switch (N) {
     case 1: EDADM_LAUNCH_CS(1); break;

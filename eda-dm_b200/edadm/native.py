@@ -42,7 +42,7 @@ _SIGNATURES = {
     "edadm_geglu_quant_rows": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, c_int, P]),
     "edadm_pack_weight_w4": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "edadm_qgemm_w4a8": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
-    "edadm_conv3x3_small_n": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "edadm_conv3x3_small_n": (c_int, [P, P, P, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
     "edadm_qattn_fwd": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int,
                                 c_float, P, c_int64, c_int64, c_int64, c_int64, P]),
 }

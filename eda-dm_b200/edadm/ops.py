@@ -562,15 +562,17 @@ def conv3x3_small_n_ok(x, weight, kwargs):
             and one(kw.get('dilation', 1), 1) and kw.get('groups', 1) == 1)
 
 
-def conv3x3_small_n(x, weight, bias=None):
-    """fp32 3x3 / stride 1 / pad 1 convolution to <= 4 output channels (the UNet output layer)."""
+def conv3x3_small_n(x, weight, bias=None, affine=None):
+    """fp32 3x3 / stride 1 / pad 1 convolution to <= 4 output channels (the UNet output layer).  affine = (a, s, silu):
+    the conv reads silu(a*x+s) with a, s [B, C] from gn_fold (GroupNorm + SiLU of the output head folded into the load)."""
     _need_cuda(x)
     x, weight = _f32c(x), _f32c(weight.detach())
     B, C, H, W = x.shape
     N = weight.shape[0]
     out = torch.empty((B, N, H, W), dtype=torch.float32, device=x.device)
     b = None if bias is None else _f32c(bias.detach())
-    lib.conv3x3_small_n(x.data_ptr(), weight.data_ptr(), _ptr(b), out.data_ptr(), B, C, H, W, N, _stream())
+    a_, s_, silu = (affine[0], affine[1], 1 if affine[2] else 0) if affine is not None else (None, None, 0)
+    lib.conv3x3_small_n(x.data_ptr(), weight.data_ptr(), _ptr(b), _ptr(a_), _ptr(s_), silu, out.data_ptr(), B, C, H, W, N, _stream())
     return out
 
 

@@ -82,6 +82,19 @@ def _prenorm_ok(conv, block):
     return isinstance(conv, QuantModule) and (not block.training or p_drop == 0)
 
 
+def _emb_layers(seq, emb):
+    """`emb_layers(emb)` = Linear(SiLU(emb)); every ResBlock of a forward applies the SiLU to the SAME embedding tensor, so it
+    is computed once per forward and kept on the tensor object (inference only; no hooks on the SiLU)."""
+    if (len(seq) == 2 and isinstance(seq[0], nn.SiLU) and not seq[0]._forward_hooks and not th.is_grad_enabled()
+            and not emb.requires_grad):
+        act = getattr(emb, '_edadm_silu', None)
+        if act is None:
+            act = seq[0](emb)
+            emb._edadm_silu = act
+        return seq[1](act)
+    return seq(emb)
+
+
 def _conv_plus(conv, residual, call):
     """`residual + call()` where `call` runs the QuantModule `conv`; the add moves into the GEMM epilogue unless a hook
     observes the conv's own output (calibration caches, FBR taps)."""
@@ -145,7 +158,7 @@ def _quant_resblock_forward(blk, x, emb, split=0):
     fuse = _prenorm_ok(in_conv, blk) and _prenorm_ok(out_conv, blk)
     if not fuse:
         return _zoo_ldm.resblock_forward(blk, x, emb, split)
-    emb_out = blk.emb_layers(emb).type(x.dtype)
+    emb_out = _emb_layers(blk.emb_layers, emb).type(x.dtype)
     while emb_out.dim() < x.dim():
         emb_out = emb_out[..., None]
     # `h + emb_out` (no scale-shift conditioning) rides on in_layers' conv as a per-(image, channel) bias unless a hook

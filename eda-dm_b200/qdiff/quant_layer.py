@@ -386,6 +386,20 @@ class QuantModule(nn.Module):
             self.split = split
             self.set_split()
         if not self.prenorm_fusable(x, norm):
+            if (backend.fuse_norm and isinstance(norm, nn.GroupNorm) and scale is None and split == 0 and self.split == 0
+                    and residual is None and bias_img is None and resample is None and not tokens_out
+                    and getattr(act_fn, '__name__', '') in ('silu', 'nonlinearity', '_swish') and self.fwd_func is F.conv2d
+                    and not (self.use_act_quant and not self.disable_act_quant)
+                    and not self._forward_hooks and not self._forward_pre_hooks and not norm._forward_hooks
+                    and isinstance(self.activation_function, StraightThrough)):
+                weight = self.weight_quantizer(self.weight) if self.use_weight_quant else self.org_weight
+                bias = self.bias if self.use_weight_quant else self.org_bias
+                if ops.conv3x3_small_n_ok(x, weight, self.fwd_kwargs):
+                    # the UNet output head (GroupNorm -> SiLU -> conv to <= 4 channels, fp32 input by design of the reference):
+                    # statistics by edadm_gn_fold, normalisation + SiLU applied while the stencil kernel loads its patches
+                    a, s = ops.gn_fold(x, norm.weight, norm.bias, norm.num_groups, norm.eps)
+                    self.last_path = 'fake' if self.use_weight_quant else 'fp'
+                    return ops.conv3x3_small_n(x, weight, bias, affine=(a, s, silu))
             h = norm(x)
             if scale is not None:
                 h = h * (1 + scale) + shift
@@ -587,6 +601,11 @@ class QuantModule(nn.Module):
         self.last_path = 'fake' if (self.use_weight_quant or self.use_act_quant) else 'fp'
         out = self.activation_function(_library_fwd(self.fwd_func, input, weight, bias, self.fwd_kwargs))
         return out if residual is None else out + residual
+
+
+def _swish(x):
+    """x * sigmoid(x): the DDIM UNet's own spelling of SiLU (ddim/models/diffusion.py nonlinearity)"""
+    return x * torch.sigmoid(x)
 
 
 def _resample_kind(m):

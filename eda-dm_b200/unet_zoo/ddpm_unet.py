@@ -190,6 +190,8 @@ class DDPMUNet(nn.Module):
                     h = level.attn[i](h)
             if lvl != 0:
                 h = level.upsample(h)
+        if hasattr(self.conv_out, 'forward_prenorm'):
+            return self.conv_out.forward_prenorm(h, self.norm_out, act_fn=nonlinearity)
         return self.conv_out(nonlinearity(self.norm_out(h)))
 
 

@@ -342,6 +342,8 @@ class UNetModel(nn.Module):
         for module in self.output_blocks:
             split = h.shape[1] if self.split_shortcut else 0
             h = module(torch.cat([h, hs.pop()], dim=1), emb, context, split=split)
+        if hasattr(self.out[-1], 'forward_prenorm') and len(self.out) == 3 and isinstance(self.out[1], nn.SiLU):
+            return self.out[2].forward_prenorm(h, self.out[0])      # GroupNorm + SiLU ride on the quantized module's producer
         return self.out(h)
 
 

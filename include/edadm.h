@@ -156,9 +156,10 @@ int edadm_qgemm_w4a8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_
 /* fp32 3x3 convolution (stride 1, zero padding 1) with N <= 4 output channels: the UNet's output layer, whose input the
  * reference leaves un-quantized (qdiff/quant_model.py `disable_network_output_quantization`), so it runs as
  * fp32 activations x fake-quantized 8-bit weights (quant_layer.py:421-434 with disable_act_quant).  x [B][C][H][W],
- * w [N][C][3][3] (already fake-quantized), bias [N] or NULL, out [B][N][H][W].                                      */
-int edadm_conv3x3_small_n(const float* x, const float* w, const float* bias, float* out, int B, int C, int H, int W, int N,
-                          void* stream);
+ * w [N][C][3][3] (already fake-quantized), bias [N] or NULL, out [B][N][H][W].  aff_a / aff_s (nullable, [B][C], from
+ * edadm_gn_fold) + silu: the conv reads silu(a*x+s) -- the `out` head's GroupNorm32 + SiLU (openaimodel.py:942-946). */
+int edadm_conv3x3_small_n(const float* x, const float* w, const float* bias, const float* aff_a, const float* aff_s, int silu,
+                          float* out, int B, int C, int H, int W, int N, void* stream);
 
 /* ---- K5: fused quantized attention (tcgen05 kind::i8 for Q.K^T and P.V, softmax + P quantization on chip) ----
  * Replaces the bmm/einsum - softmax - fake-quant chain of QuantAttnBlock.forward (qdiff/quant_block.py:431-445),

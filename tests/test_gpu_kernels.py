@@ -464,6 +464,16 @@ def test_conv3x3_small_n(cuda, B, C, H, N):
     out = ops.conv3x3_small_n(x.to(cuda), w.to(cuda), bias.to(cuda)).cpu()
     ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1).float()
     assert _rel_l2(out, ref) < 1e-6
+    # GroupNorm + SiLU of the output head folded into the patch load
+    if C % 2 == 0:
+        gn = torch.nn.GroupNorm(2, C).to(cuda)
+        with torch.no_grad():
+            gn.weight.copy_(torch.randn(C, generator=g).to(cuda) * 0.3 + 1)
+            gn.bias.copy_(torch.randn(C, generator=g).to(cuda) * 0.2)
+            a, s = ops.gn_fold(x.to(cuda), gn.weight, gn.bias, 2, gn.eps)
+            fused = ops.conv3x3_small_n(x.to(cuda), w.to(cuda), bias.to(cuda), affine=(a, s, True))
+            ref2 = F.conv2d(F.silu(gn(x.to(cuda))).double(), w.to(cuda).double(), bias.to(cuda).double(), padding=1).float()
+        assert _rel_l2(fused, ref2) < 1e-5
     assert ops.conv3x3_small_n_ok(x.to(cuda), w.to(cuda), dict(stride=(1, 1), padding=(1, 1), dilation=(1, 1), groups=1))
     assert not ops.conv3x3_small_n_ok(x.to(cuda), w.to(cuda), dict(stride=(2, 2), padding=(1, 1), dilation=(1, 1), groups=1))
 

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(handle, name), f"{name} declared in include/edadm.h but not exported"
     assert declared == set(native.exported_symbols()), declared ^ set(native.exported_symbols())
-    assert handle.edadm_abi_version() == 3
+    assert handle.edadm_abi_version() == 4
     assert handle.edadm_reduce_slots() > 0
 
 
