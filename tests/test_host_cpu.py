@@ -29,6 +29,13 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(native.exported_symbols()), declared ^ set(native.exported_symbols())
     assert handle.edadm_abi_version() == 4
     assert handle.edadm_reduce_slots() > 0
+    # the ctypes table must agree with the header on every prototype's parameter count (guards against ABI drift)
+    protos = re.findall(r"\b(?:int|const char\*)\s+(edadm_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", re.sub(r"/\*.*?\*/", "", header, flags=re.S), flags=re.S)
+    assert {n for n, _ in protos} == declared
+    for name, args in protos:
+        args = args.strip()
+        n_args = 0 if args in ("", "void") else args.count(",") + 1
+        assert n_args == len(native._SIGNATURES[name][1]), f"{name}: header has {n_args} parameters, ctypes table {len(native._SIGNATURES[name][1])}"
 
 
 def test_argument_errors_are_reported_not_crashing():
