@@ -1,4 +1,5 @@
-"""Forward-hook tap and seeding helpers (interface of the reference's qdiff/utils.py:12-54)."""
+"""Forward-hook tap and seeding helpers with the interface of the reference's qdiff/utils.py (AttentionMap :12-23,
+at / at_loss :26-32, seed_everything :35-54); used by FBR, TDAC (scripts/calibration.py) and the cache builder."""
 import os
 import random
 
@@ -7,35 +8,42 @@ import torch
 
 
 class AttentionMap:
-    """Keeps the last (input, output) of a module; FBR, TDAC and the cache builder read `.out` / `.feature`."""
+    """Tap on one module: after every forward, `.feature` is the tuple of positional inputs and `.out` the output."""
 
     def __init__(self, module):
+        self.out = None
+        self.feature = None
         self.hook = module.register_forward_hook(self.hook_fn)
 
     def hook_fn(self, module, input, output):
-        self.out = output
-        self.feature = input
+        self.feature, self.out = input, output
 
     def remove(self):
-        self.hook.remove()
+        if self.hook is not None:
+            self.hook.remove()
+            self.hook = None
 
 
 def at(x):
-    return x.view(x.size(0), -1)
+    """flatten everything but the batch axis"""
+    return x.reshape(x.shape[0], -1) if not x.is_contiguous() else x.view(x.shape[0], -1)
 
 
 def at_loss(x, y):
-    return (at(x) - at(y)).pow(2).mean(1).sum()
+    """batch sum of the per-sample mean squared difference"""
+    diff = at(x) - at(y)
+    return (diff * diff).mean(dim=1).sum()
 
 
 def seed_everything(seed):
-    random.seed(seed)
-    os.environ['PYTHONHASHSEED'] = str(seed)
-    np.random.seed(seed)
-    torch.manual_seed(seed)
+    """Seed every generator the reconstruction loop draws from (Python `random.sample`, numpy, torch CPU + CUDA) and the
+    in-kernel QDrop stream; cuDNN is put in deterministic mode as the reference does."""
+    os.environ["PYTHONHASHSEED"] = str(seed)
+    for seeder in (random.seed, np.random.seed, torch.manual_seed):
+        seeder(seed)
     if torch.cuda.is_available():
-        torch.cuda.manual_seed(seed)
         torch.cuda.manual_seed_all(seed)
     torch.backends.cudnn.deterministic = True
     from .quant_layer import backend
-    backend.qdrop_seed, backend.qdrop_offset = seed, 0
+    backend.qdrop_seed = seed
+    backend.qdrop_offset = 0
