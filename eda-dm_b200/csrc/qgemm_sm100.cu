@@ -16,6 +16,7 @@
 //                                coalesced NCHW stores (TMEM lane == output pixel == consecutive address) or float4 rows.
 // Shared memory: up to 8 pipeline stages x (16 KB A + BLOCK_N x 128 B), 128B-swizzled K-major operands.
 #include "tc05.cuh"
+#include <cstdlib>
 
 namespace edadm {
 
@@ -36,7 +37,8 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 struct GemmParams {
   // problem
   int M, N, taps, S;        // M output rows, N out channels, taps = R*S filter taps, S = filter width
-  int k_chunks;             // ceil(Cp_range / 128) K steps per tap
+  int kbytes;               // bytes of K per pipeline step: 128 (128B-swizzled tiles) or 64 (64B-swizzled; channel counts = 64 mod 128)
+  int k_chunks;             // ceil(Cp_range / kbytes) K steps per tap
   int k_last_mmas;          // MMAs (of 32 B) in the last chunk of each tap
   int a_c_offset;           // first channel of this K range inside the activation tensor (split shortcut)
   // tile -> coordinate mapping of the activation tensor map (dims: C, W, H, B)
@@ -60,6 +62,8 @@ struct GemmParams {
   const int32_t* rowsum;    // [M] or null (required when cw != null)
   const float* bias;        // [N] or null
   float* out;
+  int debug;                // debug bits (EDADM_GEMM_DEBUG): 1 = epilogue skips global stores, 2 = skips TMEM loads too
+  long long* trace;         // debug: per-CTA, per-tile role timestamps (edadm_debug_set_gemm_trace); null in production
 };
 
 struct __align__(8) PipeBarriers {
@@ -148,7 +152,8 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer (LDS/STS, not generic LD/ST)
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + p.stages * A_STAGE_BYTES;
+  const int a_stage_bytes = BLOCK_M * p.kbytes;
+  uint8_t* smem_b = smem + p.stages * a_stage_bytes;
   float* epi_scale = reinterpret_cast<float*>(smem_b + p.stages * p.b_stage_bytes);
   int* epi_zterm = reinterpret_cast<int*>(epi_scale + MAX_BLOCK_N);
   int* epi_cw = epi_zterm + MAX_BLOCK_N;
@@ -162,7 +167,7 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int num_tiles = p.m_tiles * p.n_tiles;
   const int k_iters = p.taps * p.k_chunks;
   const int stages = p.stages;
-  const uint32_t stage_tx = A_STAGE_BYTES + (uint32_t)p.block_n * (W4 ? BLOCK_K / 2 : BLOCK_K);
+  const uint32_t stage_tx = (uint32_t)a_stage_bytes + (uint32_t)p.block_n * (W4 ? BLOCK_K / 2 : p.kbytes);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -190,7 +195,9 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+      if (p.trace && lane == 0) p.trace[((size_t)blockIdx.x * 16 + (ti & 15)) * 8 + 5] = clock64();
       const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
       const int m0 = m_blk * BLOCK_M;
       const int b0 = m0 / p.HoWo;
@@ -203,13 +210,14 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           mbar_wait(&bars->empty[stage], phase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(&bars->full[stage], stage_tx);
-            tma_load_4d(smem_a + stage * A_STAGE_BYTES, &map_a, &bars->full[stage], p.a_c_offset + kc * BLOCK_K, ow0 + kw, oh0 + kh, b0);
-            tma_load_3d(smem_b + stage * p.b_stage_bytes, &map_b, &bars->full[stage], W4 ? kc * (BLOCK_K / 2) : kc * BLOCK_K, tap, n0);
+            tma_load_4d(smem_a + stage * a_stage_bytes, &map_a, &bars->full[stage], p.a_c_offset + kc * p.kbytes, ow0 + kw, oh0 + kh, b0);
+            tma_load_3d(smem_b + stage * p.b_stage_bytes, &map_b, &bars->full[stage], W4 ? kc * (BLOCK_K / 2) : kc * p.kbytes, tap, n0);
           }
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.trace && lane == 0) p.trace[((size_t)blockIdx.x * 16 + (ti & 15)) * 8 + 6] = clock64();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -221,19 +229,24 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint32_t acc_phase = 0;
     int us = 0;
     uint32_t uphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
       mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
+      if (p.trace && lane == 0) p.trace[((size_t)blockIdx.x * 16 + (ti & 15)) * 8 + 0] = clock64();
       const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BLOCK_N;
       int kc = 0;
       for (int it = 0; it < k_iters; ++it) {
-        const int nmma = (kc == p.k_chunks - 1) ? p.k_last_mmas : BLOCK_K / UMMA_K;
+        const int nmma = (kc == p.k_chunks - 1) ? p.k_last_mmas : p.kbytes / UMMA_K;
         if (++kc == p.k_chunks) kc = 0;
         mbar_wait(&bars->full[stage], phase);
         if (W4) mbar_wait(&bars->ufull[us], uphase);
         tc_fence_after();
-        const uint64_t adesc = make_smem_desc(a_base + stage * A_STAGE_BYTES);
-        const uint64_t bdesc = make_smem_desc(W4 ? u_base + us * p.u_stage_bytes : b_base + stage * p.b_stage_bytes);
+        if (p.trace && lane == 0 && it == 0) p.trace[((size_t)blockIdx.x * 16 + (ti & 15)) * 8 + 1] = clock64();
+        const bool sw64 = !W4 && p.kbytes == 64;
+        const uint64_t adesc = sw64 ? make_smem_desc_sw64(a_base + stage * a_stage_bytes) : make_smem_desc(a_base + stage * a_stage_bytes);
+        const uint64_t bdesc = sw64 ? make_smem_desc_sw64(b_base + stage * p.b_stage_bytes)
+                                    : make_smem_desc(W4 ? u_base + us * p.u_stage_bytes : b_base + stage * p.b_stage_bytes);
         if (elect_one()) {
           umma_i8(tmem_d, adesc, bdesc, idesc, it ? 1u : 0u);
           if (nmma > 1) umma_i8(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
@@ -248,6 +261,7 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       }
       if (elect_one()) umma_commit(&bars->tmem_full[acc]);
       __syncwarp();
+      if (p.trace && lane == 0) p.trace[((size_t)blockIdx.x * 16 + (ti & 15)) * 8 + 2] = clock64();
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 2 + EPI_WARPS) {
@@ -323,7 +337,8 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const long long col_stride = p.out_hw;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
       const int n_blk = tile % p.n_tiles, m_blk = tile / p.n_tiles;
       const int n0 = n_blk * p.block_n;
       for (int j = et; j < p.block_n; j += EPI_WARPS * 32) {
@@ -409,6 +424,9 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       if (has_res && c0 < p.block_n) load_residual(t0, res_row + (long long)c0 * res_stride, res_stride, p.N - (n0 + c0));
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (p.trace && et == 0) p.trace[((size_t)blockIdx.x * 16 + (ti & 15)) * 8 + 3] = clock64();
+      if (p.debug & 2) c0 = p.block_n;
+      const bool row_ok_dbg = row_ok && !(p.debug & 1);
       if (c0 < p.block_n) { tmem_ld16(taddr + c0, r0); }
       tmem_ld_wait();
       // software pipeline: the TMEM load (and residual load) of the next chunk is in flight while this one is converted and stored
@@ -418,7 +436,19 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           tmem_ld16(taddr + c1, r1);
           if (has_res) load_residual(t1, res_row + (long long)c1 * res_stride, res_stride, p.N - (n0 + c1));
         }
-        if (row_ok) {
+        if (p.debug & 4) {     // experiment: same bytes as 4 fully coalesced STG.128 per thread (layout is garbage)
+          float* cb = p.out + (size_t)tile * 128 * p.block_n + (size_t)(c0 / 16) * 2048 + quarter * 512;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 v;
+            v.x = fmaf((float)((int)r0[4 * j + 0] + epi_zterm[c0 + 4 * j + 0]), epi_scale[c0 + 4 * j + 0], epi_bias[c0 + 4 * j + 0]);
+            v.y = fmaf((float)((int)r0[4 * j + 1] + epi_zterm[c0 + 4 * j + 1]), epi_scale[c0 + 4 * j + 1], epi_bias[c0 + 4 * j + 1]);
+            v.z = fmaf((float)((int)r0[4 * j + 2] + epi_zterm[c0 + 4 * j + 2]), epi_scale[c0 + 4 * j + 2], epi_bias[c0 + 4 * j + 2]);
+            v.w = fmaf((float)((int)r0[4 * j + 3] + epi_zterm[c0 + 4 * j + 3]), epi_scale[c0 + 4 * j + 3], epi_bias[c0 + 4 * j + 3]);
+            *reinterpret_cast<float4*>(cb + (j * 32 + lane) * 4) = v;
+          }
+        } else
+        if (row_ok_dbg) {
           const int nv = p.N - (n0 + c0);
           float* dptr = out_row + (long long)c0 * col_stride;
           if (has_res) {
@@ -435,7 +465,21 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           tmem_ld16(taddr + c2, r0);
           if (has_res) load_residual(t0, res_row + (long long)c2 * res_stride, res_stride, p.N - (n0 + c2));
         }
-        if (c1 < p.block_n && row_ok) {
+        if (p.debug & 4) {
+          if (c1 < p.block_n) {
+          float* cb = p.out + (size_t)tile * 128 * p.block_n + (size_t)(c1 / 16) * 2048 + quarter * 512;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 v;
+            v.x = fmaf((float)((int)r1[4 * j + 0] + epi_zterm[c1 + 4 * j + 0]), epi_scale[c1 + 4 * j + 0], epi_bias[c1 + 4 * j + 0]);
+            v.y = fmaf((float)((int)r1[4 * j + 1] + epi_zterm[c1 + 4 * j + 1]), epi_scale[c1 + 4 * j + 1], epi_bias[c1 + 4 * j + 1]);
+            v.z = fmaf((float)((int)r1[4 * j + 2] + epi_zterm[c1 + 4 * j + 2]), epi_scale[c1 + 4 * j + 2], epi_bias[c1 + 4 * j + 2]);
+            v.w = fmaf((float)((int)r1[4 * j + 3] + epi_zterm[c1 + 4 * j + 3]), epi_scale[c1 + 4 * j + 3], epi_bias[c1 + 4 * j + 3]);
+            *reinterpret_cast<float4*>(cb + (j * 32 + lane) * 4) = v;
+          }
+          }
+        } else
+        if (c1 < p.block_n && row_ok_dbg) {
           const int nv = p.N - (n0 + c1);
           float* dptr = out_row + (long long)c1 * col_stride;
           if (has_res) {
@@ -452,6 +496,7 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+      if (p.trace && et == 0) p.trace[((size_t)blockIdx.x * 16 + (ti & 15)) * 8 + 4] = clock64();
       asm volatile("bar.sync 1, 256;" ::: "memory");  // epi_* vectors are rewritten next tile
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
@@ -486,6 +531,10 @@ static int pick_block_n(int N, int m_tiles, int sms, int step) {
 }  // namespace edadm
 
 using namespace edadm;
+
+static long long* g_gemm_trace = nullptr;
+// debug hook (scratch/ timeline experiments only): per-CTA [16 tiles][8] clock64 stamps of the warp roles
+extern "C" int edadm_debug_set_gemm_trace(long long* buf) { g_gemm_trace = buf; return 0; }
 
 // Activation codes q: [B][Hp][Wp][Cp_act] u8 (halo included), filter R x S, stride 1:  Ho = Hp-R+1, Wo = Wp-S+1.
 // A 2-D GEMM ([M][Kp] rows) is the special case B=1, Hp=1, Wp=M, R=S=1.
@@ -536,12 +585,19 @@ static int launch_qgemm(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int
   const int block_n = pick_block_n(N, m_tiles_all, sm_count(), out_hw == 1 ? 32 : 16);
   const int n_tiles = (N + block_n - 1) / block_n;
 
+  // K bytes per pipeline step: channel counts of the form 128 j + 64 (192, 576, 960 ...) would leave every tap's last 128-byte
+  // chunk half out of bounds -- such TMA boxes are slow (measured: 711 cycles for a half step vs 465 for a full one) -- so
+  // those layers run on 64-byte steps (64B-swizzled tiles, two MMAs per step) with every box in bounds.
+  int kbytes = BLOCK_K;
+  if (!w4 && (Cp_w % 128) == 64 && Cp_w <= 192) kbytes = 64;
+  if (const char* e = getenv("EDADM_GEMM_KBYTES")) { const int v = atoi(e); if (!w4 && (v == 64 || v == 128)) kbytes = v; }   // debug / tuning
   CUtensorMap map_a, map_b;
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cp_act, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)Cp_act, (cuuint64_t)Wp * Cp_act, (cuuint64_t)Hp * Wp * Cp_act};
-    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_b};
-    int rc = encode_map(&map_a, q, 4, dims, strides, box, "activations");
+    cuuint32_t box[4] = {(cuuint32_t)kbytes, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_b};
+    int rc = encode_map(&map_a, q, 4, dims, strides, box, "activations", CU_TENSOR_MAP_DATA_TYPE_UINT8,
+                        kbytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   if (w4) {   // two codes per byte, plain (unswizzled) 64-byte rows; the unpack warps produce the swizzled s8 tile
@@ -553,33 +609,39 @@ static int launch_qgemm(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int
   } else {
     cuuint64_t dims[3] = {(cuuint64_t)Cp_w, (cuuint64_t)(R * S), (cuuint64_t)Np};
     cuuint64_t strides[2] = {(cuuint64_t)Cp_w, (cuuint64_t)R * S * Cp_w};
-    cuuint32_t box[3] = {(cuuint32_t)BLOCK_K, 1u, (cuuint32_t)block_n};
-    int rc = encode_map(&map_b, wq, 3, dims, strides, box, "weights");
+    cuuint32_t box[3] = {(cuuint32_t)kbytes, 1u, (cuuint32_t)block_n};
+    int rc = encode_map(&map_b, wq, 3, dims, strides, box, "weights", CU_TENSOR_MAP_DATA_TYPE_UINT8,
+                        kbytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
 
   GemmParams p;
   p.M = (int)M; p.N = N; p.taps = R * S; p.S = S;
-  p.k_chunks = (Cp_w + BLOCK_K - 1) / BLOCK_K;
-  const int last_bytes = Cp_w - (p.k_chunks - 1) * BLOCK_K;
+  p.kbytes = kbytes;
+  p.k_chunks = (Cp_w + kbytes - 1) / kbytes;
+  const int last_bytes = Cp_w - (p.k_chunks - 1) * kbytes;
   p.k_last_mmas = (last_bytes + UMMA_K - 1) / UMMA_K;
   p.a_c_offset = a_c_offset;
   p.Wo = flat ? (1 << 30) : Wo;
   p.HoWo = flat ? (1 << 30) : Ho * Wo;
   p.block_n = block_n; p.n_tiles = n_tiles; p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
   p.w4 = w4; p.zoff = zoff;
-  p.b_stage_bytes = (block_n * (w4 ? BLOCK_K / 2 : BLOCK_K) + 1023) & ~1023;
+  p.b_stage_bytes = (block_n * (w4 ? BLOCK_K / 2 : kbytes) + 1023) & ~1023;
   p.u_stage_bytes = (block_n * BLOCK_K + 1023) & ~1023;
   // row-major outputs (linear layers) are staged through smem; needs whole float4s per row and no rowsum / accumulate / SiLU
   p.row_staging = (out_hw == 1 && !cw && !accumulate && !silu && (N % 4) == 0 && (block_n % 32) == 0 && ((reinterpret_cast<uintptr_t>(residual) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) ? 1 : 0;
   const int fixed = SMEM_FIXED + (p.row_staging ? ROW_STAGE_BYTES : 0) + (w4 ? U_STAGES * p.u_stage_bytes : 0);
-  p.stages = (SMEM_LIMIT - fixed) / (A_STAGE_BYTES + p.b_stage_bytes);
+  p.stages = (SMEM_LIMIT - fixed) / (BLOCK_M * kbytes + p.b_stage_bytes);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-  const int smem_bytes = fixed + p.stages * (A_STAGE_BYTES + p.b_stage_bytes);
+  if (const char* e = getenv("EDADM_GEMM_STAGES")) { const int v = atoi(e); if (v >= 2 && v < p.stages) p.stages = v; }   // debug
+  const int smem_bytes = fixed + p.stages * (BLOCK_M * kbytes + p.b_stage_bytes);
   p.out_hw = out_hw; p.accumulate = accumulate; p.silu = silu; p.residual = residual; p.bias_img = bias_img;
   p.delta_a = delta_a; p.zp_a = zp_a; p.delta_w = delta_w; p.wsum_eff = wsum_eff; p.cw = cw; p.rowsum = rowsum;
   p.bias = bias; p.out = out;
+  p.trace = g_gemm_trace;
+  p.debug = 0;
+  if (const char* e = getenv("EDADM_GEMM_DEBUG")) p.debug = atoi(e);
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -595,11 +657,33 @@ static int launch_qgemm(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int
   return check_launch("qgemm_i8");
 }
 
+namespace edadm {
+struct Gemm2Args {
+  const uint8_t* q; int B, Hp, Wp, Cp_act, a_c_offset;
+  const void* wq; int N, Np, R, S, Cp_w;
+  const float* delta_a; const float* zp_a; const float* delta_w; const int32_t* wsum_eff; const int32_t* cw; const int32_t* rowsum;
+  const float* bias; const float* bias_img; const float* residual;
+  void* out; int out_hw; int accumulate;
+  int out_mode;
+  const float* q_delta; const float* q_zp; int q_levels; int32_t* q_rowsum; int out_pitch;
+};
+int launch_qgemm2(const Gemm2Args& a, void* stream);     // qgemm2_sm100.cu; +1 = case not covered
+}
+
 extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_offset, const int8_t* wq,
                               int N, int Np, int R, int S, int Cp_w, const float* delta_a, const float* zp_a,
                               const float* delta_w, const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum,
                               const float* bias, const float* bias_img, const float* residual, float* out, int out_hw,
                               int accumulate, int silu, void* stream) {
+  static const bool force_v1 = getenv("EDADM_GEMM_V1") != nullptr;
+  if (!force_v1 && !silu && q && wq && delta_a && zp_a && delta_w && wsum_eff && out && (!cw || rowsum) && B >= 1 && Hp >= R && Wp >= S &&
+      R >= 1 && S >= 1 && N >= 1 && !(Cp_act & 15) && !(Cp_w & 15) && Cp_w >= 16 && a_c_offset >= 0 && a_c_offset + 16 <= Cp_act + 15 &&
+      !(((uintptr_t)q) & 15) && !(((uintptr_t)wq) & 15) && out_hw >= 1 && !(bias_img && out_hw == 1)) {
+    Gemm2Args a{q, B, Hp, Wp, Cp_act, a_c_offset, wq, N, Np, R, S, Cp_w, delta_a, zp_a, delta_w, wsum_eff, cw, rowsum, bias, bias_img, residual,
+                out, out_hw, accumulate, /*out_mode (decided from out_hw)*/ 0, nullptr, nullptr, 0, nullptr, 0};
+    const int rc = launch_qgemm2(a, stream);
+    if (rc <= 0) return rc;
+  }
   return launch_qgemm(q, B, Hp, Wp, Cp_act, a_c_offset, wq, 0, nullptr, N, Np, R, S, Cp_w, delta_a, zp_a, delta_w, wsum_eff, cw,
                       rowsum, bias, bias_img, residual, out, out_hw, accumulate, silu, stream);
 }

@@ -36,9 +36,11 @@ _SIGNATURES = {
     "edadm_conv_rowsum": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "edadm_pack_weight": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "edadm_qgemm_i8": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
+    "edadm_qgemm_i8_codes": (c_int, [P, c_int64, c_int, P, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, P, P, c_int, P, c_int, P, P]),
     "edadm_norm_act_pool2": (c_int, [P, P, P, c_int, P, c_int, c_int, c_int, c_int, P]),
     "edadm_upsample2x_codes": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P]),
     "edadm_layernorm_quant_rows": (c_int, [P, P, P, c_float, P, P, c_int64, c_int, c_int, P, P, c_int, P]),
+    "edadm_layernorm_quant_rows_multi": (c_int, [P, P, P, c_float, c_int, P, P, P, P, P, c_int64, c_int, c_int, P]),
     "edadm_geglu_quant_rows": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, c_int, P]),
     "edadm_pack_weight_w4": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "edadm_qgemm_w4a8": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
@@ -51,8 +53,8 @@ _lib = None
 
 # kernels each entry point launches (for bench.py's gpu_launches accounting)
 KERNELS_PER_CALL = {"uaq_fwd": 1, "uaq_bwd": 1, "adaround_fwd": 1, "adaround_bwd": 1, "adaround_init_alpha": 1,
-                    "round_reg": 2, "lp_loss_fwd": 2, "lp_loss_bwd": 1, "act_quant_nhwc": 1, "gn_fold": 1, "norm_act_quant_nhwc": 1, "conv3x3_small_n": 1, "layernorm_quant_rows": 1, "norm_act_pool2": 1, "upsample2x_codes": 1, "geglu_quant_rows": 1, "act_quant_rows": 1,
-                    "im2col_u8": 1, "conv_rowsum": 1, "pack_weight": 1, "pack_weight_w4": 1, "qgemm_i8": 1, "qgemm_w4a8": 1, "qattn_fwd": 1}
+                    "round_reg": 2, "lp_loss_fwd": 2, "lp_loss_bwd": 1, "act_quant_nhwc": 1, "gn_fold": 1, "norm_act_quant_nhwc": 1, "conv3x3_small_n": 1, "layernorm_quant_rows": 1, "layernorm_quant_rows_multi": 1, "norm_act_pool2": 1, "upsample2x_codes": 1, "geglu_quant_rows": 1, "act_quant_rows": 1,
+                    "im2col_u8": 1, "conv_rowsum": 1, "pack_weight": 1, "pack_weight_w4": 1, "qgemm_i8": 1, "qgemm_i8_codes": 1, "qgemm_w4a8": 1, "qattn_fwd": 1}
 launch_counter = {"kernels": 0, "calls": {}}
 
 

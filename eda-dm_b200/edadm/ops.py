@@ -476,6 +476,28 @@ def layernorm_quant_rows(x, norm_weight, norm_bias, eps, aq: ActQuant, want_rows
     return q, rowsum
 
 
+def layernorm_quant_rows_multi(x, norm_weight, norm_bias, eps, aqs, want_rowsum):
+    """One LayerNorm pass feeding len(aqs) (<= 3) activation quantizers: list of (codes [M, Kp], rowsum or None)."""
+    import ctypes
+    _need_cuda(x)
+    x2 = _f32c(x.reshape(-1, x.shape[-1]))
+    M, K = x2.shape
+    Kp = _round_up(K, 16)
+    n = len(aqs)
+    dev = x.device
+    qs = [torch.empty((M, Kp), dtype=torch.uint8, device=dev) for _ in range(n)]
+    rss = [torch.empty(M, dtype=torch.int32, device=dev) if w else None for w in want_rowsum]
+    ds = [_qparam(a.delta0, dev) for a in aqs]
+    zs = [_qparam(a.zp0, dev) for a in aqs]
+    g = None if norm_weight is None else _f32c(norm_weight.detach())
+    b = None if norm_bias is None else _f32c(norm_bias.detach())
+    vp = ctypes.c_void_p * n
+    lib.layernorm_quant_rows_multi(x2.data_ptr(), _ptr(g), _ptr(b), float(eps), n, vp(*[t.data_ptr() for t in qs]),
+                                   vp(*[_ptr(t) for t in rss]), vp(*[t.data_ptr() for t in ds]), vp(*[t.data_ptr() for t in zs]),
+                                   (ctypes.c_int * n)(*[a.levels0 for a in aqs]), M, K, Kp, _stream())
+    return list(zip(qs, rss))
+
+
 def geglu_quant_rows(h, aq: ActQuant, want_rowsum=False):
     """h [..., 2K] (GEGLU.proj output) -> u8 codes [M, Kp] of h[..., :K] * gelu(h[..., K:]) (one pass)."""
     _need_cuda(h)
@@ -546,6 +568,36 @@ def qgemm_i8(q, pw: PackedWeight, delta_a, zp_a, out, out_hw, bias=None, rowsum=
         m = B * (Hp - R + 1) * (Wp - S + 1)
         prof.append((ev0, ev1, m * pw.N * pw.C * pw.R * pw.S))
     return out
+
+
+def qgemm_i8_codes(q, pw: PackedWeight, delta_a, zp_a, consumer, bias=None, rowsum=None, geglu=False, want_rowsum=False):
+    """Linear GEMM whose epilogue emits the u8 codes of the NEXT activation quantizer (`consumer` = (delta, zero_point,
+    n_levels)) instead of fp32 -- optionally through the GEGLU gate.  q: [M, Kp] u8 codes.  Returns (codes [M, Kp_out], rowsum)."""
+    if pw.w4:
+        raise EdadmError("qgemm_i8_codes: nibble-packed weights are not supported by the code-emitting epilogue")
+    M, Kp_act = q.shape
+    dev = q.device
+    n_out = pw.N // 2 if geglu else pw.N
+    pitch = _round_up(n_out, 16)
+    codes = torch.empty((M, pitch), dtype=torch.uint8, device=dev)
+    rs_out = torch.zeros(M, dtype=torch.int32, device=dev) if want_rowsum else None
+    da, za = _qparam(delta_a, dev), _qparam(zp_a, dev)
+    cd, cz = _qparam(consumer[0], dev), _qparam(consumer[1], dev)
+    if pw.needs_rowsum and rowsum is None:
+        raise EdadmError("8-bit weight codes need the activation row sums (zero-point fold); pass rowsum")
+    cw = pw.cw if pw.needs_rowsum else None
+    prof = gemm_profile
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    lib.qgemm_i8_codes(q.data_ptr(), M, Kp_act, pw.wq.data_ptr(), pw.N, pw.Np, pw.wq.shape[1] * pw.wq.shape[2], da.data_ptr(),
+                       za.data_ptr(), pw.delta_w.data_ptr(), pw.wsum_eff.data_ptr(), _ptr(cw), _ptr(rowsum), _ptr(bias),
+                       1 if geglu else 0, cd.data_ptr(), cz.data_ptr(), int(consumer[2]), codes.data_ptr(), pitch, _ptr(rs_out),
+                       _stream())
+    if prof is not None:
+        ev1.record()
+        prof.append((ev0, ev1, M * pw.N * pw.C * pw.R * pw.S))
+    return codes, rs_out
 
 
 def conv3x3_small_n_ok(x, weight, kwargs):
@@ -643,3 +695,18 @@ def qattn_bnd(q, k, v, heads, aquant: AttnQuant, sm_scale):
     out = torch.empty((B, Tq, heads * d), dtype=torch.float32, device=q.device)
     return qattn(qc.reshape(BH, Tq, -1), kc.reshape(BH, Tk, -1), vc.reshape(BH, d, -1), rq.reshape(BH, Tq), rk.reshape(BH, Tk),
                  rv.reshape(BH, d), heads, d, Tk, aquant, sm_scale, out, (Tq * heads * d, d, heads * d, 1))
+
+
+def qattn_bnd_codes(qc, rq, kc, rk, v, heads, aquant: AttnQuant, sm_scale):
+    """qattn_bnd with q / k already given as u8 codes [BH, T, dp] + per-token code sums [BH, T] (emitted by the to_q / to_k
+    GEMM epilogues); v fp32 [BH, Tk, d]."""
+    _need_cuda(qc, kc, v)
+    BH, Tq, _ = qc.shape
+    Tk, d = v.shape[1], v.shape[2]
+    aqv = ActQuant(aquant.v[0], aquant.v[1], aquant.v[2])
+    vc, rv = act_quant_nhwc(_f32c(v).reshape(BH, Tk, 1, d), aqv, 0, want_chsum=True)   # "channels" = keys -> [BH,1,d,Tkp]
+    B = BH // heads
+    out = torch.empty((B, Tq, heads * d), dtype=torch.float32, device=v.device)
+    return qattn(qc, kc, vc.reshape(BH, d, -1), rq, rk, rv.reshape(BH, d), heads, d, Tk, aquant, sm_scale, out,
+                 (Tq * heads * d, d, heads * d, 1))
+

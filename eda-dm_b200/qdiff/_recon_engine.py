@@ -179,6 +179,9 @@ def _cosine_lr(lr0, t, t_max):
 def _graph_capturable(unit, device):
     if device.type != 'cuda' or not backend.recon_cuda_graph:
         return False
+    if backend.qdrop_inkernel_rng:
+        # the Philox (seed, offset) of in-kernel QDrop draws are host scalars: a captured launch would replay ONE mask forever
+        return False
     for m in unit.modules():
         # activation checkpointing re-enters autograd and snapshots RNG state: keep those units on the eager loop
         if isinstance(m, QuantAttentionBlock) or getattr(m, 'use_checkpoint', False) or getattr(m, 'checkpoint', False) is True:

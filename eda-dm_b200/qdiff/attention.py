@@ -20,8 +20,15 @@ def _bmm(a, b):
     return _library_fwd(lambda x, w, _b: th.bmm(x, w), a, b, None, {})
 
 
-def _fusable(tensors, quantizers):
-    if not backend.integer_path:
+# limits of edadm_qattn_fwd (csrc/qattn.cu): u8 codes for q/k/v and the probabilities, one CTA row of <= 4096 keys,
+# blockIdx.y = batch*heads
+_MAX_KEYS, _MAX_BH = 4096, 65535
+
+
+def _fusable(tensors, quantizers, n_keys=0, bh=0):
+    if not backend.integer_path or n_keys > _MAX_KEYS or bh > _MAX_BH:
+        return False
+    if any(q.n_levels > 256 for q in quantizers):
         return False
     for t in tensors:
         if not t.is_cuda or t.dtype != th.float32 or (th.is_grad_enabled() and t.requires_grad):
@@ -45,7 +52,7 @@ def qk_scores_bct(q, k):
 
 def quantized_attention_bnd(q, k, v, heads, scale, quant_q, quant_k, quant_v, quant_w):
     """q: [b*h, i, d]; k, v: [b*h, j, d] -> [b, i, h*d]   (cross_attn_forward, heads merged on the way out)."""
-    if _fusable((q, k, v), (quant_q, quant_k, quant_v, quant_w)):
+    if _fusable((q, k, v), (quant_q, quant_k, quant_v, quant_w), n_keys=k.shape[1], bh=q.shape[0]):
         return ops.qattn_bnd(q, k, v, heads, _aquant(quant_q, quant_k, quant_v, quant_w), scale)
     sim = _bmm(quant_q(q), quant_k(k).transpose(1, 2)) * scale
     attn = sim.softmax(dim=-1)
@@ -56,7 +63,7 @@ def quantized_attention_bnd(q, k, v, heads, scale, quant_q, quant_k, quant_v, qu
 
 def quantized_attention_bct(q, k, v, scale, quant_q, quant_k, quant_v, quant_w):
     """q, k, v: [b, c, t] -> [b, c, t]   (DDIM AttnBlock layout; softmax over keys; scale applied to the scores)."""
-    if _fusable((q, k, v), (quant_q, quant_k, quant_v, quant_w)):
+    if _fusable((q, k, v), (quant_q, quant_k, quant_v, quant_w), n_keys=k.shape[2], bh=q.shape[0]):
         return ops.qattn_bct(q, k, v, _aquant(quant_q, quant_k, quant_v, quant_w), 1.0, scale)
     qq = quant_q(q.permute(0, 2, 1))          # [b, t, c], quantized in the layout the reference uses
     kq = quant_k(k)                           # [b, c, s]
@@ -76,7 +83,8 @@ def legacy_attention_forward(self, qkv):
     self.qkv_matmul.scale = scale
     qk, sv = self.qkv_matmul, self.smv_matmul
     if qk.use_act_quant and sv.use_act_quant and \
-            _fusable((qkv,), (qk.act_quantizer_q, qk.act_quantizer_k, sv.act_quantizer_v, sv.act_quantizer_w)):
+            _fusable((qkv,), (qk.act_quantizer_q, qk.act_quantizer_k, sv.act_quantizer_v, sv.act_quantizer_w), n_keys=length,
+                     bh=bs * self.n_heads):
         aq = _aquant(qk.act_quantizer_q, qk.act_quantizer_k, sv.act_quantizer_v, sv.act_quantizer_w)
         return ops.qattn_bct(q, k, v, aq, scale, 1.0).reshape(bs, -1, length)
     weight = qk(q, k)

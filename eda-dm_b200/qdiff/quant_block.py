@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from unet_zoo import ddpm_unet as _zoo_ddpm
 from unet_zoo import ldm_unet as _zoo_ldm
-from .quant_layer import QuantModule, UniformAffineQuantizer, StraightThrough
+from .quant_layer import QuantModule, UniformAffineQuantizer, StraightThrough, backend
 from . import attention as qattn
 
 logger = logging.getLogger(__name__)
@@ -87,11 +87,12 @@ def _emb_layers(seq, emb):
     is computed once per forward and kept on the tensor object (inference only; no hooks on the SiLU)."""
     if (len(seq) == 2 and isinstance(seq[0], nn.SiLU) and not seq[0]._forward_hooks and not th.is_grad_enabled()
             and not emb.requires_grad):
-        act = getattr(emb, '_edadm_silu', None)
-        if act is None:
-            act = seq[0](emb)
-            emb._edadm_silu = act
-        return seq[1](act)
+        key = (emb._version, emb.data_ptr())
+        cached = getattr(emb, '_edadm_silu', None)
+        if cached is None or cached[0] != key:        # a reused buffer that was updated in place gets a fresh activation
+            cached = (key, seq[0](emb))
+            emb._edadm_silu = cached
+        return seq[1](cached[1])
     return seq(emb)
 
 
@@ -263,6 +264,9 @@ def cross_attn_forward(self, x, context=None, mask=None, norm=None, residual=Non
     if mask is not None:
         raise NotImplementedError("attention masks are not used by any EDA-DM configuration")
     self_attn = context is None
+    fast = _cross_attn_integer(self, x, context, norm, residual)
+    if fast is not None:
+        return fast
     if norm is not None:
         mods = (self.to_q, self.to_k, self.to_v) if self_attn else (self.to_q,)
         if all(isinstance(m, QuantModule) and m.prenorm_fusable(x, norm) for m in mods):
@@ -294,6 +298,59 @@ def cross_attn_forward(self, x, context=None, mask=None, norm=None, residual=Non
     return _conv_plus(lin, residual, lambda **kw: lin(out, **kw))
 
 
+def _cross_attn_integer(attn, x, context, norm, residual):
+    """Integer-path forms of cross_attn_forward (reference quant_block.py:204-235) that never materialise fp32 q / k; None when
+    they do not apply (then the module-by-module formulation below runs).
+
+    * one context token (the class embedding of LDM-4 ImageNet, `ClassEmbedder` -> [B, 1, 512]): softmax over a single key is
+      exactly 1 whatever q is, so `attn = Q_w(1)` and every query row of a sample gets the same `Q_w(1) * Q_v(v)`; to_q, its
+      LayerNorm pass and the attention matmuls drop out and to_out runs on B rows instead of B*T.
+    * single-head self attention: one LayerNorm pass emits the codes of to_q / to_k / to_v's activation quantizers, and the
+      to_q / to_k GEMMs emit the codes of the attention's q / k quantizers from their epilogue."""
+    if th.is_grad_enabled() or norm is None or residual is None or not attn.use_act_quant or not backend.fuse_epilogue:
+        return None
+    lin_out, rest = attn.to_out[0], attn.to_out[1:]
+    if any(isinstance(m, nn.Dropout) and m.p > 0 and m.training for m in rest) or any(m._forward_hooks for m in rest):
+        return None
+    mods = (attn.to_q, attn.to_k, attn.to_v, lin_out)
+    if not all(isinstance(m, QuantModule) for m in mods):
+        return None
+    qs = (attn.act_quantizer_q, attn.act_quantizer_k, attn.act_quantizer_v, attn.act_quantizer_w)
+    if not qattn._fusable((x,), qs):
+        return None
+    if context is not None and context.shape[1] == 1 and lin_out._integer_path_ok(x) and not lin_out._forward_hooks \
+            and not lin_out._forward_pre_hooks and not attn.to_q._forward_hooks and not attn.to_q._forward_pre_hooks \
+            and not norm._forward_hooks and lin_out._epilogue_residual(residual) is not None:
+        v = attn.to_v(context)                                   # [B, 1, h*d]
+        attn.to_k(context)                                       # keeps to_k's hooks / path report alive; its value cannot matter
+        qw, qv = attn.act_quantizer_w, attn.act_quantizer_v
+        one = th.ones(1, dtype=v.dtype, device=v.device)
+        # Q_w(softmax over one key) * Q_v(v), the same row for every query -- in the arithmetic of the fused attention kernel
+        # (integer product of the zero-point-free codes, scaled once by dP*dv) so both routes agree bit for bit
+        p_int = qw.codes(one).to(th.int32) - qw.zero_point.to(th.int32)
+        v_int = qv.codes(v).to(th.int32) - qv.zero_point.to(th.int32)
+        out = (p_int * v_int).to(v.dtype) * (qw.delta.detach() * qv.delta.detach())
+        row = lin_out(out)                                       # [B, 1, C]
+        attn.to_q.last_path = 'elided'                           # (QuantModel.path_report)
+        return residual + row
+    if context is None and attn.heads == 1 and backend.fuse_epilogue and all(m.codes_consumer_ok() for m in mods[:3]) \
+            and all(m.prenorm_fusable(x, norm) for m in mods[:3]) and attn.to_q.emit_ok(attn.act_quantizer_q) \
+            and attn.to_k.emit_ok(attn.act_quantizer_k):
+        from edadm import ops
+        lead = x.shape[:-1]
+        aqs = [ops.ActQuant(m.act_quantizer.delta, m.act_quantizer.zero_point, m.act_quantizer.n_levels) for m in mods[:3]]
+        (cq, rq), (ck, rk), (cv, rv) = ops.layernorm_quant_rows_multi(x, norm.weight, norm.bias, norm.eps, aqs,
+                                                                      [m.needs_act_rowsum() for m in mods[:3]])
+        qc, qr = attn.to_q.forward_from_codes(cq, rq, lead, emit=('plain', attn.act_quantizer_q, True))
+        kc, kr = attn.to_k.forward_from_codes(ck, rk, lead, emit=('plain', attn.act_quantizer_k, True))
+        v = attn.to_v.forward_from_codes(cv, rv, lead)
+        B, T = x.shape[0], x.shape[1]
+        out = ops.qattn_bnd_codes(qc.reshape(B, T, -1), qr.reshape(B, T), kc.reshape(B, T, -1), kr.reshape(B, T), v, 1,
+                                  qattn._aquant(*qs), attn.scale)
+        return _conv_plus(lin_out, residual, lambda **kw: lin_out(out, **kw))
+    return None
+
+
 def _ff_forward(ff, x, norm):
     """`ff(norm(x)) + x` of BasicTransformerBlock (ldm/modules/attention.py:  FeedForward = [GEGLU | Linear+GELU], Dropout,
     Linear) with LayerNorm, the GEGLU gate and the residual folded into the two linears' producers / epilogue."""
@@ -303,6 +360,11 @@ def _ff_forward(ff, x, norm):
     lin_in = first.proj if geglu else first[0]
     if drop_active or not isinstance(lin_in, QuantModule) or not isinstance(last, QuantModule):
         return ff(norm(x)) + x
+    if (geglu and not th.is_grad_enabled() and last.codes_consumer_ok() and lin_in.prenorm_fusable(x, norm)
+            and lin_in.emit_ok(last.act_quantizer, geglu=True) and last._epilogue_residual(x) is not None):
+        # GEGLU gate + net[2]'s activation quantizer in the projection's GEMM epilogue: the [.., 2*inner] fp32 tensor never exists
+        codes, rs = lin_in.forward_prenorm(x, norm, silu=False, emit=('geglu', last.act_quantizer, last.needs_act_rowsum()))
+        return last.forward_from_codes(codes, rs, x.shape[:-1], residual=x)
     h = lin_in.forward_prenorm(x, norm, silu=False)
     if geglu:
         return _conv_plus(last, x, lambda **kw: last.forward_geglu(h, **kw))

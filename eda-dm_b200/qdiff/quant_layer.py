@@ -30,6 +30,7 @@ class _Backend:
     allow_tf32 = False       # library conv/matmul of the calibration path in strict fp32
     integer_path = True      # use the tcgen05 int8 GEMM whenever it applies
     fuse_norm = True         # GroupNorm + SiLU + activation quantizer as one producer pass on the integer path
+    fuse_epilogue = True     # linears whose only consumer is the next activation quantizer emit its u8 codes from the GEMM epilogue
     # (4-bit weight storage with in-smem unpack: `edadm.ops.w4_storage`)
     recon_cuda_graph = True  # capture the reconstruction iteration in one CUDA graph after 3 eager iterations
     recon_overlap_fp = False  # ... with the FP forward on a forked stream (a parallel graph branch): +4 % on a church
@@ -215,12 +216,45 @@ class UniformAffineQuantizer(nn.Module):
             delta, zero_point = delta.reshape(shape), zero_point.reshape(shape)
         return delta, zero_point
 
+    def init_quantization_scale_2(self, x: torch.Tensor, channel_wise: bool = False):
+        """'max' / 'max_scale' range (reference quant_layer.py:278-345): the tensor's (per-channel) extrema instead of a
+        search.  The reference walks the channels in a Python loop with `.item()` on every one; here the same float64 host
+        arithmetic (`x_absmax / n_levels`, `round(-x_min / delta)`) is applied to the vector of channel extrema."""
+        if 'max' not in self.scale_method:
+            raise NotImplementedError
+        with torch.no_grad():
+            y = torch.flatten(x.detach(), 1) if channel_wise else x.detach().reshape(1, -1)
+            lo64, hi64 = y.amin(1).double(), y.amax(1).double()
+            if self.leaf_param and not channel_wise:
+                self.x_min, self.x_max = x.data.min(), x.data.max()
+            x_min, x_max = lo64.clamp(max=0.0), hi64.clamp(min=0.0)
+            if 'scale' in self.scale_method:
+                x_min, x_max = x_min * (self.n_bits + 2) / 8, x_max * (self.n_bits + 2) / 8
+            if self.sym:
+                delta = torch.max(x_min.abs(), x_max) / self.n_levels
+            else:
+                delta = (hi64 - lo64) / (self.n_levels - 1)
+            delta = torch.where(delta < 1e-8, torch.full_like(delta, 1e-8), delta)
+            if self.sym or self.always_zero:
+                zero_point = torch.zeros_like(delta)
+            else:
+                zero_point = torch.round(-x_min / delta)
+            delta, zero_point = delta.to(x.dtype), zero_point.to(x.dtype)
+        if channel_wise:
+            shape = [1] * x.dim()
+            shape[0] = x.shape[0]
+            return delta.reshape(shape), zero_point.reshape(shape)
+        return delta.reshape(()), zero_point.reshape(())
+
     # ---- forward -------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor):
         if self.inited is False:
-            if self.scale_method != 'mse':
+            if self.scale_method == 'mse':
+                delta, self.zero_point = self.init_quantization_scale_1(x, self.channel_wise)
+            elif self.scale_method == 'max':
+                delta, self.zero_point = self.init_quantization_scale_2(x, self.channel_wise)
+            else:
                 raise NotImplementedError
-            delta, self.zero_point = self.init_quantization_scale_1(x, self.channel_wise)
             self.delta = torch.nn.Parameter(delta) if self.leaf_param else delta
         if not x.is_cuda:
             raise EdadmError("UniformAffineQuantizer needs CUDA tensors: the fake-quant kernel has no CPU fallback")
@@ -314,9 +348,13 @@ class QuantModule(nn.Module):
         return [self.weight_quantizer], [self.act_quantizer]
 
     def _integer_path_ok(self, input):
-        if not (backend.integer_path and self.use_weight_quant and self.use_act_quant and not self.disable_act_quant):
-            return False
         if not input.is_cuda or input.dtype != torch.float32 or torch.is_grad_enabled() and input.requires_grad:
+            return False
+        return self._integer_state_ok(input)
+
+    def _integer_state_ok(self, input=None):
+        """quantizer / layer state allows the integer path (input: only needed for the shape checks of split convs)"""
+        if not (backend.integer_path and self.use_weight_quant and self.use_act_quant and not self.disable_act_quant):
             return False
         wqs, aqs = self._quantizers()
         for aq in aqs:
@@ -334,6 +372,12 @@ class QuantModule(nn.Module):
         if torch.is_grad_enabled() and any(getattr(wq, 'alpha', None) is not None and wq.alpha.requires_grad and
                                            getattr(wq, 'soft_targets', False) for wq in wqs):
             return False
+        # hard limits of the kernels: u8 activation codes, s8 weight codes; anything wider takes the fake-quant route
+        if any(aq.n_levels > 256 for aq in aqs) or any(wq.n_levels > 256 for wq in wqs):
+            return False
+        # 8-bit weight codes need the per-row activation code sums (zero-point fold), which exist per tensor, not per K range
+        if self.split != 0 and any(wq.n_levels > 128 for wq in wqs):
+            return False
         kw = self.fwd_kwargs
         if kw:
             if kw['groups'] != 1 or any(d != 1 for d in kw['dilation']):
@@ -341,6 +385,16 @@ class QuantModule(nn.Module):
             pad, stride = kw['padding'], kw['stride']
             if isinstance(pad, str) or len(set(pad)) != 1 or len(set(stride)) != 1:
                 return False
+            if self.fwd_func is F.conv1d and int(pad[0]) != 0:
+                return False
+            if self.split != 0 and input is not None and input.dim() == 4:
+                # a split shortcut runs as two K-range GEMMs over the implicit (TMA-tiled) route only
+                R, S = self.weight.shape[2], self.weight.shape[3]
+                p0, s0 = int(pad[0]), int(stride[0])
+                Ho = (input.shape[2] + 2 * p0 - R) // s0 + 1
+                Wo = (input.shape[3] + 2 * p0 - S) // s0 + 1
+                if s0 != 1 or not _implicit_tiling_ok(input.shape[0], Ho, Wo):
+                    return False
         return True
 
     def _packed_weights(self):
@@ -376,7 +430,7 @@ class QuantModule(nn.Module):
                     and not self._forward_pre_hooks and not norm._forward_hooks)
 
     def forward_prenorm(self, x, norm, silu: bool = True, scale=None, shift=None, split: int = 0, act_fn=F.silu,
-                        residual=None, tokens_out: bool = False, bias_img=None, resample=None):
+                        residual=None, tokens_out: bool = False, bias_img=None, resample=None, emit=None):
         """`self(silu(norm(x) [* (1 + scale) + shift]))` for a GroupNorm in front of this conv (or a LayerNorm in front of this
         linear).  On the integer path normalisation + conditioning + SiLU + activation quantization run as ONE producer
         pass (edadm_gn_fold + edadm_norm_act_quant_nhwc, or edadm_layernorm_quant_rows); otherwise it is computed module
@@ -412,6 +466,8 @@ class QuantModule(nn.Module):
         self.last_path = 'int8'
         if isinstance(norm, nn.LayerNorm):
             assert scale is None and not silu
+            if emit is not None:        # (codes, rowsum) of the consumer quantizer; the caller checked emit_ok()
+                return self._forward_int8(x, rows=('layernorm', norm), emit=emit)
             return self._finish(self._forward_int8(x, rows=('layernorm', norm), residual=self._epilogue_residual(residual)), residual)
         a, s = ops.gn_fold(x, norm.weight, norm.bias, norm.num_groups, norm.eps, scale, shift)
         codes = None
@@ -465,6 +521,37 @@ class QuantModule(nn.Module):
         self.last_path = 'int8'
         return self._finish(self._forward_int8(y, rows=('tokens', H, W), residual=self._epilogue_residual(residual)), residual)
 
+    def needs_act_rowsum(self) -> bool:
+        """the integer GEMM of this layer needs per-row activation code sums (8-bit weight codes, zero-point fold)"""
+        return any(p.needs_rowsum for p in self._packed_weights())
+
+    def emit_ok(self, consumer_q, geglu: bool = False) -> bool:
+        """This linear may emit the u8 codes of `consumer_q` (the next activation quantizer) from its GEMM epilogue: nothing but
+        that quantizer (and, with `geglu`, the GEGLU gate) may observe its fp32 output.  The caller checks the input side
+        (`prenorm_fusable` / `_integer_path_ok`)."""
+        if not (backend.fuse_epilogue and self.fwd_func is F.linear and self.split == 0 and not self._forward_hooks
+                and isinstance(self.activation_function, StraightThrough) and not torch.is_grad_enabled()):
+            return False
+        q = consumer_q
+        if q.inited is False or q.delta is None or q.channel_wise or q.n_levels > 256 or (q.is_training and q.prob < 1.0):
+            return False
+        if any(p.w4 for p in self._packed_weights()):
+            return False
+        n_out = self.weight.shape[0] // 2 if geglu else self.weight.shape[0]
+        return n_out % 32 == 0 if geglu else True
+
+    def codes_consumer_ok(self) -> bool:
+        """This linear can take its activation codes ready-made (from the producing GEMM's epilogue or a shared LayerNorm pass)."""
+        return bool(self.fwd_func is F.linear and self.split == 0 and self._integer_state_ok() and not self._forward_hooks
+                    and not self._forward_pre_hooks and not torch.is_grad_enabled())
+
+    def forward_from_codes(self, q, rowsum, lead, residual=None, emit=None):
+        """`self(x)` for an input that only exists as the u8 codes `q` [M, Kp] of this layer's own activation quantizer."""
+        self.last_path = 'int8'
+        if emit is not None:
+            return self._forward_int8(None, rows=('codes', q, rowsum, lead), emit=emit)
+        return self._finish(self._forward_int8(None, rows=('codes', q, rowsum, lead), residual=self._epilogue_residual(residual)), residual)
+
     def _epilogue_residual(self, residual):
         """`residual` if the GEMM epilogue may add it (nothing but a StraightThrough sits between conv and add)."""
         return residual if isinstance(self.activation_function, StraightThrough) else None
@@ -475,7 +562,7 @@ class QuantModule(nn.Module):
             out = out + residual
         return out
 
-    def _forward_int8(self, input, affine=None, residual=None, rows=None, tokens_out=False, bias_img=None, codes=None):
+    def _forward_int8(self, input, affine=None, residual=None, rows=None, tokens_out=False, bias_img=None, codes=None, emit=None):
         """Exact integer GEMM: out = dA*dW[n]*sum (qa-za)(qw-zw) + bias  == the reference's fp32 conv of the
         dequantised tensors (quant_layer.py:414-434) without its per-product rounding."""
         packs = self._packed_weights()
@@ -500,14 +587,22 @@ class QuantModule(nn.Module):
             self._gemm_chain(q, packs, aqs, out, H * W, bias, rowsum, residual)     # flat GEMM, NCHW store (out_hw = H*W)
             return out
         if self.fwd_func is F.linear:
-            lead = input.shape[:-1]
-            if rows is None:
-                q, rowsum = ops.act_quant_rows(input.reshape(-1, input.shape[-1]), aq, want_rowsum=needs_rowsum)
-            elif rows[0] == 'layernorm':
-                q, rowsum = ops.layernorm_quant_rows(input, rows[1].weight, rows[1].bias, rows[1].eps, aq, want_rowsum=needs_rowsum)
-            else:   # 'geglu'
-                q, rowsum = ops.geglu_quant_rows(input, aq, want_rowsum=needs_rowsum)
-            out = torch.empty((q.shape[0], N), dtype=torch.float32, device=input.device)
+            if rows is not None and rows[0] == 'codes':     # activation codes emitted by the producing GEMM / a shared LayerNorm pass
+                _, q, rowsum, lead = rows
+            else:
+                lead = input.shape[:-1]
+                if rows is None:
+                    q, rowsum = ops.act_quant_rows(input.reshape(-1, input.shape[-1]), aq, want_rowsum=needs_rowsum)
+                elif rows[0] == 'layernorm':
+                    q, rowsum = ops.layernorm_quant_rows(input, rows[1].weight, rows[1].bias, rows[1].eps, aq, want_rowsum=needs_rowsum)
+                else:   # 'geglu'
+                    q, rowsum = ops.geglu_quant_rows(input, aq, want_rowsum=needs_rowsum)
+            if emit is not None:
+                # the only consumer of this linear is the activation quantizer `emit[1]`: its codes come straight from the epilogue
+                kind, cons, want_rs = emit
+                return ops.qgemm_i8_codes(q, pw0, aqs[0].delta, aqs[0].zero_point, (cons.delta, cons.zero_point, cons.n_levels),
+                                          bias=bias, rowsum=rowsum, geglu=(kind == 'geglu'), want_rowsum=want_rs)
+            out = torch.empty((q.shape[0], N), dtype=torch.float32, device=q.device)
             if residual is not None:
                 residual = residual.reshape(-1, N).contiguous()
             if q.shape[0] > 0:

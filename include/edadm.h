@@ -112,6 +112,11 @@ int edadm_upsample2x_codes(const uint8_t* q_lo, uint8_t* q_hi, int B, int C, int
  * FeedForward.net[2].  h is GEGLU.proj's output [M][2K]; q [M][Kp] u8; rowsum nullable.                             */
 int edadm_layernorm_quant_rows(const float* x, const float* gamma, const float* beta, float eps, uint8_t* q, int32_t* rowsum,
                                int64_t M, int K, int Kp, const float* delta, const float* zp, int n_levels, void* stream);
+/* The same pass feeding n (1..3) quantizers at once -- norm1 in front of to_q / to_k / to_v (qdiff/quant_block.py:254,
+ * cross_attn_forward :211-213): q[t] [M][Kp], rowsum[t] (nullable array / entries), delta[t] / zp[t] device scalars.     */
+int edadm_layernorm_quant_rows_multi(const float* x, const float* gamma, const float* beta, float eps, int n,
+                                     uint8_t* const* q, int32_t* const* rowsum, const float* const* delta,
+                                     const float* const* zp, const int* n_levels, int64_t M, int K, int Kp, void* stream);
 int edadm_geglu_quant_rows(const float* h, uint8_t* q, int32_t* rowsum, int64_t M, int K, int Kp, const float* delta,
                            const float* zp, int n_levels, void* stream);
 int edadm_im2col_u8(const uint8_t* q, uint8_t* a, int B, int Hp, int Wp, int Cp, int Ho, int Wo, int R, int S,
@@ -140,6 +145,16 @@ int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int a_c_
                    int R, int S, int Cp_w, const float* delta_a, const float* zp_a, const float* delta_w,
                    const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum, const float* bias,
                    const float* bias_img, const float* residual, float* out, int out_hw, int accumulate, int silu, void* stream);
+
+/* Same GEMM for a linear whose ONLY consumer is the activation quantizer of the next QuantModule (the consumer's
+ * `input = self.act_quantizer(input)`, qdiff/quant_layer.py:414-422): the epilogue applies that quantizer and stores its u8
+ * codes, out_codes [M][out_pitch], so the fp32 tensor never exists.  geglu = 1 additionally applies GEGLU.forward
+ * (ldm/modules/attention.py:37-44): codes of y[:, n] * gelu(y[:, N/2 + n]) for n < N/2.  q_rowsum (nullable, zeroed by the
+ * caller) accumulates the per-row code sums the consumer GEMM / the attention kernel need for their zero-point fold.   */
+int edadm_qgemm_i8_codes(const uint8_t* q, int64_t M, int Kp_act, const int8_t* wq, int N, int Np, int Cp_w,
+                         const float* delta_a, const float* zp_a, const float* delta_w, const int32_t* wsum_eff,
+                         const int32_t* cw, const int32_t* rowsum, const float* bias, int geglu, const float* q_delta,
+                         const float* q_zp, int q_levels, uint8_t* out_codes, int out_pitch, int32_t* q_rowsum, void* stream);
 
 /* W4 storage: the same GEMM with the weights kept as 4-bit codes, two per byte -- wq4 u8 [Np][R*S][Cp/2] (Cp % 32 == 0; inside
  * each 32-bit word byte j = code[c0+j] | code[c0+4+j] << 4), zoff[n] = zp[n] -- and unpacked to s8 (code - zoff[n]) in

@@ -1,14 +1,58 @@
-import ctypes, os, torch
-lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmmapeak.so"))
+"""Tensor-pipe microbenchmark (scratch/mma_peak_lib.cu): back-to-back tcgen05.mma from resident smem tiles on all 148 SMs.
+Prints cycles per MMA instruction (SM clock, CTA 0) and chip-wide TOP/s from CUDA events; `sustained` repeats the best int8
+configuration back to back for ~3 s (power-capped clocks).  Output is committed as profiles/int8_peak_r02.txt and read by bench.py."""
+import ctypes, json, os, sys, time, torch
+HERE = os.path.dirname(os.path.abspath(__file__))
+lib = ctypes.CDLL(os.path.join(HERE, "libmmapeak.so"))
 lib.run_peak.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+lib.run_peak2.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 dev = torch.device("cuda:0")
 cyc = torch.zeros(148, dtype=torch.int64, device=dev)
-for (n, ce, rd) in [(192, 0, 0), (192, 1, 0), (192, 2, 0), (192, 4, 0), (192, 0, 4), (192, 1, 4), (256, 1, 0), (256, 1, 4), (64, 1, 0)]:
-    iters, grid, f16 = 4096, 148, 0
-    st = torch.cuda.current_stream().cuda_stream
-    lib.run_peak(n, iters, f16, grid, cyc.data_ptr(), st, ce, rd); torch.cuda.synchronize()
+st = torch.cuda.current_stream().cuda_stream
+iters = 4096
+best = {}
+
+
+def run(fn, label, n, f16):
+    fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); rc = lib.run_peak(n, iters, f16, grid, cyc.data_ptr(), st, ce, rd); e1.record(); torch.cuda.synchronize()
+    e0.record(); rc = fn(); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    ops = 2.0 * 128 * n * 32 * 4 * iters * grid
-    print(f"i8 N={n:3d} commit every {ce} k-steps (4 MMAs each), tmem readers {rd}: rc={rc} {cyc[0].item() / (4 * iters):7.1f} cycles/MMA  {ops / (ms * 1e-3) / 1e12:8.1f} TOP/s", flush=True)
+    kk = 16 if f16 else 32
+    ops = 2.0 * 128 * n * kk * 4 * iters * 148          # every CTA contributes 128 rows x n columns per instruction
+    tops = ops / (ms * 1e-3) / 1e12
+    print(f"{label:58s} rc={rc} {cyc[0].item() / (4 * iters):7.1f} cycles/MMA {tops:8.1f} T{'FL' if f16 else ''}OP/s", flush=True)
+    key = "f16" if f16 else "i8"
+    best[key] = max(best.get(key, 0.0), tops)
+    return tops
+
+
+for f16 in (0, 1):
+    kind = "f16" if f16 else "i8 "
+    for n in (64, 128, 192, 256):
+        for ce in (0, 1):
+            run(lambda: lib.run_peak(n, iters, f16, 148, cyc.data_ptr(), st, ce, 0), f"{kind} cta_group::1 M=128 N={n:3d} commit/{ce} k-step", n, f16)
+    for n in (64, 128, 192, 256):
+        for ce in (0, 1):
+            run(lambda: lib.run_peak2(n, iters, f16, 148, cyc.data_ptr(), st, ce), f"{kind} cta_group::2 M=256 N={n:3d} commit/{ce} k-step", n, f16)
+
+# sustained: ~3 s of back-to-back launches of the best shape (cta_group::2, N=256, commit per k-step)
+for name, fn, f16 in (("i8 cta_group::2 N=256", lambda: lib.run_peak2(256, iters, 0, 148, cyc.data_ptr(), st, 1), 0),
+                      ("f16 cta_group::2 N=256", lambda: lib.run_peak2(256, iters, 1, 148, cyc.data_ptr(), st, 1), 1)):
+    fn(); torch.cuda.synchronize()
+    t0 = time.time(); reps = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    while time.time() - t0 < 3.0:
+        for _ in range(50):
+            fn()
+        reps += 50
+        torch.cuda.synchronize()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    kk = 16 if f16 else 32
+    tops = 2.0 * 128 * 256 * kk * 4 * iters * 148 * reps / (ms * 1e-3) / 1e12
+    print(f"sustained {name}: {reps} launches in {ms / 1e3:.2f} s -> {tops:.1f} T{'FL' if f16 else ''}OP/s", flush=True)
+    best[("f16" if f16 else "i8") + "_sustained"] = tops
+print("SUMMARY " + json.dumps({"int8_tops_burst": best.get("i8"), "int8_tops_sustained": best.get("i8_sustained"),
+                               "f16_tflops_burst": best.get("f16"), "f16_tflops_sustained": best.get("f16_sustained")}))

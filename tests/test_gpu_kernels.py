@@ -654,3 +654,113 @@ def test_resample_producers(cuda):
         q_hi = ops.upsample2x_codes(q_lo, C, 1, aq)
         ref, _ = ops.act_quant_nhwc(F.interpolate(y, scale_factor=2, mode="nearest"), aq, 1)
         assert torch.equal(q_hi, ref)
+
+
+# ---- round 2: second-generation GEMM (CTA pairs, TMA-store epilogue, code-emitting epilogues) -------------------------------
+@pytest.mark.parametrize("ctas", ["1", "2"])
+@pytest.mark.parametrize("B,C,H,N,k,res", [(6, 192, 32, 192, 3, True), (3, 128, 64, 96, 3, False), (40, 64, 8, 320, 3, True),
+                                           (70, 96, 4, 160, 3, True), (5, 72, 16, 40, 1, False)])
+def test_qgemm2_conv_pairs_and_tma_store(cuda, monkeypatch, ctas, B, C, H, N, k, res):
+    """cta_group::2 pairs / single CTAs, NCHW TMA-store epilogue incl. tiles that span several images (HW < 128), M and N tails,
+    TMA-loaded residual: exact vs an fp64 convolution of the integer codes"""
+    from edadm import ops
+    monkeypatch.setenv("EDADM_GEMM_CTAS", ctas)
+    g = torch.Generator().manual_seed(B * 131 + C)
+    x = torch.randn(B, C, H, H, generator=g).to(cuda)
+    w = (torch.randn(N, C, k, k, generator=g) * 0.05).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    d = torch.tensor([0.03], device=cuda); z = torch.tensor([128.], device=cuda)
+    dw = (w.flatten(1).abs().amax(1) / 7.5).reshape(-1, 1, 1, 1); zw = torch.full_like(dw, 8.)
+    pw = ops.pack_weight(w, dw, zw, 16, want_codes=True, w4=False)
+    q, _ = ops.act_quant_nhwc(x, ops.ActQuant(d, z, 256), k // 2)
+    out = torch.empty(B, N, H, H, device=cuda)
+    r = torch.randn(B, N, H, H, generator=g).to(cuda) if res else None
+    ops.qgemm_i8(q, pw, d, z, out, H * H, bias=bias, residual=r)
+    p = k // 2
+    ai = q[:, p:q.shape[1] - p or None, p:q.shape[2] - p or None, :C].permute(0, 3, 1, 2).double() - 128.0
+    ref = F.conv2d(ai, pw.codes.double() - 8.0, padding=p) * (0.03 * dw.double().reshape(1, -1, 1, 1)) + bias.double().reshape(1, -1, 1, 1)
+    if res:
+        ref = ref + r.double()
+    assert _rel_l2(out.double(), ref) < 1e-6
+
+
+@pytest.mark.parametrize("M,K,N,geglu,w_bits", [(300, 384, 384, False, 4), (4096, 384, 3072, True, 4), (1000, 96, 192, True, 4),
+                                                (77, 320, 80, False, 8), (513, 128, 64, True, 8)])
+def test_qgemm_codes_epilogue_bit_exact(cuda, M, K, N, geglu, w_bits):
+    """the code-emitting epilogue (plain / GEGLU-gated) == fp32 GEMM output followed by the standalone quantizer producers"""
+    from edadm import ops
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g).to(cuda)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    L = 2 ** w_bits
+    d = torch.tensor([0.03], device=cuda); z = torch.tensor([128.], device=cuda)
+    dw = (w.abs().amax(1) / (L / 2 - 0.5)).reshape(-1, 1); zw = torch.full_like(dw, float(L // 2 - (w_bits == 8)))
+    pw = ops.pack_weight(w, dw, zw, L, w4=False)
+    aq = ops.ActQuant(d, z, 256)
+    q, rowsum = ops.act_quant_rows(x, aq, want_rowsum=pw.needs_rowsum)
+    y = torch.empty(M, N, device=cuda)
+    ops.qgemm_i8(q, pw, d, z, y, 1, bias=bias, rowsum=rowsum)
+    cd = torch.tensor([0.011], device=cuda); cz = torch.tensor([128.], device=cuda)
+    cons = ops.ActQuant(cd, cz, 256)
+    if geglu:
+        want, want_rs = ops.geglu_quant_rows(y, cons, want_rowsum=True)
+    else:
+        want, want_rs = ops.act_quant_rows(y, cons, want_rowsum=True)
+    got, got_rs = ops.qgemm_i8_codes(q, pw, d, z, (cd, cz, 256), bias=bias, rowsum=rowsum, geglu=geglu, want_rowsum=True)
+    n_out = N // 2 if geglu else N
+    assert torch.equal(got[:, :n_out], want[:, :n_out])
+    assert torch.equal(got_rs, want_rs)
+
+
+def test_layernorm_multi_equals_single(cuda):
+    from edadm import ops
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(333, 384, generator=g) * 2).to(cuda)
+    ln = torch.nn.LayerNorm(384).to(cuda)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5); ln.bias.uniform_(-0.3, 0.3)
+    aqs = [ops.ActQuant(torch.tensor([s], device=cuda), torch.tensor([zp], device=cuda), 256) for s, zp in ((0.02, 128.), (0.031, 127.), (0.05, 128.))]
+    multi = ops.layernorm_quant_rows_multi(x, ln.weight, ln.bias, ln.eps, aqs, [True, False, True])
+    for aq, (qc, rs), want_rs in zip(aqs, multi, [True, False, True]):
+        q1, r1 = ops.layernorm_quant_rows(x, ln.weight, ln.bias, ln.eps, aq, want_rowsum=True)
+        assert torch.equal(qc, q1)
+        assert (rs is None) == (not want_rs) and (rs is None or torch.equal(rs, r1))
+
+
+@pytest.mark.parametrize("ctx_tokens,heads", [(1, 1), (5, 1), (1, 4)])
+def test_transformer_epilogue_fusions_are_exact(cuda, ctx_tokens, heads):
+    """GEGLU / q / k codes from the GEMM epilogue, the shared LayerNorm pass and the one-key cross-attention shortcut leave a
+    QuantBasicTransformerBlock's output bit-identical to the module-by-module integer path (backend.fuse_epilogue off)"""
+    from qdiff import QuantModel, set_weight_quantize_params, set_act_quantize_params
+    from qdiff.quant_layer import backend
+    from unet_zoo.ldm_unet import UNetModel
+    torch.manual_seed(17)
+    model = UNetModel(image_size=16, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=1,
+                      attention_resolutions=(1, 2), channel_mult=(1, 2), num_heads=heads, use_spatial_transformer=True,
+                      transformer_depth=1, context_dim=48).to(cuda).eval()
+    for p in model.parameters():
+        if p.dim() > 1 and float(p.abs().max()) == 0:
+            torch.nn.init.normal_(p, std=0.02)
+    wq = dict(n_bits=4, symmetric=True, channel_wise=True, scale_method='mse')
+    aq = dict(n_bits=8, symmetric=True, channel_wise=False, scale_method='mse', leaf_param=True, prob=1.0)
+    qnn = QuantModel(model, wq, aq, sm_abit=8).to(cuda).eval()
+    qnn.set_first_last_layer_to_8bit()
+    qnn.disable_network_output_quantization()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(8, 4, 16, 16, generator=g).to(cuda)
+    t = torch.randint(0, 1000, (8,), generator=g).to(cuda)
+    ctx = torch.randn(8, ctx_tokens, 48, generator=g).to(cuda)
+    qnn.set_quant_state(True, True)
+    with torch.no_grad():
+        set_weight_quantize_params(qnn, (x, t, ctx))
+        set_act_quantize_params(qnn, (x, t, ctx), all_attention=True)
+        qnn.set_quant_state(True, True)
+        y1 = qnn(x, t, ctx)
+        backend.fuse_epilogue = False
+        try:
+            y0 = qnn(x, t, ctx)
+        finally:
+            backend.fuse_epilogue = True
+    assert torch.isfinite(y1).all()
+    assert torch.equal(y1, y0)
