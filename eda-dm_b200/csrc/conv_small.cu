@@ -58,7 +58,9 @@ conv3x3_small_n_kernel(const float* __restrict__ x, const float* __restrict__ w,
           v = __ldg(xb + ((size_t)c * H + iy) * W + ix);
           if (aff_a) {
             v = fmaf(v, __ldg(aff_a + (size_t)b * C + c), __ldg(aff_s + (size_t)b * C + c));
-            if (silu) v = v / (1.0f + __expf(-v));
+            if (silu & 16) v = __fdividef(v, 1.0f + __expf(-v));
+            else if (silu == 2) v = v * (1.0f / (1.0f + expf(-v)));
+            else if (silu) v = v / (1.0f + expf(-v));
           }
         }
       }

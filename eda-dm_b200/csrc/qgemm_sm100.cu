@@ -675,14 +675,21 @@ extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_ac
                               const float* delta_w, const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum,
                               const float* bias, const float* bias_img, const float* residual, float* out, int out_hw,
                               int accumulate, int silu, void* stream) {
-  static const bool force_v1 = getenv("EDADM_GEMM_V1") != nullptr;
+  const bool force_v1 = getenv("EDADM_GEMM_V1") != nullptr;
   if (!force_v1 && !silu && q && wq && delta_a && zp_a && delta_w && wsum_eff && out && (!cw || rowsum) && B >= 1 && Hp >= R && Wp >= S &&
       R >= 1 && S >= 1 && N >= 1 && !(Cp_act & 15) && !(Cp_w & 15) && Cp_w >= 16 && a_c_offset >= 0 && a_c_offset + 16 <= Cp_act + 15 &&
       !(((uintptr_t)q) & 15) && !(((uintptr_t)wq) & 15) && out_hw >= 1 && !(bias_img && out_hw == 1)) {
     Gemm2Args a{q, B, Hp, Wp, Cp_act, a_c_offset, wq, N, Np, R, S, Cp_w, delta_a, zp_a, delta_w, wsum_eff, cw, rowsum, bias, bias_img, residual,
                 out, out_hw, accumulate, /*out_mode (decided from out_hw)*/ 0, nullptr, nullptr, 0, nullptr, 0};
-    const int rc = launch_qgemm2(a, stream);
-    if (rc <= 0) return rc;
+    // Which generation (profiles/gemm_shapes_r02_*.txt): the second one wins where operand traffic or the residual read
+    // dominates (>= 8 K steps per tile, or an NCHW residual / accumulate operand); short-K layers are bound by the fp32 output
+    // write, where the first generation's eight independently storing epilogue warps keep more bytes in flight.
+    const int k_steps = R * S * ((Cp_w + 127) / 128);
+    const bool force_v2 = getenv("EDADM_GEMM_V2") != nullptr;
+    if (force_v2 || (out_hw > 1 && (k_steps >= 8 || residual || accumulate))) {
+      const int rc = launch_qgemm2(a, stream);
+      if (rc <= 0) return rc;
+    }
   }
   return launch_qgemm(q, B, Hp, Wp, Cp_act, a_c_offset, wq, 0, nullptr, N, Np, R, S, Cp_w, delta_a, zp_a, delta_w, wsum_eff, cw,
                       rowsum, bias, bias_img, residual, out, out_hw, accumulate, silu, stream);

@@ -416,7 +416,7 @@ def norm_act_quant_nhwc(x, aff_a, aff_s, silu, aq: ActQuant, pad: int, want_chsu
     d0, z0 = _qparam(aq.delta0, dev), _qparam(aq.zp0, dev)
     d1 = _qparam(aq.delta1, dev) if aq.split else None
     z1 = _qparam(aq.zp1, dev) if aq.split else None
-    lib.norm_act_quant_nhwc(x.data_ptr(), aff_a.data_ptr(), aff_s.data_ptr(), 1 if silu else 0, q.data_ptr(), _ptr(chsum), B, C, H, W,
+    lib.norm_act_quant_nhwc(x.data_ptr(), aff_a.data_ptr(), aff_s.data_ptr(), int(silu), q.data_ptr(), _ptr(chsum), B, C, H, W,
                             Cp, pad, d0.data_ptr(), z0.data_ptr(), aq.levels0, aq.split, _ptr(d1), _ptr(z1), aq.levels1, _stream())
     return q, chsum
 
@@ -446,7 +446,7 @@ def norm_act_pool2(x, aff_a, aff_s, silu):
     x = _f32c(x)
     B, C, H, W = x.shape
     out = torch.empty((B, C, H // 2, W // 2), dtype=torch.float32, device=x.device)
-    lib.norm_act_pool2(x.data_ptr(), aff_a.data_ptr(), aff_s.data_ptr(), 1 if silu else 0, out.data_ptr(), B, C, H, W, _stream())
+    lib.norm_act_pool2(x.data_ptr(), aff_a.data_ptr(), aff_s.data_ptr(), int(silu), out.data_ptr(), B, C, H, W, _stream())
     return out
 
 
@@ -557,12 +557,12 @@ def qgemm_i8(q, pw: PackedWeight, delta_a, zp_a, out, out_hw, bias=None, rowsum=
         cp_w = pw.Cp if filter_rs is None else pw.wq.shape[1] * pw.Cp // (R * S)
         lib.qgemm_w4a8(q.data_ptr(), B, Hp, Wp, Cp_act, int(a_c_offset), pw.wq.data_ptr(), pw.zoff.data_ptr(), pw.N, pw.Np,
                        R, S, cp_w, da.data_ptr(), za.data_ptr(), pw.delta_w.data_ptr(), pw.wsum_eff.data_ptr(), _ptr(bias),
-                       _ptr(bias_img), _ptr(residual), out.data_ptr(), int(out_hw), 1 if accumulate else 0, 1 if silu else 0, _stream())
+                       _ptr(bias_img), _ptr(residual), out.data_ptr(), int(out_hw), 1 if accumulate else 0, int(silu), _stream())
     else:
         lib.qgemm_i8(q.data_ptr(), B, Hp, Wp, Cp_act, int(a_c_offset), pw.wq.data_ptr(), pw.N, pw.Np, R, S,
                      pw.wq.shape[2] if filter_rs is None else pw.wq.shape[1] * pw.wq.shape[2] // (R * S),
                      da.data_ptr(), za.data_ptr(), pw.delta_w.data_ptr(), pw.wsum_eff.data_ptr(), _ptr(cw), _ptr(rowsum),
-                     _ptr(bias), _ptr(bias_img), _ptr(residual), out.data_ptr(), int(out_hw), 1 if accumulate else 0, 1 if silu else 0, _stream())
+                     _ptr(bias), _ptr(bias_img), _ptr(residual), out.data_ptr(), int(out_hw), 1 if accumulate else 0, int(silu), _stream())
     if prof is not None:
         ev1.record()
         m = B * (Hp - R + 1) * (Wp - S + 1)
@@ -623,7 +623,7 @@ def conv3x3_small_n(x, weight, bias=None, affine=None):
     N = weight.shape[0]
     out = torch.empty((B, N, H, W), dtype=torch.float32, device=x.device)
     b = None if bias is None else _f32c(bias.detach())
-    a_, s_, silu = (affine[0], affine[1], 1 if affine[2] else 0) if affine is not None else (None, None, 0)
+    a_, s_, silu = (affine[0], affine[1], int(affine[2])) if affine is not None else (None, None, 0)
     lib.conv3x3_small_n(x.data_ptr(), weight.data_ptr(), _ptr(b), _ptr(a_), _ptr(s_), silu, out.data_ptr(), B, C, H, W, N, _stream())
     return out
 

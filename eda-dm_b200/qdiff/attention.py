@@ -26,7 +26,7 @@ _MAX_KEYS, _MAX_BH = 4096, 65535
 
 
 def _fusable(tensors, quantizers, n_keys=0, bh=0):
-    if not backend.integer_path or n_keys > _MAX_KEYS or bh > _MAX_BH:
+    if not (backend.integer_path and backend.fused_attention) or n_keys > _MAX_KEYS or bh > _MAX_BH:
         return False
     if any(q.n_levels > 256 for q in quantizers):
         return False

@@ -30,6 +30,9 @@ class _Backend:
     allow_tf32 = False       # library conv/matmul of the calibration path in strict fp32
     integer_path = True      # use the tcgen05 int8 GEMM whenever it applies
     fuse_norm = True         # GroupNorm + SiLU + activation quantizer as one producer pass on the integer path
+    fast_silu = False        # True: SiLU in the fused GroupNorm producer through the SFU ex2 / rcp approximations (~3 ulp, a few 1e-4 of
+                             # the codes move by one step); False: ATen's exact forms, codes equal the module-by-module CUDA path
+    fused_attention = True   # quantized attention as one tcgen05 kernel (edadm_qattn_fwd); False: fake-quant kernels around library bmm
     fuse_epilogue = True     # linears whose only consumer is the next activation quantizer emit its u8 codes from the GEMM epilogue
     # (4-bit weight storage with in-smem unpack: `edadm.ops.w4_storage`)
     recon_cuda_graph = True  # capture the reconstruction iteration in one CUDA graph after 3 eager iterations
@@ -37,6 +40,7 @@ class _Backend:
                               # 16x16 ResBlock, -23 % on an ImageNet 32x32 one (measured), hence opt-in
     qdrop_inkernel_rng = False  # False: QDrop masks come from torch.rand_like (the reference's stream, graph-safe);
                                 # True: drawn inside the kernel (Philox4x32, no extra memory pass)
+    code_tap = None          # test hook: callable(module, codes, pad) that sees the u8 activation codes the integer path consumes
     qdrop_seed = None        # None -> torch.initial_seed()
     qdrop_offset = 0         # running Philox offset (one fresh sub-stream per fake-quant call)
 
@@ -453,7 +457,7 @@ class QuantModule(nn.Module):
                     # statistics by edadm_gn_fold, normalisation + SiLU applied while the stencil kernel loads its patches
                     a, s = ops.gn_fold(x, norm.weight, norm.bias, norm.num_groups, norm.eps)
                     self.last_path = 'fake' if self.use_weight_quant else 'fp'
-                    return ops.conv3x3_small_n(x, weight, bias, affine=(a, s, silu))
+                    return ops.conv3x3_small_n(x, weight, bias, affine=(a, s, _silu_mode(silu, act_fn)))
             h = norm(x)
             if scale is not None:
                 h = h * (1 + scale) + shift
@@ -464,6 +468,7 @@ class QuantModule(nn.Module):
             out = self(h, split=split, residual=residual, bias_img=bias_img)
             return out.flatten(2).permute(0, 2, 1) if tokens_out else out
         self.last_path = 'int8'
+        silu = _silu_mode(silu, act_fn)
         if isinstance(norm, nn.LayerNorm):
             assert scale is None and not silu
             if emit is not None:        # (codes, rowsum) of the consumer quantizer; the caller checked emit_ok()
@@ -581,6 +586,8 @@ class QuantModule(nn.Module):
             _, H, W = rows
             B = input.shape[0]
             q, rowsum = ops.act_quant_rows(input.reshape(-1, input.shape[-1]), aq, want_rowsum=needs_rowsum)
+            if backend.code_tap is not None:
+                backend.code_tap(self, q, 0)
             out = torch.empty((B, N, H, W), dtype=torch.float32, device=input.device)
             if residual is not None:
                 residual = residual.contiguous()
@@ -597,6 +604,8 @@ class QuantModule(nn.Module):
                     q, rowsum = ops.layernorm_quant_rows(input, rows[1].weight, rows[1].bias, rows[1].eps, aq, want_rowsum=needs_rowsum)
                 else:   # 'geglu'
                     q, rowsum = ops.geglu_quant_rows(input, aq, want_rowsum=needs_rowsum)
+            if backend.code_tap is not None:
+                backend.code_tap(self, q, 0)
             if emit is not None:
                 # the only consumer of this linear is the activation quantizer `emit[1]`: its codes come straight from the epilogue
                 kind, cons, want_rs = emit
@@ -628,6 +637,8 @@ class QuantModule(nn.Module):
         else:
             q, chsum = ops.act_quant_nhwc(x4, aq, pad, want_chsum=needs_rowsum, cp=cp_act)
         rowsum = ops.conv_rowsum(chsum, Ho, Wo, R, S, stride) if needs_rowsum else None
+        if backend.code_tap is not None:
+            backend.code_tap(self, q, pad)
         if tokens_out and R == 1 and S == 1 and stride == 1 and pad == 0 and residual is None and not self.split:
             out = torch.empty((B, Ho * Wo, N), dtype=torch.float32, device=input.device)     # row-major [B*T][N] == tokens
             self._gemm_chain(q.reshape(-1, q.shape[-1]), packs, aqs, out, 1, bias, rowsum, None)
@@ -696,6 +707,15 @@ class QuantModule(nn.Module):
         self.last_path = 'fake' if (self.use_weight_quant or self.use_act_quant) else 'fp'
         out = self.activation_function(_library_fwd(self.fwd_func, input, weight, bias, self.fwd_kwargs))
         return out if residual is None else out + residual
+
+
+def _silu_mode(silu, act_fn) -> int:
+    """activation code of the fused producers (csrc/pack.cu norm_act): 0 none, 1 `F.silu` / `nn.SiLU` (x / (1 + exp(-x))),
+    2 `x * sigmoid(x)` (the DDIM UNet's nonlinearity), +16 SFU approximations"""
+    if not silu:
+        return 0
+    mode = 2 if getattr(act_fn, '__name__', '') in ('nonlinearity', '_swish') else 1
+    return mode + (16 if backend.fast_silu else 0)
 
 
 def _swish(x):
