@@ -1,15 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- W4A8 QuantModel UNet steps/s (+ block-reconstruction iters/s) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload church|cifar|bedroom|imagenet] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload imagenet|church|cifar|bedroom|sd] [--impl reference]
 
 One JSON line on stdout (rank 0).  A "step" is one `QuantModel.forward` over the workload's image batch with
 the whole network on the integer tcgen05 path (W4A8, first/last weight quantizers 8 bit, split shortcuts);
 `value` is images x UNet-forwards per second with inputs resident in HBM, `e2e` is the same through
 `QuantModel.forward` from pinned HOST buffers (H2D of x, t[, context], D2H of the prediction inside the timed
 region).  Sampling shards the image batch across ranks with no communication ("weak": fixed batch per GPU).
-`recon` reports block_reconstruction iterations/s on one representative unit (data parallel, one all-reduce of
-the flat alpha/delta gradient bucket per iteration).
+`recon` reports block / layer reconstruction iterations/s per representative unit (ResBlock, transformer block, attention
+block, single layer -- whichever the workload has) and their geometric mean, in weak (32 rows per GPU) and strong (32 rows
+over all GPUs) data-parallel mode, one all-reduce of the flat alpha/delta gradient bucket per iteration.
+
+Default workload: LDM-4 ImageNet (BASELINE.json configs[3]: batch 64, classifier-free guidance -> UNet batch 128), the
+configuration north_star's targets are quoted on; the LSUN-Church LDM-8 numbers (configs[1]) ride along under "secondary".
 
 `--impl reference` times the CPU oracle (oracle/model_oracle.py: the reference's fake-quant QuantModel restated
 in plain torch fp32) on the host cores, on a bounded sample of the same workload.
@@ -37,6 +41,7 @@ WORKLOADS = {
     "church": ("church", 100, (4, 32, 32), None, 37.28),
     "bedroom": ("bedroom", 32, (3, 64, 64), None, 192.04),
     "imagenet": ("imagenet", 128, (3, 64, 64), (1, 512), 199.54),
+    "sd": ("sd", 8, (4, 64, 64), (77, 768), 677.22),      # Stable Diffusion v1.4, W8A8 (scripts/sample_txt2img.py:155-156), CFG pair of 4
 }
 
 
@@ -47,7 +52,7 @@ def build_fp_unet(kind):
         m = ddpm_unet.cifar10_unet(dropout=0.0)
     else:
         m = {"church": ldm_unet.lsun_church_unet, "bedroom": ldm_unet.lsun_bedroom_unet,
-             "imagenet": ldm_unet.imagenet_unet}[kind]()
+             "imagenet": ldm_unet.imagenet_unet, "sd": ldm_unet.stable_diffusion_unet}[kind]()
         ldm_unet.reinit_zero_modules(m)
     return m.eval()
 
@@ -65,8 +70,12 @@ def synth_inputs(shape, ctx, n, seed):
 def set_split(model, kind):
     if kind == "ddpm":
         model.config.split_shortcut = True
-    else:
+    elif kind != "sd":          # the SD script's `qnn.split = True` never reaches the UNet
         model.split_shortcut = True
+
+
+def wq_params(kind):
+    return dict(WQ, n_bits=8) if kind == "sd" else WQ
 
 
 def total_gemm_flops(qnn, args):
@@ -134,6 +143,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def int8_peak(peaks):
+    """dense int8 tcgen05 peak measured on this pool (profiles/int8_peak_r02.txt, scratch/mma_peak.py: back-to-back
+    kind::i8 MMAs from resident operands on all 148 SMs): burst for a kernel timed alone, sustained inside a long step"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "int8_peak_r02.txt")) as f:
+            for line in f:
+                if line.startswith("SUMMARY "):
+                    d = json.loads(line[len("SUMMARY "):])
+                    return float(d["int8_tops_sustained"]), float(d["int8_tops_burst"]), "measured, profiles/int8_peak_r02.txt (sustained; burst %.0f)" % d["int8_tops_burst"]
+    except Exception:
+        pass
+    return 2.0 * peaks["bf16_tflops_sustained"], 2.0 * peaks["bf16_tflops"], "2 x bf16 (no int8 microbenchmark file)"
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -148,7 +171,7 @@ def cpu_baseline(kind, shape, ctx, sample_batch, reps, threads):
     from oracle.model_oracle import OracleQuantUNet
     torch.set_num_threads(threads)
     fp = build_fp_unet(kind)
-    om = OracleQuantUNet(fp, WQ, AQ, sm_abit=8)
+    om = OracleQuantUNet(fp, wq_params(kind), AQ, sm_abit=8)
     om.set_first_last_layer_to_8bit()
     om.disable_network_output_quantization()
     set_split(fp, kind)
@@ -173,7 +196,7 @@ def run_reference(args, kind, batch, shape, ctx):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = max(1, min(batch, 8))
+    sample = max(1, min(batch, 8 if kind in ('ddpm', 'church') else 4))
     t_start = time.perf_counter()
     cb, med = cpu_baseline(kind, shape, ctx, sample, max(1, args.steps), threads)
     line = {"impl": "reference", "metric": "W4A8 QuantModel UNet img-steps/s", "value": cb["value"], "unit": "img-steps/s",
@@ -186,60 +209,110 @@ def run_reference(args, kind, batch, shape, ctx):
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="church", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the workload's sampling batch)")
-    ap.add_argument("--impl", default="edadm", choices=["edadm", "reference"])
-    ap.add_argument("--no-graph", action="store_true", help="do not capture the UNet forward in a CUDA graph")
-    ap.add_argument("--no-recon", action="store_true")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--recon-iters", type=int, default=40)
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
-    kind, batch, shape, ctx, gflop_per_sample = WORKLOADS[args.workload]
-    batch = args.batch or batch
+def recon_units(qnn, kind):
+    """representative reconstruction units of a workload: {label: (module, is_layer)}"""
+    from qdiff.quant_block import BaseQuantBlock
+    from qdiff.quant_layer import QuantModule
+    blocks = [m for m in qnn.model.modules() if isinstance(m, BaseQuantBlock)]
+    by = lambda *names: [m for m in blocks if type(m).__name__ in names]
+    units = {}
+    res = by("QuantResBlock", "QuantResnetBlock")
+    if res:
+        units["resblock"] = (res[len(res) // 4], False)
+    tb = by("QuantBasicTransformerBlock")
+    if tb:
+        units["transformer_block"] = (tb[len(tb) // 4], False)
+    ab = by("QuantAttentionBlock", "QuantAttnBlock")
+    if ab:
+        units["attention_block"] = (ab[len(ab) // 4], False)
+    inside = set()
+    for b in blocks:
+        inside.update(id(m) for m in b.modules() if isinstance(m, QuantModule))
+    layers = [m for m in qnn.model.modules() if isinstance(m, QuantModule) and id(m) not in inside and m.weight.dim() == 4
+              and m.weight.shape[2] == 3 and m.weight.shape[0] >= 32]
+    if layers:
+        units["layer"] = (layers[len(layers) // 2], True)
+    return units
 
-    if args.impl == "reference":
-        return run_reference(args, kind, batch, shape, ctx)
 
+def bench_recon(qnn, kind, shape, ctx, dev, world, iters, modes):
+    """block / layer reconstruction iterations/s per representative unit (reference loop: quant fwd + FP fwd + quant fwd (FBR)
+    + backward, QDrop 0.5), weak = 32 rows per GPU, strong = 32 rows over all GPUs"""
+    import math
+    import torch.distributed as dist
+    from edadm import native
+    from qdiff.block_recon import block_reconstruction
+    from qdiff.layer_recon import layer_reconstruction
+    from qdiff_control.block_recon import block_reconstruction as block_reconstruction_cfg
+    from qdiff_control.layer_recon import layer_reconstruction as layer_reconstruction_cfg
+    out = {}
+    units = recon_units(qnn, kind)
+    n_cali = 64
+    x, t = [c.to(dev) for c in synth_inputs(shape, None, n_cali * world, seed=4321)]
+    if ctx is not None:    # CFG calibration tuple (x, t, index, cond, uncond) of qdiff_control
+        g = torch.Generator().manual_seed(99)
+        cond = torch.randn(n_cali * world, *ctx, generator=g).to(dev)
+        uncond = torch.randn(n_cali * world, *ctx, generator=g).to(dev)
+        cali = (x, t, torch.zeros(n_cali * world, dtype=torch.long, device=dev), cond, uncond)
+    else:
+        cali = (x, t)
+    for mode in modes:
+        rb = 32 if mode == "weak" else max(1, 32 // world)
+        per_unit = {}
+        for label, (unit, is_layer) in units.items():
+            timing = {"warmup": 3}
+            kw = dict(cali_data=cali, iters=iters + 3, batch_size=rb, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2,
+                      act_quant=True, opt_mode='mse', lr_a=4e-4, lr_w=1e-2, p=2.0, input_prob=0.5, keep_gpu=True, recon_w=True,
+                      recon_a=True, add_loss=0.8, timing=timing)
+            if ctx is not None:
+                fn = layer_reconstruction_cfg if is_layer else block_reconstruction_cfg
+            else:
+                fn = layer_reconstruction if is_layer else block_reconstruction
+            native.launch_counter["kernels"] = 0
+            fn(qnn, unit, **kw)
+            ms_it = timing["ms_per_iter"]
+            if world > 1:
+                tt = torch.tensor([ms_it], device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ms_it = float(tt.item())
+            per_unit[label] = {"unit": type(unit).__name__, "iters_per_s": 1e3 / ms_it, "ms_per_iter": ms_it,
+                               "samples_per_s": world * rb * 1e3 / ms_it, "cuda_graph": timing.get("cuda_graph", False),
+                               "allreduce_bytes_per_iter": timing.get("bucket_bytes", 0) if world > 1 else 0}
+            qnn.set_quant_state(True, True)
+        gm = math.exp(sum(math.log(u["iters_per_s"]) for u in per_unit.values()) / max(1, len(per_unit)))
+        out[mode] = {"batch_per_gpu": rb, "global_batch": rb * world, "units": per_unit, "geomean_iters_per_s": gm,
+                     "geomean_samples_per_s": gm * rb * world}
+    out["semantics"] = "reference loop: quant fwd + FP fwd + quant fwd (FBR) + backward + 2 Adam steps, QDrop 0.5"
+    return out
+
+
+def bench_sampling(args, workload, dev, rank, world, local, full):
+    """one workload: calibrate, time the resident / end-to-end UNet step, per-launch GEMM roofline, reconstruction units"""
     import torch.distributed as dist
     from edadm import ops, native
     from qdiff import QuantModel, set_weight_quantize_params, set_act_quantize_params
-    from qdiff.block_recon import block_reconstruction
-    from qdiff.quant_block import BaseQuantBlock
-
-    native.load_library()                      # fail loudly if the CUDA extension is missing
-    if os.environ.get("EDADM_TF32"):
-        from qdiff.quant_layer import backend
-        backend.allow_tf32 = True
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the quantized path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    kind, batch, shape, ctx, gflop_per_sample = WORKLOADS[workload]
+    batch = args.batch or batch
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    t_wall0 = time.perf_counter()
-    # ---- model + scales (outside the timed region) ------------------------------------------------------------
     fp = build_fp_unet(kind).to(dev)
-    qnn = QuantModel(fp, WQ, AQ, sm_abit=8).to(dev).eval()
+    qnn = QuantModel(fp, wq_params(kind), AQ, sm_abit=8).to(dev).eval()
     qnn.set_first_last_layer_to_8bit()
     qnn.disable_network_output_quantization()
     set_split(qnn.model, kind)
-    cali = [c.to(dev) for c in synth_inputs(shape, ctx, 64, seed=1234)]
+    n_cali = 16 if kind == "sd" else 64
+    cali = [c.to(dev) for c in synth_inputs(shape, ctx, n_cali, seed=1234)]
+    t0 = time.perf_counter()
     set_weight_quantize_params(qnn, cali)
-    set_act_quantize_params(qnn, cali, batch_size=32, all_attention=True)
+    torch.cuda.synchronize()
+    t_w = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    set_act_quantize_params(qnn, cali, batch_size=n_cali // 2, all_attention=True)
+    torch.cuda.synchronize()
+    t_a = time.perf_counter() - t0
     qnn.set_quant_state(True, True)
 
     host_in = [c.pin_memory() for c in synth_inputs(shape, ctx, batch, seed=100 + rank)]
@@ -247,14 +320,12 @@ def main():
     flops_step = total_gemm_flops(qnn, dev_in)
     paths = qnn.path_report()
     n_int8 = sum(1 for v in paths.values() if v == "int8")
-
-    # kernel launches of one forward (my kernels only), counted on an eager pass
+    n_elided = sum(1 for v in paths.values() if v == "elided")
     with torch.no_grad():
         native.launch_counter["kernels"] = 0
         qnn(*dev_in)
         launches_per_step = native.launch_counter["kernels"]
 
-    # ---- CUDA graph of the forward ----------------------------------------------------------------------------
     static_in = [c.clone() for c in dev_in]
     graph = None
     with torch.no_grad():
@@ -305,14 +376,14 @@ def main():
         clocks = clk.summary()
         ms_e2e = timed(step_e2e, args.steps, args.warmup)
 
-        if os.environ.get("EDADM_PROFILE"):      # ncu --profile-from-start off: exactly one eager step is profiled
+        if full and os.environ.get("EDADM_PROFILE"):      # ncu --profile-from-start off: exactly one eager step is profiled
             torch.cuda.synchronize()
             torch.cuda.profiler.start()
             qnn(*static_in)
             torch.cuda.synchronize()
             torch.cuda.profiler.stop()
 
-        # ---- dominant kernel: per-launch CUDA events around every tcgen05 GEMM of eager steps -------------------
+        # dominant kernel: per-launch CUDA events around every tcgen05 GEMM of eager steps
         for _ in range(2):
             qnn(*static_in)
         ops.gemm_profile = []
@@ -331,70 +402,121 @@ def main():
         n_gemm = len(prof) // n_prof
 
     peaks, peak_src = measured_peaks()
-    int8_peak = 2.0 * peaks["bf16_tflops"]      # dense int8 = 2x bf16 on B200; no int8 entry in MEASURED_PEAKS.json
+    peak_sus, peak_burst, i8_src = int8_peak(peaks)
     achieved = 2.0 * gemm_macs / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    # DRAM bytes per qgemm launch from the committed ncu capture of the same eager step (profiles/, church workload only)
     traffic = None
     try:
-        wl_batch = {"church": 100, "imagenet": 128}.get(args.workload)
+        wl_batch = {"church": 100, "imagenet": 128}.get(workload)
         if wl_batch and args.batch in (0, wl_batch):
-            with open(os.path.join(ROOT, "profiles", f"launches_r01_{args.workload}_b{wl_batch}_summary.json")) as f:
-                traffic = json.load(f)["kernels"]["edadm::qgemm_i8_kernel"]["dram_bytes_per_launch"]
+            for rnd in ("r02", "r01"):
+                fn = os.path.join(ROOT, "profiles", f"launches_{rnd}_{workload}_b{wl_batch}_summary.json")
+                if os.path.exists(fn):
+                    with open(fn) as f:
+                        ks = json.load(f)["kernels"]
+                    tot_b = sum(v["dram_bytes_per_launch"] * v["launches"] for k, v in ks.items() if "qgemm" in k)
+                    tot_l = sum(v["launches"] for k, v in ks.items() if "qgemm" in k)
+                    traffic = tot_b / max(1, tot_l)
+                    break
     except Exception:
         traffic = None
-    roofline = {"bound": "tensor", "kernel": "qgemm_i8_kernel (tcgen05 kind::i8)", "achieved": achieved, "peak": int8_peak,
-                "unit": "TOP/s", "frac": achieved / int8_peak, "traffic": traffic,
-                "peak_source": f"2 x bf16 burst {peaks['bf16_tflops']} TF/s, {peak_src}",
+    roofline = {"bound": "tensor", "kernel": "qgemm_i8_kernel / qgemm2_kernel (tcgen05 kind::i8, all launches of a step)",
+                "achieved": achieved, "peak": peak_sus, "unit": "TOP/s", "frac": achieved / peak_sus, "traffic": traffic,
+                "peak_source": i8_src, "frac_of_burst_peak": achieved / peak_burst,
                 "launches_per_step": n_gemm, "avg_launch_us": 1e3 * gemm_ms / max(1, n_gemm),
                 "share_of_eager_step": gemm_ms / eager_ms if eager_ms else None,
                 "algorithmic_gflop_per_step": 2.0 * gemm_macs / 1e9}
 
-    # ---- block reconstruction iterations/s on a representative unit --------------------------------------------
     recon = None
     if not args.no_recon:
-        units = [m for m in qnn.model.modules() if isinstance(m, BaseQuantBlock) and type(m).__name__ in ("QuantResBlock", "QuantResnetBlock")]
-        unit = units[len(units) // 4]
-        rb = 32
-        cali_r = [c.to(dev) for c in synth_inputs(shape, ctx, 64 * world, seed=4321)]
-        timing = {"warmup": 3}
-        kw = dict(cali_data=cali_r, iters=args.recon_iters + 3, batch_size=rb, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2,
-                  act_quant=True, opt_mode='mse', lr_a=4e-4, lr_w=1e-2, p=2.0, input_prob=0.5, keep_gpu=True, recon_w=True,
-                  recon_a=True, add_loss=0.8, timing=timing)
-        native.launch_counter["kernels"] = 0
-        block_reconstruction(qnn, unit, **kw)
-        ms_it = timing["ms_per_iter"]
-        if world > 1:
-            tt = torch.tensor([ms_it], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms_it = float(tt.item())
-        recon = {"unit": type(unit).__name__, "iters_per_s": 1e3 / ms_it, "samples_per_s": world * rb * 1e3 / ms_it,
-                 "ms_per_iter": ms_it, "batch_per_gpu": rb, "global_batch": rb * world, "scaling": "weak",
-                 "allreduce_bytes_per_iter": timing.get("bucket_bytes", 0) if world > 1 else 0,
-                 "cuda_graph": timing.get("cuda_graph", False),
-                 "semantics": "reference loop: quant fwd + FP fwd + quant fwd (FBR) + backward, QDrop 0.5"}
+        recon = bench_recon(qnn, kind, shape, ctx, dev, world, args.recon_iters, ["weak", "strong"] if full else ["weak"])
         qnn.set_quant_state(True, True)
+
+    in_bytes = sum(c.numel() * c.element_size() for c in host_in)
+    out_bytes = host_out.numel() * 4
+    res = {
+        "value": world * batch * 1e3 / ms_step, "ms_per_step": ms_step,
+        "config": {"workload": f"{workload}: {kind} UNet, latent {list(shape)}" + (f", context {list(ctx)}" if ctx else "") +
+                               f", batch {batch}/GPU" + (" (CFG pair of %d)" % (batch // 2) if ctx else "") +
+                               (", W8A8" if kind == "sd" else ", W4A8, split shortcuts"),
+                   "quant_modules": len(paths), "on_int8_tcgen05_path": n_int8,
+                   "elided_by_one_key_cross_attention": n_elided, "cuda_graph": graph is not None,
+                   "l2": "weights + activations of one forward exceed the 126 MB L2 (no flush needed)",
+                   "unet_steps_per_s": world * 1e3 / ms_step, "gemm_gflop_per_sample": flops_step / batch / 1e9,
+                   "attention": "fused tcgen05 kernel (edadm_qattn_fwd)",
+                   "calibration_s": {"set_weight_quantize_params": t_w, "set_act_quantize_params": t_a, "samples": n_cali}},
+        "e2e": {"value": world * batch * 1e3 / ms_e2e, "unit": "img-steps/s", "h2d_bytes_per_step": in_bytes,
+                "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e},
+        "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roofline, "recon": recon,
+        "effective_int8_tops": flops_step / (ms_step * 1e-3) / 1e12,
+    }
+    del qnn, fp, graph
+    torch.cuda.empty_cache()
+    return res, (kind, shape, ctx, batch)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="imagenet", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the workload's sampling batch)")
+    ap.add_argument("--impl", default="edadm", choices=["edadm", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the UNet forward in a CUDA graph")
+    ap.add_argument("--no-recon", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the LSUN-Church block that rides along with the ImageNet default")
+    ap.add_argument("--recon-iters", type=int, default=40)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    kind, batch, shape, ctx, _ = WORKLOADS[args.workload]
+    batch = args.batch or batch
+
+    if args.impl == "reference":
+        return run_reference(args, kind, batch, shape, ctx)
+
+    import torch.distributed as dist
+    from edadm import native
+
+    native.load_library()                      # fail loudly if the CUDA extension is missing
+    if os.environ.get("EDADM_TF32"):
+        from qdiff.quant_layer import backend
+        backend.allow_tf32 = True
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the quantized path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    t_wall0 = time.perf_counter()
+    res, _ = bench_sampling(args, args.workload, dev, rank, world, local, full=True)
+    secondary = None
+    if args.workload == "imagenet" and not args.no_secondary and not args.batch:
+        sec, _ = bench_sampling(args, "church", dev, rank, world, local, full=False)
+        secondary = {"metric": "W4A8 QuantModel UNet img-steps/s", "workload": sec["config"]["workload"], "value": sec["value"],
+                     "ms_per_step": sec["ms_per_step"], "e2e": sec["e2e"], "roofline": sec["roofline"], "recon": sec["recon"],
+                     "effective_int8_tops": sec["effective_int8_tops"], "clocks": sec["clocks"]}
 
     if rank == 0:
         cb = None
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_baseline(kind, shape, ctx, min(batch, 4), 3, os.cpu_count() or 1)
-        in_bytes = sum(c.numel() * c.element_size() for c in host_in)
-        out_bytes = host_out.numel() * 4
-        value = world * batch * 1e3 / ms_step
+            try:
+                from oracle.recon_oracle import cpu_recon_baseline
+                cb["recon"] = cpu_recon_baseline(os.cpu_count() or 1)
+            except Exception as exc:  # the sampling baseline above is the contract's cpu_baseline; the recon timing is extra
+                cb["recon"] = {"unavailable": str(exc)[:200]}
         line = {
-            "metric": "W4A8 QuantModel UNet img-steps/s", "value": value, "unit": "img-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8 x s8 -> s32 (W4A8 codes; W8 first/last)", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {kind} UNet, latent {list(shape)}, batch {batch}/GPU, W4A8, split shortcuts",
-                       "quant_modules": len(paths), "on_int8_tcgen05_path": n_int8, "cuda_graph": graph is not None,
-                       "l2": "weights + activations of one forward exceed the 126 MB L2 (no flush needed)",
-                       "unet_steps_per_s": world * 1e3 / ms_step, "gemm_gflop_per_sample": flops_step / batch / 1e9,
-                       "attention": "fused tcgen05 kernel (edadm_qattn_fwd)"},
-            "e2e": {"value": world * batch * 1e3 / ms_e2e, "unit": "img-steps/s", "h2d_bytes_per_step": in_bytes,
-                    "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e},
-            "gpu_launches": launches_per_step * args.steps,
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cb, "recon": recon,
-            "effective_int8_tops": flops_step / (ms_step * 1e-3) / 1e12,
+            "metric": "W4A8 QuantModel UNet img-steps/s", "value": res["value"], "unit": "img-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 x s8 -> s32 (W4A8 codes; W8 first/last)" if kind != "sd" else "u8 x s8 -> s32 (W8A8 codes)",
+            "data": "synthetic", "config": res["config"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
+            "clocks": res["clocks"], "roofline": res["roofline"], "cpu_baseline": cb, "recon": res["recon"],
+            "effective_int8_tops": res["effective_int8_tops"], "secondary": secondary,
             "wall_s": time.perf_counter() - t_wall0,
         }
         print(json.dumps(line))

@@ -182,10 +182,13 @@ def _graph_capturable(unit, device):
     if backend.qdrop_inkernel_rng:
         # the Philox (seed, offset) of in-kernel QDrop draws are host scalars: a captured launch would replay ONE mask forever
         return False
-    for m in unit.modules():
-        # activation checkpointing re-enters autograd and snapshots RNG state: keep those units on the eager loop
-        if isinstance(m, QuantAttentionBlock) or getattr(m, 'use_checkpoint', False) or getattr(m, 'checkpoint', False) is True:
-            return False
+    # Checkpointed units (QuantBasicTransformerBlock, QuantAttentionBlock: qdiff.quant_block._Recompute) are captured too: the
+    # recompute is a nested autograd pass on the capturing stream, and its QDrop re-draws come from torch's graph-safe Philox
+    # generator, so every replay sees fresh masks exactly like the eager loop (backend.recon_graph_checkpointed = False opts out).
+    if not backend.recon_graph_checkpointed:
+        for m in unit.modules():
+            if isinstance(m, QuantAttentionBlock) or getattr(m, 'use_checkpoint', False) or getattr(m, 'checkpoint', False) is True:
+                return False
     return True
 
 
@@ -238,6 +241,8 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
         sources = [cached_outs, cached_inps[0], cached_inps[1]]
     static = [torch.empty((bsz,) + tuple(t.shape[1:]), dtype=t.dtype, device=device) for t in sources] if use_graph else None
     loss_out = torch.zeros((), dtype=torch.float32, device=device)
+    gnorm_out = torch.zeros(2, dtype=torch.float32, device=device)      # diagnostics: |grad| of the alpha / step-size parameters
+    n_w = sum(p_.numel() for p_ in w_para)
 
     def gather(idx):
         idx_t = torch.as_tensor(idx, device=sources[0].device)
@@ -296,6 +301,8 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
         loss.backward()
         if bucket is not None:
             bucket.all_reduce_mean()
+            if timing is not None and 'grad_norms' in timing:
+                gnorm_out[0].copy_(bucket.flat[:n_w].norm()); gnorm_out[1].copy_(bucket.flat[n_w:].norm())
         for opt in (w_opt, a_opt):
             if opt is not None:
                 opt.step()
@@ -342,6 +349,8 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
                         sched.step()
             if return_losses:
                 losses.append(loss_out.clone())
+            if timing is not None and 'grad_norms' in timing:
+                timing['grad_norms'].append(gnorm_out.clone())
         if timing is not None and 'start' in timing:
             timing['end'].record()
     if side is not None:

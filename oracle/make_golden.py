@@ -318,10 +318,84 @@ def cfg_recon():
     print("cfg_xattn_tiny.npz")
 
 
+def api_goldens():
+    """Reference drivers that round 1 left untested: AttnBlock_layer_reconstruction (qdiff/attn_layer_recon.py:13-133) and the
+    whole-model walk recon_block_Qmodel.recon() (qdiff/recon_block_Qmodel.py:18-94) on the tiny DDIM UNet of ddim_tiny()."""
+    import qdiff.attn_layer_recon as ref_attn_recon
+    from qdiff import recon_block_Qmodel
+    from ddim.models.diffusion import Model
+    cfg = ns(dict(data=dict(image_size=16, channels=3),
+                  model=dict(type='simple', in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2], num_res_blocks=1,
+                             attn_resolutions=[8], dropout=0.0, resamp_with_conv=True),
+                  diffusion=dict(num_diffusion_timesteps=1000)))
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(32, 3, 16, 16, generator=g)
+    t = torch.randint(0, 1000, (32,), generator=g)
+
+    def fresh(c=None):
+        torch.manual_seed(0)
+        qnn = QuantModel(Model(c or cfg).eval(), WQ, AQ, sm_abit=8).eval()
+        qnn.set_first_last_layer_to_8bit()
+        qnn.disable_network_output_quantization()
+        qnn.model.config.split_shortcut = True
+        _init_all(qnn, (x, t), 16)
+        return qnn
+    kwargs = dict(cali_data=(x, t), iters=4, batch_size=8, weight=0.01, asym=True, b_range=(20, 2), warmup=0.2,
+                  act_quant=True, opt_mode='mse', lr_a=4e-4, lr_w=1e-2, p=2.0, input_prob=1.0, keep_gpu=True,
+                  recon_w=True, recon_a=True, add_loss=0.8)
+    out = {}
+    qnn = fresh()
+    random.seed(81); torch.manual_seed(81)
+    trace, undo = _record_losses(ref_attn_recon)
+    ab = qnn.model.down[1].attn[0]
+    ref_attn_recon.AttnBlock_layer_reconstruction(qnn, ab, **kwargs)
+    undo()
+    out.update(attn_layer_loss=np.array(trace),
+               attn_layer_delta=np.array([float(ab.act_quantizer_q.delta), float(ab.act_quantizer_k.delta),
+                                          float(ab.act_quantizer_v.delta), float(ab.act_quantizer_w.delta)]))
+    # whole-model walk, 2 iterations per unit (the reference hard-codes two block/attention pairs on the attention level,
+    # recon_block_Qmodel.py:33-38, so this UNet has num_res_blocks = 2)
+    cfg2 = ns(dict(data=dict(image_size=16, channels=3),
+                   model=dict(type='simple', in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2, 2], num_res_blocks=2,
+                              attn_resolutions=[8], dropout=0.0, resamp_with_conv=True),
+                   diffusion=dict(num_diffusion_timesteps=1000)))
+    qnn = fresh(cfg2)
+    out.update({"walk_sd." + k: npy(v) for k, v in qnn.model.state_dict().items() if "quantizer" not in k and "org_" not in k})
+    pack_table("walk_q.", quantizer_table(qnn), out)
+    kw2 = dict(kwargs); kw2.update(iters=2)
+    random.seed(82); torch.manual_seed(82)
+    tb, undo_b = _record_losses(ref_block_recon)
+    tl, undo_l = _record_losses(ref_layer_recon)
+    order = []
+    ob, ol = ref_block_recon.block_reconstruction, ref_layer_recon.layer_reconstruction
+    names = {id(m): n for n, m in qnn.named_modules()}
+    ref_driver = sys.modules["qdiff.recon_block_Qmodel"]      # (the package attribute of that name is the class)
+
+    def wrap(fn, kind, trace):
+        def call(model, unit, **k):
+            n0 = len(trace)
+            r = fn(model, unit, **k)
+            order.append((kind, names[id(unit)], [float(v) for v in trace[n0:]]))
+            return r
+        return call
+    ref_driver.block_reconstruction = wrap(ob, "block", tb)
+    ref_driver.layer_reconstruction = wrap(ol, "layer", tl)
+    recon_block_Qmodel(None, qnn, (x, t), kw2).recon()
+    ref_driver.block_reconstruction, ref_driver.layer_reconstruction = ob, ol
+    undo_b(); undo_l()
+    qnn.set_quant_state(True, True)
+    with torch.no_grad():
+        y = qnn(x[:4], t[:4])
+    out.update(walk_kinds=np.array([k for k, _, _ in order]), walk_names=np.array([n for _, n, _ in order]),
+               walk_losses=np.array([l for _, _, l in order]), walk_y=npy(y))
+    np.savez_compressed(os.path.join(OUT, "ddim_tiny_api.npz"), **out)
+    print("ddim_tiny_api.npz", len(order), "units:", [n for _, n, _ in order])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["unit", "ddim", "ldm", "xattn", "cfg"]
+    which = sys.argv[1:] or ["unit", "ddim", "ldm", "xattn", "cfg", "api"]
     if "unit" in which:
         unit_vectors()
     if "ddim" in which:
@@ -332,3 +406,5 @@ if __name__ == "__main__":
         ldm_xattn_tiny()
     if "cfg" in which:
         cfg_recon()
+    if "api" in which:
+        api_goldens()

@@ -266,3 +266,37 @@ def test_cfg_reconstruction_traces_qdiff_control(cuda):
          float(tb.attn2.act_quantizer_k.delta), float(tb.attn2.act_quantizer_v.delta)]
     # the softmax step size (2e-4) moves by Adam-normalised steps of up to 4e-4: compare it absolutely
     assert np.allclose(d, g["recon_tb_delta"], rtol=1e-2, atol=1e-4)
+
+
+def test_checkpointed_unit_reconstruction_graph_equals_eager(cuda):
+    """transformer-block reconstruction (activation recompute in the backward, reference util.py:119-148) captured in a CUDA graph
+    follows the eager loop's loss trajectory (no QDrop: deterministic), and the capture really happened"""
+    from qdiff_control.block_recon import block_reconstruction
+    from qdiff.quant_layer import backend
+    g = H.load("cfg_xattn_tiny.npz")
+    traces = []
+    for use_graph in (True, False):
+        qnn = _product(g, H.ldm_model("ldm_xattn_tiny.npz"), cuda, _set_split_ldm)
+        cali = tuple(T(g[k]).to(cuda) for k in ("x", "t", "index", "cond", "uncond"))
+        with torch.no_grad():
+            qnn(cali[0][:4], cali[1][:4], cali[3][:4])
+        H.install_qparams(qnn, H.qtable(g))
+        kw = dict(RECON_KW); kw.update(batch_size=4, iters=8)
+        random.seed(56); torch.manual_seed(56)
+        tb = qnn.model.input_blocks[1][1].transformer_blocks[0]
+        tb.checkpoint = True
+        timing = {"warmup": 0}
+        backend.recon_cuda_graph = use_graph
+        try:
+            losses = block_reconstruction(qnn, tb, cali_data=cali, return_losses=True, timing=timing, **kw)
+        finally:
+            backend.recon_cuda_graph = True
+        assert timing["cuda_graph"] == use_graph
+        traces.append(losses.cpu().numpy())
+    # The two loops use different Adam kernels (capturable, device-side learning rate vs the plain one): parameters differ in
+    # the last bits after the first update, and the step-size gradients of this unit (softmax / q / k quantizers sitting on
+    # rounding boundaries) are sensitive enough that the trajectories drift apart by percents within a few iterations --
+    # measured: both loops are run-to-run deterministic, |d loss| 3e-4 at iteration 1, 15 % at iteration 3.
+    assert np.allclose(traces[0][:3], traces[1][:3], rtol=2e-3), (traces[0], traces[1])
+    assert np.allclose(traces[0], traces[1], rtol=0.35), (traces[0], traces[1])
+    assert np.all(np.isfinite(traces[0]))
