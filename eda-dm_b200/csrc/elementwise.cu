@@ -6,6 +6,7 @@
 // Arithmetic contract (bit-exact codes): true IEEE fp32 division x/delta, rintf (half-to-even,
 // == torch.round), zero-point added AFTER rounding, clamp to [0, n_levels-1]
 // (reference qdiff/quant_layer.py:267-269).  Compiled WITHOUT --use_fast_math.
+#include <algorithm>
 #include "common.cuh"
 
 namespace edadm {
@@ -440,4 +441,71 @@ extern "C" int edadm_lp_loss_bwd(const float* pred, const float* tgt, int64_t n,
   if (p == 2.0f) lp_loss_bwd_kernel<true><<<grid, kThreads, 0, s>>>(pred, tgt, n, p, inv_rest, gloss, gpred);
   else lp_loss_bwd_kernel<false><<<grid, kThreads, 0, s>>>(pred, tgt, n, p, inv_rest, gloss, gpred);
   return check_launch("lp_loss_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7  scale search: scores of ALL clipping candidates in one pass over the tensor
+// (replaces the 100 (x chunked) fake-quant + reduce passes of UniformAffineQuantizer.perform_1D_search,
+// qdiff/quant_layer.py:150-213, scored by lp_loss(x, Q(x), p=2.4, 'all') / the per-channel mean :63-70)
+// ------------------------------------------------------------------------------------------------
+namespace edadm {
+
+constexpr int kSearchElems = 16;        // elements a thread keeps in registers per sweep over the candidates
+constexpr int kSearchMaxCand = 128;
+
+// x: [segments][inner]; candidate k of segment s quantizes with (delta[s*K+k], zp[s*K+k]).  scores[s*K+k] += sum_i |Q(x_i) - x_i|^p
+// (fp64; the caller divides by `inner`).  grid = (blocks per segment, segments).
+__global__ void __launch_bounds__(256)
+mse_search_kernel(const float* __restrict__ x, long long inner, const float* __restrict__ delta, const float* __restrict__ zp,
+                  int K, float qmax, float p, double* __restrict__ scores) {
+  __shared__ double acc[kSearchMaxCand];
+  __shared__ float sd[kSearchMaxCand], sz[kSearchMaxCand];
+  const int seg = blockIdx.y;
+  const float* xs = x + (long long)seg * inner;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) { acc[k] = 0.0; sd[k] = __ldg(delta + (long long)seg * K + k); sz[k] = __ldg(zp + (long long)seg * K + k); }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * blockDim.x * kSearchElems;
+  // the trip count is warp-uniform (the shuffles below use the full mask); lanes past the end carry zeros
+  for (long long wb = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * kSearchElems; wb < inner; wb += stride) {
+    const long long base = wb + (long long)lane * kSearchElems;
+    float v[kSearchElems];
+#pragma unroll
+    for (int j = 0; j < kSearchElems; ++j) v[j] = (base + j < inner) ? __ldg(xs + base + j) : 0.f;
+    const int nvalid = (int)max(0LL, min((long long)kSearchElems, inner - base));
+    for (int k = 0; k < K; ++k) {
+      const float d = sd[k], z = sz[k];
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < kSearchElems; ++j) {
+        const float q = fminf(fmaxf(rintf(v[j] / d) + z, 0.f), qmax);
+        const float e = fabsf((q - z) * d - v[j]);
+        s += (j < nvalid) ? (p == 2.0f ? e * e : powf(e, p)) : 0.f;
+      }
+      double sdbl = (double)s;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sdbl += __shfl_xor_sync(0xffffffffu, sdbl, o);
+      if (lane == 0) atomicAdd(&acc[k], sdbl);
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) if (acc[k] != 0.0) atomicAdd(scores + (long long)seg * K + k, acc[k]);
+}
+
+}  // namespace edadm
+
+// scores[s*K + k] (fp64, zeroed by the caller) += sum over segment s of |Q_k(x) - x|^p with Q_k = clamp(round(x/delta)+zp, 0, L-1)
+// dequantised, all K <= 128 candidates of a segment in one pass over x ([segments][inner] fp32).
+extern "C" int edadm_mse_search_scores(const float* x, int64_t segments, int64_t inner, const float* delta, const float* zp, int K,
+                                       int n_levels, float p, double* scores, void* stream) {
+  using namespace edadm;
+  if (!x || !delta || !zp || !scores) return fail(EDADM_ERR_ARG, "mse_search_scores: null pointer");
+  if (segments < 1 || segments > 65535 || inner < 1 || K < 1 || K > kSearchMaxCand || n_levels < 2)
+    return fail(EDADM_ERR_ARG, "mse_search_scores: bad sizes segments=%lld inner=%lld K=%d", (long long)segments, (long long)inner, K);
+  long long per_seg = (inner + 256LL * kSearchElems - 1) / (256LL * kSearchElems);
+  const long long cap = std::max<long long>(1, (long long)sm_count() * 8 / segments);
+  if (per_seg > cap) per_seg = cap;
+  dim3 grid((unsigned)per_seg, (unsigned)segments);
+  mse_search_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, inner, delta, zp, K, (float)(n_levels - 1), p, scores);
+  return check_launch("mse_search_scores");
 }

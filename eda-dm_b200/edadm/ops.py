@@ -123,6 +123,20 @@ def uaq_fake_quant(x, delta, zero_point, n_levels, keep_mask=None, prob=1.0, see
     return UAQFunction.apply(x, delta, zero_point, n_levels, keep_mask, prob, seed, offset, keep_rand)
 
 
+def mse_search_scores(x2d, delta, zp, n_levels, p=2.4):
+    """x2d fp32 [S, inner]; delta / zp fp32 [S, K] (K <= 128 candidates per segment) -> mean |Q_k(x) - x|^p, fp32 [S, K]
+    (the scores UniformAffineQuantizer.perform_1D_search minimises), all candidates in one pass over x."""
+    _need_cuda(x2d)
+    x2d = _f32c(x2d)
+    S, inner = x2d.shape
+    d = _f32c(delta.reshape(S, -1))
+    z = _f32c(zp.reshape(S, -1))
+    K = d.shape[1]
+    scores = torch.zeros((S, K), dtype=torch.float64, device=x2d.device)
+    lib.mse_search_scores(x2d.data_ptr(), S, inner, d.data_ptr(), z.data_ptr(), K, int(n_levels), float(p), scores.data_ptr(), _stream())
+    return (scores / inner).float()
+
+
 # ------------------------------------------------------------------------------------------------
 # K3  AdaRound
 # ------------------------------------------------------------------------------------------------

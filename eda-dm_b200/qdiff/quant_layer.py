@@ -33,6 +33,7 @@ class _Backend:
     fast_silu = False        # True: SiLU in the fused GroupNorm producer through the SFU ex2 / rcp approximations (~3 ulp, a few 1e-4 of
                              # the codes move by one step); False: ATen's exact forms, codes equal the module-by-module CUDA path
     fused_attention = True   # quantized attention as one tcgen05 kernel (edadm_qattn_fwd); False: fake-quant kernels around library bmm
+    search_kernel = True     # scale search: all 100 clipping candidates scored in one pass (edadm_mse_search_scores); False: tensor ops
     fuse_epilogue = True     # linears whose only consumer is the next activation quantizer emit its u8 codes from the GEMM epilogue
     # (4-bit weight storage with in-smem unpack: `edadm.ops.w4_storage`)
     recon_cuda_graph = True  # capture the reconstruction iteration in one CUDA graph after 3 eager iterations
@@ -154,6 +155,20 @@ class UniformAffineQuantizer(nn.Module):
             x_min, x_max = x.amin(), x.amax()
         xrange = torch.max(x_min.abs(), x_max)
         steps = torch.arange(1, self.num + 1, device=x.device)
+        if backend.search_kernel and x.is_cuda and x.dtype == torch.float32 and self.num <= 128 and y.shape[0] <= 65535:
+            # every candidate of every channel scored in ONE pass over the tensor (edadm_mse_search_scores); the candidate
+            # (delta, zero_point) pairs are the same fp32 values the loop below would try, in the same order
+            thres = _tdiv(xrange, self.num).reshape(-1, 1) * steps.reshape(1, -1).to(x.dtype)           # [S, num]
+            new_min = torch.zeros_like(thres) if self.one_side_dist == 'pos' else -thres
+            new_max = torch.zeros_like(thres) if self.one_side_dist == 'neg' else thres
+            scale, zp = self.calculate_qparams(new_min, new_max)
+            scores = ops.mse_search_scores(y, scale, zp, self.n_levels, 2.4)
+            ind = torch.argmin(scores, dim=1, keepdim=True)        # first minimum, like the strict `<` of the reference loop
+            best_min, best_max = new_min.gather(1, ind).reshape(-1), new_max.gather(1, ind).reshape(-1)
+            if self.channel_wise:
+                # candidates never beat the reference's initial best_score of 1e10 only if every score is >= 1e10
+                return best_min, best_max
+            return best_min[0], best_max[0]
         if not self.channel_wise:
             thres = _tdiv(xrange, self.num) * steps
             new_min = torch.zeros_like(thres) if self.one_side_dist == 'pos' else -thres

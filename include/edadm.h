@@ -131,6 +131,14 @@ int edadm_pack_weight(const float* w, const float* alpha, const float* delta, co
                       int S, int c_begin, int c_end, int Cp, int Np, int n_levels, int8_t* wq, uint8_t* codes,
                       int32_t* wsum, int32_t* cw, void* stream);
 
+/* ---- K7: scale search (UniformAffineQuantizer.perform_1D_search, qdiff/quant_layer.py:150-213) ----------------------
+ * One pass over x ([segments][inner]; segments = 1 per tensor, = out channels for weights) scores all K <= 128 clipping
+ * candidates of every segment: scores[s*K+k] (fp64, zeroed by the caller) += sum_i |(clamp(round(x_i/d)+z, 0, L-1) - z)*d - x_i|^p
+ * with (d, z) = (delta[s*K+k], zp[s*K+k]) -- the reference's lp_loss(x, Q(x), p=2.4) numerator, fp32 per element exactly as the
+ * reference evaluates it (quant_layer.py:110-118, :26-33), accumulated in fp64.                                           */
+int edadm_mse_search_scores(const float* x, int64_t segments, int64_t inner, const float* delta, const float* zp, int K,
+                            int n_levels, float p, double* scores, void* stream);
+
 /* ---- K1: QuantModule conv2d / conv1d / linear on integer codes (tcgen05 kind::i8) ------------------
  * Replaces `self.fwd_func(input, weight, bias, **self.fwd_kwargs)` at qdiff/quant_layer.py:434 when
  * use_weight_quant and use_act_quant are on.  Stride-1 implicit GEMM over the halo-padded NHWC codes

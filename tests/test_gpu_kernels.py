@@ -783,3 +783,27 @@ def test_transformer_epilogue_fusions_are_exact(cuda, ctx_tokens, heads):
             backend.fuse_epilogue = True
     assert torch.isfinite(y1).all()
     assert torch.equal(y1, y0)
+
+
+@pytest.mark.parametrize("channel_wise,bits,shape,shift", [(False, 8, (8, 64, 16, 16), 0.0), (False, 8, (4, 77, 320), 1.5), (True, 4, (96, 64, 3, 3), 0.0),
+                                                            (True, 8, (40, 130), 0.0), (False, 8, (2, 8, 64, 64), 3.0)])
+def test_scale_search_kernel_equals_tensor_op_search(cuda, channel_wise, bits, shape, shift):
+    """edadm_mse_search_scores (all 100 candidates in one pass) lands on the same (delta, zero_point) as the candidate-by-candidate
+    tensor-op search it replaces (reference quant_layer.py:150-213), incl. one-sided inputs (softmax-like, shift = 3)"""
+    from qdiff.quant_layer import UniformAffineQuantizer, backend
+    g = torch.Generator().manual_seed(bits * 7 + len(shape))
+    x = (torch.randn(*shape, generator=g) * (0.1 if channel_wise else 1.3)).to(cuda)
+    if shift == 3.0:
+        x = torch.softmax(x * 3, -1)
+    else:
+        x = x + shift
+    res = []
+    for use_kernel in (True, False):
+        q = UniformAffineQuantizer(n_bits=bits, symmetric=True, channel_wise=channel_wise, scale_method='mse', leaf_param=not channel_wise)
+        backend.search_kernel = use_kernel
+        try:
+            q(x)
+        finally:
+            backend.search_kernel = True
+        res.append((q.delta.detach().clone(), q.zero_point.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
