@@ -59,6 +59,10 @@ struct AttnParams {
   int Tq, Tk, d;
   int k_chunks, k_last_mmas, s_tiles;
   int d_chunk, heads;
+  int s_bufs;                // S accumulators in TMEM: 2 (d_chunk <= 256) or 1 (d_chunk <= 384, O takes columns [128, 512))
+  int qk_stages;             // Q / K smem ring depth (3, or 2 when the V tiles are 48 KB)
+  int v_halves;              // 1, or 2 when d_chunk > 256: V tile loaded and multiplied as two halves (TMA box / UMMA N <= 256)
+  int v_stage_bytes;
   long long o_sb, o_sh, o_st, o_sc;
   float sm_scale;
   const float *dq, *zq, *dk, *zk, *dv, *zv, *dpq, *zpq;
@@ -77,7 +81,7 @@ struct __align__(8) AttnBarriers {
 };
 
 constexpr int ATT_MAX_KEYS = 4096;               // per-key zero-point terms of a whole (batch, head) stay in shared memory
-constexpr int ATT_SMEM_BYTES = 1024 + QK_STAGES * 2 * ATT_TILE_BYTES + V_STAGES * V_TILE_BYTES + 2 * ATT_TILE_BYTES + 256 + ATT_MAX_KEYS * 4;
+constexpr int ATT_SMEM_BYTES = 220 * 1024;   // dynamic opt-in ceiling (the kernel also has 6 KB of static shared memory); each launch asks for what its tiles need
 
 // SMALL_V: |raw - zq*rk| < 2^22 (head dim <= 64), so int -> float goes through the exact magic-number add instead of I2F.
 // The softmax is bound by the 16-op/clk XU pipe (ex2, I2F, F2I); with the conversions moved to the ALU/FMA pipes only the
@@ -89,9 +93,9 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer (LDS/STS)
   uint8_t* smem_q = smem;
-  uint8_t* smem_k = smem_q + QK_STAGES * ATT_TILE_BYTES;
-  uint8_t* smem_v = smem_k + QK_STAGES * ATT_TILE_BYTES;
-  uint8_t* smem_p = smem_v + V_STAGES * V_TILE_BYTES;
+  uint8_t* smem_k = smem_q + p.qk_stages * ATT_TILE_BYTES;
+  uint8_t* smem_v = smem_k + p.qk_stages * ATT_TILE_BYTES;
+  uint8_t* smem_p = smem_v + V_STAGES * p.v_stage_bytes;
   AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem_p + 2 * ATT_TILE_BYTES);
   int* colint = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [s_tiles*128]: bias - zq*rk[s]
 
@@ -139,13 +143,16 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             tma_load_3d(smem_k + stage * ATT_TILE_BYTES, &map_k, &bars->qk_full[stage], kc * ATT_KB, j * ATT_S, bh);
           }
           __syncwarp();
-          if (++stage == QK_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.qk_stages) { stage = 0; phase ^= 1; }
         }
         if (pass == 1) {
           mbar_wait(&bars->v_empty[vs], vphase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(&bars->v_full[vs], (uint32_t)p.d_chunk * ATT_KB);
-            tma_load_3d(smem_v + vs * V_TILE_BYTES, &map_v, &bars->v_full[vs], j * ATT_S, dc * p.d_chunk, bh);
+            const int vrows = p.d_chunk / p.v_halves;
+            tma_load_3d(smem_v + vs * p.v_stage_bytes, &map_v, &bars->v_full[vs], j * ATT_S, dc * p.d_chunk, bh);
+            if (p.v_halves == 2)
+              tma_load_3d(smem_v + vs * p.v_stage_bytes + vrows * ATT_KB, &map_v, &bars->v_full[vs], j * ATT_S, dc * p.d_chunk + vrows, bh);
           }
           __syncwarp();
           if (++vs == V_STAGES) { vs = 0; vphase ^= 1; }
@@ -155,8 +162,9 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc_s = make_idesc_i8(ATT_S, 0, 0);
-    const uint32_t idesc_o = make_idesc_i8(p.d_chunk, 0, 0);
-    const uint32_t tmem_o = tmem_base + 256;
+    const int vrows = p.d_chunk / p.v_halves;
+    const uint32_t idesc_o = make_idesc_i8(vrows, 0, 0);
+    const uint32_t tmem_o = tmem_base + 128u * p.s_bufs;
     const uint32_t q_base = smem_u32(smem_q), k_base = smem_u32(smem_k), v_base = smem_u32(smem_v), p_base = smem_u32(smem_p);
     int stage = 0; uint32_t phase = 0;
     int vs = 0; uint32_t vphase = 0;
@@ -166,12 +174,19 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       mbar_wait(&bars->v_full[vs], vphase);
       tc_fence_after();
       const uint64_t adesc = make_smem_desc(p_base + pb * ATT_TILE_BYTES);
-      const uint64_t bdesc = make_smem_desc(v_base + vs * V_TILE_BYTES);
+      const uint64_t bdesc = make_smem_desc(v_base + vs * p.v_stage_bytes);
       if (elect_one()) {
         umma_i8(tmem_o, adesc, bdesc, idesc_o, jj ? 1u : 0u);
         umma_i8(tmem_o, adesc + 2, bdesc + 2, idesc_o, 1u);
         umma_i8(tmem_o, adesc + 4, bdesc + 4, idesc_o, 1u);
         umma_i8(tmem_o, adesc + 6, bdesc + 6, idesc_o, 1u);
+        if (p.v_halves == 2) {      // second half of the head-dim chunk: next `vrows` rows of the V tile -> next `vrows` O columns
+          const uint64_t bdesc2 = make_smem_desc(v_base + vs * p.v_stage_bytes + vrows * ATT_KB);
+          umma_i8(tmem_o + vrows, adesc, bdesc2, idesc_o, jj ? 1u : 0u);
+          umma_i8(tmem_o + vrows, adesc + 2, bdesc2 + 2, idesc_o, 1u);
+          umma_i8(tmem_o + vrows, adesc + 4, bdesc2 + 4, idesc_o, 1u);
+          umma_i8(tmem_o + vrows, adesc + 6, bdesc2 + 6, idesc_o, 1u);
+        }
         umma_commit(&bars->v_empty[vs]);
         umma_commit(&bars->p_empty[pb]);
       }
@@ -181,8 +196,8 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     int g = 0;
     for (int pass = 0; pass < 2; ++pass) {
       for (int j = 0; j < p.s_tiles; ++j, ++g) {
-        const int sb = g & 1;
-        mbar_wait(&bars->s_empty[sb], (uint32_t)(((g >> 1) & 1) ^ 1));
+        const int sb = p.s_bufs == 2 ? (g & 1) : 0;
+        mbar_wait(&bars->s_empty[sb], (uint32_t)(((p.s_bufs == 2 ? (g >> 1) : g) & 1) ^ 1));
         tc_fence_after();
         const uint32_t tmem_s = tmem_base + (uint32_t)sb * ATT_S;
         for (int kc = 0; kc < p.k_chunks; ++kc) {
@@ -199,7 +214,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             umma_commit(&bars->qk_empty[stage]);
           }
           __syncwarp();
-          if (++stage == QK_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.qk_stages) { stage = 0; phase ^= 1; }
         }
         if (elect_one()) umma_commit(&bars->s_full[sb]);
         __syncwarp();
@@ -238,14 +253,18 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     int g = 0;
     // ---- pass 1: row max and sum ----
     for (int j = 0; j < p.s_tiles; ++j, ++g) {
-      const int sb = g & 1;
-      mbar_wait(&bars->s_full[sb], (uint32_t)((g >> 1) & 1));
+      const int sb = p.s_bufs == 2 ? (g & 1) : 0;
+      mbar_wait(&bars->s_full[sb], (uint32_t)((p.s_bufs == 2 ? (g >> 1) : g) & 1));
       tc_fence_after();
       uint32_t raws[SM_COLS / 16][16];
 #pragma unroll
       for (int cc = 0; cc < SM_COLS / 16; ++cc)      // both TMEM loads in flight before the first is consumed
         if (j * ATT_S + col_base + cc * 16 < p.Tk) tmem_ld16(lane_addr + (uint32_t)sb * ATT_S + col_base + cc * 16, raws[cc]);
       tmem_ld_wait();
+      // the scores are in registers: hand the S accumulator back right away so the next Q.K^T runs under this tile's softmax math
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
       if ((j + 1) * ATT_S <= p.Tk) {
         // full tile (the common case): all 32 columns of this thread at once, no per-chunk bounds logic, one rescale
         const int4* cv = reinterpret_cast<const int4*>(&colint[j * ATT_S + col_base]);
@@ -313,9 +332,6 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         }
       }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
     }
     // merge the column parts of every row
     stat_m[part][r] = m; stat_l[part][r] = l;
@@ -341,14 +357,17 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     const bool fast_codes = p.p_levels == 256;
     int rp = 0;
     for (int j = 0; j < p.s_tiles; ++j, ++g) {
-      const int sb = g & 1, pb = j & 1;
-      mbar_wait(&bars->s_full[sb], (uint32_t)((g >> 1) & 1));
+      const int sb = p.s_bufs == 2 ? (g & 1) : 0, pb = j & 1;
+      mbar_wait(&bars->s_full[sb], (uint32_t)((p.s_bufs == 2 ? (g >> 1) : g) & 1));
       tc_fence_after();
       uint32_t raws[SM_COLS / 16][16];
 #pragma unroll
       for (int cc = 0; cc < SM_COLS / 16; ++cc)
         if (j * ATT_S + col_base + cc * 16 < p.Tk) tmem_ld16(lane_addr + (uint32_t)sb * ATT_S + col_base + cc * 16, raws[cc]);
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->s_empty[sb]);
       mbar_wait(&bars->p_empty[pb], (uint32_t)(((j >> 1) & 1) ^ 1));
       uint8_t* prow = smem_p + pb * ATT_TILE_BYTES + r * 128;
       if (fast_codes && (j + 1) * ATT_S <= p.Tk) {
@@ -413,7 +432,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&bars->p_full[pb]); mbar_arrive(&bars->s_empty[sb]); }
+      if (lane == 0) mbar_arrive(&bars->p_full[pb]);
     }
     // ---- epilogue: O -> fp32 output (the four threads of a row take alternate 16-column groups) ----
     stat_rp[part][r] = rp;
@@ -431,7 +450,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     const int row_o = p.Tk * zp_i * zv - zv * rp;
     for (int c0 = part * 16; c0 < p.d_chunk; c0 += 16 * SM_PARTS) {
       uint32_t raw[16];
-      tmem_ld16(lane_addr + 256 + c0, raw);
+      tmem_ld16(lane_addr + 128u * p.s_bufs + c0, raw);
       tmem_ld_wait();
       if (row_ok) {
 #pragma unroll
@@ -477,8 +496,20 @@ extern "C" int edadm_qattn_fwd(const uint8_t* qc, const uint8_t* kc, const uint8
   p.k_chunks = (dp + ATT_KB - 1) / ATT_KB;
   p.k_last_mmas = (dp - (p.k_chunks - 1) * ATT_KB + UMMA_K - 1) / UMMA_K;
   p.s_tiles = (Tk + ATT_S - 1) / ATT_S;
-  const int d_chunks = (d + 255) / 256;
+  // head-dim chunk of one CTA: two S accumulators + O need 256 + d_chunk <= 512 TMEM columns; a single S accumulator (handed
+  // back as soon as the softmax warps hold the scores in registers) leaves 384 columns for O, so d = 384 (LDM-4 ImageNet,
+  // 32x32 level) needs ONE pass over the scores instead of two
+  p.s_bufs = d <= 256 ? 2 : 1;
+  const int d_cap = 512 - 128 * p.s_bufs;
+  const int d_chunks = (d + d_cap - 1) / d_cap;
   p.d_chunk = (((d + d_chunks - 1) / d_chunks) + 15) & ~15;
+  p.v_halves = p.d_chunk > 256 ? 2 : 1;
+  if (p.v_halves == 2) p.d_chunk = (p.d_chunk + 31) & ~31;
+  p.v_stage_bytes = (p.d_chunk * ATT_KB + 1023) & ~1023;
+  p.qk_stages = QK_STAGES;
+  while (p.qk_stages > 2 && 1024 + p.qk_stages * 2 * ATT_TILE_BYTES + V_STAGES * p.v_stage_bytes + 2 * ATT_TILE_BYTES + 256 + ATT_MAX_KEYS * 4 > ATT_SMEM_BYTES) --p.qk_stages;
+  const int att_smem = 1024 + p.qk_stages * 2 * ATT_TILE_BYTES + V_STAGES * p.v_stage_bytes + 2 * ATT_TILE_BYTES + 256 + ATT_MAX_KEYS * 4;
+  if (att_smem > ATT_SMEM_BYTES) return fail(EDADM_ERR_UNSUPPORTED, "qattn_fwd: shared memory budget exceeded (d_chunk %d)", p.d_chunk);
   p.heads = heads;
   p.o_sb = o_sb; p.o_sh = o_sh; p.o_st = o_st; p.o_sc = o_sc;
   p.sm_scale = sm_scale;
@@ -504,7 +535,7 @@ extern "C" int edadm_qattn_fwd(const uint8_t* qc, const uint8_t* kc, const uint8
   {
     cuuint64_t dims[3] = {(cuuint64_t)Tkp, (cuuint64_t)d, (cuuint64_t)BH};
     cuuint64_t strides[2] = {(cuuint64_t)Tkp, (cuuint64_t)d * Tkp};
-    cuuint32_t box[3] = {(cuuint32_t)ATT_S, (cuuint32_t)p.d_chunk, 1u};
+    cuuint32_t box[3] = {(cuuint32_t)ATT_S, (cuuint32_t)(p.d_chunk / p.v_halves), 1u};
     int rc = encode_map(&map_v, vc, 3, dims, strides, box, "attention v codes");
     if (rc) return rc;
   }
@@ -518,8 +549,8 @@ extern "C" int edadm_qattn_fwd(const uint8_t* qc, const uint8_t* kc, const uint8
   dim3 grid((Tq + ATT_M - 1) / ATT_M, d_chunks, BH);
   // |raw - zq*rk| <= 255*255*max(d, dp): the magic-number int->float conversion is exact below 2^22
   if ((long long)dp * 65025LL < (1LL << 22))
-    qattn_kernel<true><<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(map_q, map_k, map_v, p);
+    qattn_kernel<true><<<grid, ATT_THREADS, att_smem, (cudaStream_t)stream>>>(map_q, map_k, map_v, p);
   else
-    qattn_kernel<false><<<grid, ATT_THREADS, ATT_SMEM_BYTES, (cudaStream_t)stream>>>(map_q, map_k, map_v, p);
+    qattn_kernel<false><<<grid, ATT_THREADS, att_smem, (cudaStream_t)stream>>>(map_q, map_k, map_v, p);
   return check_launch("qattn_fwd");
 }

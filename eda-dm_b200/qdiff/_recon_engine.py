@@ -234,12 +234,25 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
     fbr = (not is_layer) and len(hooks) != 0 and add_loss != 0.0
     bsz = min(batch_size, sz)
 
-    # cache tensors in the order (out, inp, sym[, emb_inp, emb_sym]); static minibatch buffers for the graph
+    # cache tensors in the order (out, inp, sym[, emb_inp, emb_sym])
     if resblock:
         sources = [cached_outs, cached_inps[0][0], cached_inps[1][0], cached_inps[0][1], cached_inps[1][1]]
     else:
         sources = [cached_outs, cached_inps[0], cached_inps[1]]
-    static = [torch.empty((bsz,) + tuple(t.shape[1:]), dtype=t.dtype, device=device) for t in sources] if use_graph else None
+    on_device = all(t.device == device for t in sources)
+    # Device-resident iteration state: with the cache in HBM the whole iteration -- minibatch gather included -- reads its
+    # indices and learning rates from tables indexed by a device-side counter, so a captured step needs NO per-iteration host
+    # work (the host only replays; 8 data-parallel ranks stay in lockstep instead of waiting for the slowest host loop at the
+    # all-reduce).  The index table is drawn up front with the reference's own call sequence (one random.sample per iteration).
+    device_state = use_graph and on_device
+    it_counter = torch.zeros(1, dtype=torch.long, device=device)
+    if device_state:
+        idx_all = torch.tensor([rng.sample(range(sz), bsz) for _ in range(iters)], dtype=torch.long, device=device)
+        w_lr_all = torch.tensor([_cosine_lr(lr_w, t, iters) for t in range(iters)], dtype=torch.float32, device=device)
+        a_lr_all = torch.tensor([_cosine_lr(lr_a, t, iters) for t in range(iters)], dtype=torch.float32, device=device)
+        loss_all = torch.zeros(iters, dtype=torch.float32, device=device)
+    static = [torch.empty((bsz,) + tuple(t.shape[1:]), dtype=t.dtype, device=device) for t in sources] \
+        if (use_graph and not device_state) else None
     loss_out = torch.zeros((), dtype=torch.float32, device=device)
     gnorm_out = torch.zeros(2, dtype=torch.float32, device=device)      # diagnostics: |grad| of the alpha / step-size parameters
     n_w = sum(p_.numel() for p_ in w_para)
@@ -252,6 +265,13 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
         for dst, src in zip(static, rows):
             dst.copy_(src, non_blocking=True)
         return static
+
+    def device_rows():
+        """this iteration's minibatch and learning rates, selected on the device by the iteration counter"""
+        idx = idx_all.index_select(0, it_counter).reshape(-1)
+        w_lr.copy_(w_lr_all.index_select(0, it_counter).reshape(()))
+        a_lr.copy_(a_lr_all.index_select(0, it_counter).reshape(()))
+        return [t.index_select(0, idx) for t in sources]
 
     def step(rows):
         cur_out, cur_inp, cur_sym = rows[0], rows[1], rows[2]
@@ -307,15 +327,20 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
             if opt is not None:
                 opt.step()
         loss_out.copy_(block_loss.detach())
+        if device_state:
+            loss_all.index_copy_(0, it_counter, block_loss.detach().reshape(1))
+            it_counter.add_(1)
 
     graph = None
     n_eager = 3
     # Warm-up iterations and the capture run on ONE non-default stream (library handles / workspaces used by the
     # autograd thread must never have been bound to the legacy stream, or capture is invalidated).
     side = torch.cuda.Stream(device=device) if use_graph else None
+    if bucket is not None and device.type == 'cuda' and backend.recon_overlap_allreduce:
+        bucket.overlap_backward(stream=side)
     # a parallel FP branch pays off while the unit's kernels are launch/latency bound (+4 % on a church 16x16 ResBlock) and
     # hurts on larger units (ImageNet 32x32 ResBlock: -23 %): opt-in (backend.recon_overlap_fp) and size-gated
-    small_unit = static is not None and static[1].numel() <= (4 << 20)
+    small_unit = use_graph and bsz * sources[1][0].numel() <= (4 << 20)
     fp_stream = torch.cuda.Stream(device=device) if (use_graph and backend.recon_overlap_fp and small_unit) else None
     if side is not None:
         side.wait_stream(torch.cuda.current_stream(device))
@@ -327,7 +352,7 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
                     side.synchronize()
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph, stream=side):
-                        step(static)
+                        step(device_rows() if device_state else static)
                 except Exception as exc:  # keep optimising eagerly; the captured work never ran
                     logger.warning("CUDA-graph capture of the reconstruction step failed (%s); continuing eagerly", exc)
                     graph, use_graph = False, False
@@ -336,19 +361,25 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
                 qdist.barrier()
                 torch.cuda.synchronize()
                 timing['start'].record()
-            rows = gather(rng.sample(range(sz), bsz))
-            if w_lr is not None:
-                w_lr.fill_(_cosine_lr(lr_w, it, iters))
-                a_lr.fill_(_cosine_lr(lr_a, it, iters))
-            if graph:
-                graph.replay()
+            if device_state:
+                if graph:
+                    graph.replay()
+                else:
+                    step(device_rows())
             else:
-                step(rows)
-                for sched in (w_sched, a_sched):
-                    if sched is not None:
-                        sched.step()
-            if return_losses:
-                losses.append(loss_out.clone())
+                rows = gather(rng.sample(range(sz), bsz))
+                if w_lr is not None:
+                    w_lr.fill_(_cosine_lr(lr_w, it, iters))
+                    a_lr.fill_(_cosine_lr(lr_a, it, iters))
+                if graph:
+                    graph.replay()
+                else:
+                    step(rows)
+                    for sched in (w_sched, a_sched):
+                        if sched is not None:
+                            sched.step()
+                if return_losses:
+                    losses.append(loss_out.clone())
             if timing is not None and 'grad_norms' in timing:
                 timing['grad_norms'].append(gnorm_out.clone())
         if timing is not None and 'start' in timing:
@@ -365,8 +396,11 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
         timing['cuda_graph'] = bool(graph)
     finish_unit(unit, trained, hooks, attn_only)
     if bucket is not None:
+        bucket.release()
         for prm in bucket.params:
             prm.grad = None
     if return_losses:
+        if device_state:
+            return loss_all.clone()
         return torch.stack(losses) if losses else torch.empty(0)
     return None

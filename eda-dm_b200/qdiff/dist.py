@@ -3,6 +3,8 @@ rows sharded across ranks, ONE all-reduce per reconstruction step over a flat fp
 AdaRound alpha gradient and every activation step-size gradient of the unit.  torch.distributed (NCCL over
 NVLink on the box, gloo in the CPU tests) carries the collective; with no process group everything is a no-op.
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
 
@@ -54,13 +56,61 @@ class GradBucket:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
 
+        self._works, self._done, self._hooks = [], set(), []
+
     def zero(self):
         self.flat.zero_()
+        self._works, self._done = [], set()
+
+    def overlap_backward(self, min_numel: int = 1 << 16, stream=None):
+        """Start the exchange of every large gradient (an AdaRound alpha) the moment autograd has finished accumulating it,
+        instead of one all-reduce after the whole backward: the reduction of the last layers' gradients then runs on NCCL's
+        stream underneath the backward of the earlier layers.  Every rank builds the same autograd graph, so the collectives are
+        issued in the same order everywhere.  Small gradients (step sizes) and whatever was not reduced early go out in one final
+        call from `all_reduce_mean`.  Works inside CUDA-graph capture (the asynchronous collectives become a parallel branch)."""
+        if not is_active() or self._hooks:
+            return
+        for i, p in enumerate(self.params):
+            if p.numel() < min_numel:
+                continue
+
+            def hook(param, i=i):
+                if i not in self._done and param.grad is not None and param.grad.data_ptr() == self._view_ptr[i]:
+                    self._done.add(i)
+                    # issued against the loop's compute stream (hooks run on an autograd worker thread whose current stream
+                    # need not be the one the accumulation was enqueued on): NCCL's stream waits for everything queued so far
+                    ctx = torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+                    with ctx:
+                        self._works.append(dist.all_reduce(param.grad, op=dist.ReduceOp.SUM, async_op=True))
+            self._hooks.append(p.register_post_accumulate_grad_hook(hook))
+        self._view_ptr = [p.grad.data_ptr() for p in self.params]
+
+    def release(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
 
     def all_reduce_mean(self):
-        if is_active():
+        if not is_active():
+            return
+        if not self._done:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(world_size())
+        else:
+            # contiguous runs of parameters that were not reduced during the backward
+            off, run = 0, None
+            for i, p in enumerate(self.params + [None]):
+                pending = p is not None and i not in self._done
+                if pending and run is None:
+                    run = off
+                if not pending and run is not None:
+                    self._works.append(dist.all_reduce(self.flat[run:off], op=dist.ReduceOp.SUM, async_op=True))
+                    run = None
+                if p is not None:
+                    off += p.numel()
+            for w in self._works:
+                w.wait()            # the compute stream waits for NCCL's stream (no host synchronisation)
+            self._works, self._done = [], set()
+        self.flat.div_(world_size())
 
     def nbytes(self):
         return self.flat.numel() * 4

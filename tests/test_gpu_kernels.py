@@ -433,7 +433,8 @@ def test_qattn_ldm_legacy_layout(cuda, B, heads, ch, T):
 
 
 @pytest.mark.parametrize("B,heads,d,Tq,Tk", [(2, 1, 384, 256, 256), (2, 8, 40, 128, 77), (1, 1, 576, 64, 1), (2, 8, 80, 300, 300),
-                                             (1, 1, 960, 64, 64)])
+                                             (1, 1, 960, 64, 64), (1, 1, 384, 1024, 1024), (2, 1, 576, 256, 256), (1, 1, 300, 200, 200),
+                                             (1, 1, 512, 128, 128)])
 def test_qattn_cross_layout(cuda, B, heads, d, Tq, Tk):
     from edadm import ops
     g = torch.Generator().manual_seed(23)
