@@ -82,7 +82,9 @@ def legacy_attention_forward(self, qkv):
     scale = 1 / math.sqrt(math.sqrt(ch))
     self.qkv_matmul.scale = scale
     qk, sv = self.qkv_matmul, self.smv_matmul
-    if qk.use_act_quant and sv.use_act_quant and \
+    # (a hook on either matmul module -- they are reconstruction units of their own, reference recon_block_Qmodel.py:48-55 --
+    # must see the module's call, so the fused kernel steps aside)
+    if qk.use_act_quant and sv.use_act_quant and not qk._forward_hooks and not sv._forward_hooks and \
             _fusable((qkv,), (qk.act_quantizer_q, qk.act_quantizer_k, sv.act_quantizer_v, sv.act_quantizer_w), n_keys=length,
                      bh=bs * self.n_heads):
         aq = _aquant(qk.act_quantizer_q, qk.act_quantizer_k, sv.act_quantizer_v, sv.act_quantizer_w)

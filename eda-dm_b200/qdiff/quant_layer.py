@@ -39,6 +39,7 @@ class _Backend:
     recon_cuda_graph = True  # capture the reconstruction iteration in one CUDA graph after 3 eager iterations
     recon_graph_checkpointed = True   # ... including units whose backward recomputes the forward (transformer / attention blocks)
     recon_overlap_allreduce = True    # data parallel: all-reduce each alpha gradient as soon as its backward has produced it
+    cache_prefix_reuse = True         # calibration cache builder keeps the network state at the frontier of the finished units (f2)
     recon_overlap_fp = False  # ... with the FP forward on a forked stream (a parallel graph branch): +4 % on a church
                               # 16x16 ResBlock, -23 % on an ImageNet 32x32 one (measured), hence opt-in
     qdrop_inkernel_rng = False  # False: QDrop masks come from torch.rand_like (the reference's stream, graph-safe);

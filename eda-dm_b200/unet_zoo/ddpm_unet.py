@@ -165,34 +165,89 @@ class DDPMUNet(nn.Module):
         self.norm_out = _gn(block_in)
         self.conv_out = nn.Conv2d(block_in, out_ch, 3, 1, 1)
 
-    def forward(self, x, t=None, context=None):
-        temb = self.temb.dense[1](nonlinearity(self.temb.dense[0](sinusoidal_embedding(t, self.ch))))
-        hs = [self.conv_in(x)]
+    # stages over an explicit state (see unet_zoo/ldm_unet.py UNetModel.stage_modules): embedding, conv_in, every
+    # (ResnetBlock [+ AttnBlock]) pair and resampling layer in execution order, the middle, the output head
+    def _plan(self):
+        plan = [("temb", None, None), ("conv_in", None, None)]
         for lvl in range(self.num_resolutions):
-            level = self.down[lvl]
             for i in range(self.num_res_blocks):
-                h = level.block[i](hs[-1], temb)
-                if len(level.attn) > 0:
-                    h = level.attn[i](h)
-                hs.append(h)
+                plan.append(("down", lvl, i))
             if lvl != self.num_resolutions - 1:
-                hs.append(level.downsample(hs[-1]))
-        h = self.mid.block_2(self.mid.attn_1(self.mid.block_1(hs[-1], temb)), temb)
+                plan.append(("downsample", lvl, None))
+        plan.append(("mid", None, None))
         for lvl in reversed(range(self.num_resolutions)):
-            level = self.up[lvl]
             for i in range(self.num_res_blocks + 1):
-                # split shortcut: the concat boundary is handed to the 1x1 shortcut conv so the two halves get
-                # their own quantizers (reference ddim/models/diffusion.py:357-368)
-                split = h.size(1) if self.config.split_shortcut else 0
-                h = level.block[i](torch.cat([h, hs.pop()], dim=1), temb, split=split) if split else \
-                    level.block[i](torch.cat([h, hs.pop()], dim=1), temb)
-                if len(level.attn) > 0:
-                    h = level.attn[i](h)
+                plan.append(("up", lvl, i))
             if lvl != 0:
-                h = level.upsample(h)
-        if hasattr(self.conv_out, 'forward_prenorm'):
-            return self.conv_out.forward_prenorm(h, self.norm_out, act_fn=nonlinearity)
-        return self.conv_out(nonlinearity(self.norm_out(h)))
+                plan.append(("upsample", lvl, None))
+        plan.append(("out", None, None))
+        return plan
+
+    def stage_modules(self):
+        mods = []
+        for kind, lvl, i in self._plan():
+            if kind == "temb":
+                mods.append(list(self.temb.dense))
+            elif kind == "conv_in":
+                mods.append([self.conv_in])
+            elif kind in ("down", "up"):
+                level = (self.down if kind == "down" else self.up)[lvl]
+                mods.append([level.block[i]] + ([level.attn[i]] if len(level.attn) > 0 else []))
+            elif kind == "downsample":
+                mods.append([self.down[lvl].downsample])
+            elif kind == "upsample":
+                mods.append([self.up[lvl].upsample])
+            elif kind == "mid":
+                mods.append([self.mid.block_1, self.mid.attn_1, self.mid.block_2])
+            else:
+                mods.append([self.norm_out, self.conv_out])
+        return mods
+
+    def stage_begin(self, x, t=None, context=None):
+        return {"x": x, "t": t, "h": None, "hs": [], "temb": None}
+
+    def run_stage(self, k, st):
+        st = dict(st)
+        kind, lvl, i = self._plan()[k]
+        if kind == "temb":
+            st["temb"] = self.temb.dense[1](nonlinearity(self.temb.dense[0](sinusoidal_embedding(st["t"], self.ch))))
+        elif kind == "conv_in":
+            st["hs"] = [self.conv_in(st["x"])]
+        elif kind == "down":
+            level = self.down[lvl]
+            h = level.block[i](st["hs"][-1], st["temb"])
+            if len(level.attn) > 0:
+                h = level.attn[i](h)
+            st["hs"] = st["hs"] + [h]
+        elif kind == "downsample":
+            st["hs"] = st["hs"] + [self.down[lvl].downsample(st["hs"][-1])]
+        elif kind == "mid":
+            st["h"] = self.mid.block_2(self.mid.attn_1(self.mid.block_1(st["hs"][-1], st["temb"])), st["temb"])
+        elif kind == "up":
+            level, h = self.up[lvl], st["h"]
+            # split shortcut: the concat boundary is handed to the 1x1 shortcut conv so the two halves get
+            # their own quantizers (reference ddim/models/diffusion.py:357-368)
+            split = h.size(1) if self.config.split_shortcut else 0
+            cat = torch.cat([h, st["hs"][-1]], dim=1)
+            h = level.block[i](cat, st["temb"], split=split) if split else level.block[i](cat, st["temb"])
+            if len(level.attn) > 0:
+                h = level.attn[i](h)
+            st["h"], st["hs"] = h, st["hs"][:-1]
+        elif kind == "upsample":
+            st["h"] = self.up[lvl].upsample(st["h"])
+        else:
+            h = st["h"]
+            if hasattr(self.conv_out, 'forward_prenorm'):
+                st["h"] = self.conv_out.forward_prenorm(h, self.norm_out, act_fn=nonlinearity)
+            else:
+                st["h"] = self.conv_out(nonlinearity(self.norm_out(h)))
+        return st
+
+    def forward(self, x, t=None, context=None):
+        st = self.stage_begin(x, t, context)
+        for k in range(len(self._plan())):
+            st = self.run_stage(k, st)
+        return st["h"]
 
 
 def cifar10_unet(**overrides):

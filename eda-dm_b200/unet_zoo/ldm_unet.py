@@ -330,21 +330,48 @@ class UNetModel(nn.Module):
                 self.output_blocks.append(TimestepEmbedSequential(*layers))
         self.out = nn.Sequential(GroupNorm32(32, ch), nn.SiLU(), _zero(nn.Conv2d(model_channels, out_channels, 3, padding=1)))
 
-    def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
-        emb = self.time_embed(timestep_embedding(timesteps, self.model_channels))
-        if self.num_classes is not None:
-            emb = emb + self.label_emb(y)
-        hs, h = [], x
-        for module in self.input_blocks:
-            h = module(h, emb, context)
-            hs.append(h)
-        h = self.middle_block(h, emb, context)
-        for module in self.output_blocks:
+    # The forward pass as a list of stages over an explicit state {h, hs, emb, context}: `forward` runs them all; the calibration
+    # cache builder (qdiff/data_utils.py StagedCache) keeps the state of every calibration batch at the frontier of the units
+    # already reconstructed and only ever runs each stage once per path, instead of re-running the whole prefix for every unit.
+    def stage_modules(self):
+        return ([[self.time_embed] + ([self.label_emb] if self.num_classes is not None else [])] + [[m] for m in self.input_blocks] +
+                [[self.middle_block]] + [[m] for m in self.output_blocks] + [[self.out]])
+
+    def stage_begin(self, x, timesteps=None, context=None, y=None, **kwargs):
+        return {"x": x, "timesteps": timesteps, "context": context, "y": y, "h": x, "hs": [], "emb": None}
+
+    def run_stage(self, k, st):
+        st = dict(st)
+        n_in = len(self.input_blocks)
+        if k == 0:
+            emb = self.time_embed(timestep_embedding(st["timesteps"], self.model_channels))
+            if self.num_classes is not None:
+                emb = emb + self.label_emb(st["y"])
+            st["emb"] = emb
+        elif k <= n_in:
+            st["h"] = self.input_blocks[k - 1](st["h"], st["emb"], st["context"])
+            st["hs"] = st["hs"] + [st["h"]]
+        elif k == n_in + 1:
+            st["h"] = self.middle_block(st["h"], st["emb"], st["context"])
+        elif k <= n_in + 1 + len(self.output_blocks):
+            module = self.output_blocks[k - n_in - 2]
+            h = st["h"]
             split = h.shape[1] if self.split_shortcut else 0
-            h = module(torch.cat([h, hs.pop()], dim=1), emb, context, split=split)
-        if hasattr(self.out[-1], 'forward_prenorm') and len(self.out) == 3 and isinstance(self.out[1], nn.SiLU):
-            return self.out[2].forward_prenorm(h, self.out[0])      # GroupNorm + SiLU ride on the quantized module's producer
-        return self.out(h)
+            st["h"] = module(torch.cat([h, st["hs"][-1]], dim=1), st["emb"], st["context"], split=split)
+            st["hs"] = st["hs"][:-1]
+        else:
+            h = st["h"]
+            if hasattr(self.out[-1], 'forward_prenorm') and len(self.out) == 3 and isinstance(self.out[1], nn.SiLU):
+                st["h"] = self.out[2].forward_prenorm(h, self.out[0])      # GroupNorm + SiLU ride on the quantized module's producer
+            else:
+                st["h"] = self.out(h)
+        return st
+
+    def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
+        st = self.stage_begin(x, timesteps, context, y)
+        for k in range(len(self.input_blocks) + len(self.output_blocks) + 3):
+            st = self.run_stage(k, st)
+        return st["h"]
 
 
 def reinit_zero_modules(model: nn.Module, std: float = 0.02, seed: int = 0):

@@ -300,3 +300,40 @@ def test_checkpointed_unit_reconstruction_graph_equals_eager(cuda):
     assert np.allclose(traces[0][:3], traces[1][:3], rtol=2e-3), (traces[0], traces[1])
     assert np.allclose(traces[0], traces[1], rtol=0.35), (traces[0], traces[1])
     assert np.all(np.isfinite(traces[0]))
+
+
+def test_staged_cache_equals_prefix_rerun_quantized_path(cuda):
+    """f2 on the GPU: while a few units are reconstructed in walk order, the staged cache builder (frontier states kept in HBM)
+    hands every unit bit-identical (quantized-path input, FP output, FP-path input) tensors to what re-running the whole
+    prefix gives (reference data_utils.py:125-171)"""
+    from qdiff.block_recon import block_reconstruction
+    from qdiff.layer_recon import layer_reconstruction
+    from qdiff.data_utils import save_inp_oup_data
+    from qdiff.quant_layer import backend, QuantModule
+    g = H.load("ddim_tiny.npz")
+    qnn = _product(g, H.ddim_tiny_model(), cuda, _set_split_ddim)
+    x, t = T(g["x"]).to(cuda), T(g["t"]).to(cuda)
+    with torch.no_grad():
+        qnn(x[:4], t[:4])
+    H.install_qparams(qnn, H.qtable(g))
+    m = qnn.model
+    walk = [m.temb.dense[0], m.conv_in, m.down[0].block[0], m.down[0].downsample.conv, m.down[1].block[0], m.down[1].attn[0], m.mid.block_1,
+            m.up[1].block[0], m.up[0].block[1], m.conv_out]
+    kw = dict(RECON_KW); kw.update(iters=2, cali_data=(x, t))
+    random.seed(5); torch.manual_seed(5)
+    for unit in walk:
+        got = []
+        for reuse in (True, False):
+            backend.cache_prefix_reuse = reuse
+            try:
+                got.append(save_inp_oup_data(qnn, unit, (x, t), asym=True, act_quant=True, batch_size=16, input_prob=True, keep_gpu=True))
+            finally:
+                backend.cache_prefix_reuse = True
+        (r0, i0, o0), (r1, i1, o1) = got
+        flat = lambda tt: [a for pair in tt for a in (pair if isinstance(pair, (list, tuple)) else [pair])]
+        assert r0 == r1 and torch.equal(o0, o1), type(unit).__name__
+        for a, b in zip(flat(i0), flat(i1)):
+            assert torch.equal(a, b), type(unit).__name__
+        # reconstruct the unit (changes its quantizers) before moving on, as the whole-model walk does
+        (layer_reconstruction if isinstance(unit, QuantModule) else block_reconstruction)(qnn, unit, **kw)
+    assert qnn._stage_cache.stage > 5          # the frontier really advanced instead of being rebuilt for every unit

@@ -227,3 +227,49 @@ def test_data_parallel_plumbing_gloo_world2(tmp_path):
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count("ok") == 2
+
+
+def test_staged_cache_equals_prefix_rerun_fp_path():
+    """f2: the staged cache builder (frontier state reuse) returns the tensors the reference-style builder computes by re-running
+    the prefix -- FP path on the CPU here (the quantized path is covered by the -m gpu twin), units visited in walk order, plus a
+    backwards request (forces a rebuild) and the staged == plain forward identity of the zoo UNets"""
+    import torch
+    from unet_zoo.ddpm_unet import DDPMUNet
+    from unet_zoo.ldm_unet import UNetModel
+    from qdiff import QuantModel
+    from qdiff.quant_layer import backend, QuantModule
+    from qdiff.quant_block import BaseQuantBlock
+    from qdiff.data_utils import save_inp_oup_data
+    wq = {'n_bits': 4, 'symmetric': True, 'channel_wise': True, 'scale_method': 'mse'}
+    aq = {'n_bits': 8, 'symmetric': True, 'channel_wise': False, 'scale_method': 'mse', 'leaf_param': True, 'prob': 1.0}
+    torch.manual_seed(0)
+    cases = [(DDPMUNet(ch=32, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=(8,), resolution=16, dropout=0.0), (3, 16, 16), None),
+             (UNetModel(image_size=8, in_channels=3, out_channels=3, model_channels=32, attention_resolutions=[1, 2], num_res_blocks=1,
+                        channel_mult=[1, 2], num_heads=2, use_spatial_transformer=True, transformer_depth=1, context_dim=24), (3, 8, 8), (3, 24))]
+    for fp, shape, ctx in cases:
+        fp = fp.eval()
+        g = torch.Generator().manual_seed(1)
+        cali = [torch.randn(8, *shape, generator=g), torch.randint(0, 1000, (8,), generator=g)]
+        if ctx:
+            cali.append(torch.randn(8, *ctx, generator=g))
+        with torch.no_grad():
+            y_plain = fp(*cali)
+        qnn = QuantModel(fp, wq, aq, sm_abit=8).eval()
+        with torch.no_grad():
+            assert torch.equal(qnn(*cali), y_plain)            # staged forward of the rewritten model == the FP model's output
+        units = [m for m in qnn.model.modules() if isinstance(m, BaseQuantBlock) and type(m).__name__ not in ("QuantQKMatMul", "QuantSMVMatMul")]
+        units += [m for m in qnn.model.modules() if isinstance(m, QuantModule)][:3]
+        order = sorted(units, key=lambda m: [id(x) for x in qnn.model.modules()].index(id(m)))
+        for unit in order + [order[1]]:
+            got = []
+            for reuse in (True, False):
+                backend.cache_prefix_reuse = reuse
+                try:
+                    got.append(save_inp_oup_data(qnn, unit, cali, asym=False, act_quant=False, batch_size=4, input_prob=True, keep_gpu=True))
+                finally:
+                    backend.cache_prefix_reuse = True
+            (r0, i0, o0), (r1, i1, o1) = got
+            assert r0 == r1 and torch.equal(o0, o1)
+            flat = lambda t: [a for pair in t for a in (pair if isinstance(pair, (list, tuple)) else [pair])]
+            for a, b in zip(flat(i0), flat(i1)):
+                assert torch.equal(a, b)
