@@ -203,3 +203,40 @@ def test_set_quantize_params_cfg_drivers(cuda, stub_samplers, which):
     act = [torch.cat([calls[1][i], calls[2][i]]) for i in range(3)]
     set_act_quantize_params(q2, act, batch_size=4, all_attention=True)
     _tables_equal(q1, q2)
+
+
+def test_packed_w4_export_roundtrip(cuda, tmp_path):
+    """f4: export after reconstruction (hard AdaRound codes, learned step sizes) -> file -> fresh model: bit-identical forward;
+    4-bit codes cost half a byte per weight"""
+    from qdiff.block_recon import block_reconstruction
+    from qdiff.export import export_packed, load_packed, packed_nbytes
+    g = H.load("ddim_tiny.npz")
+    qnn = _product(g, H.ddim_tiny_model(), cuda, _set_split_ddim)
+    x, t = T(g["x"]).to(cuda), T(g["t"]).to(cuda)
+    with torch.no_grad():
+        qnn(x[:4], t[:4])
+    H.install_qparams(qnn, H.qtable(g))
+    random.seed(1); torch.manual_seed(1)
+    block_reconstruction(qnn, qnn.model.down[0].block[0], cali_data=(x, t), **dict(RECON_KW, iters=3))
+    qnn.set_quant_state(True, True)
+    with torch.no_grad():
+        y0 = qnn(x[:8], t[:8])
+    path = tmp_path / "w4a8.pt"
+    blob = export_packed(qnn, str(path))
+    n_w = sum(m.weight.numel() for m in qnn.modules() if hasattr(m, "weight_quantizer"))
+    n_w4 = sum(m.weight.numel() for m in qnn.modules() if hasattr(m, "weight_quantizer") and m.weight_quantizer.n_bits <= 4)
+    code_bytes = sum(p["codes"].numel() for e in blob["layers"].values() for p in e["weights"])
+    assert code_bytes <= n_w4 // 2 + (n_w - n_w4) + 64 * len(blob["layers"])          # two 4-bit codes per byte
+    assert packed_nbytes(blob) < 0.3 * 4 * sum(p.numel() for p in H.ddim_tiny_model().parameters())
+    fresh = _product(g, H.ddim_tiny_model(), cuda, _set_split_ddim)
+    with torch.no_grad():
+        torch.manual_seed(123)
+        for p in fresh.parameters():
+            p.add_(torch.randn_like(p) * 0.01)                 # whatever the fresh model holds is overwritten
+        fresh(x[:4], t[:4])                                    # creates the split twins
+    load_packed(fresh, str(path))
+    fresh.set_quant_state(True, True)
+    with torch.no_grad():
+        y1 = fresh(x[:8], t[:8])
+    assert torch.equal(y0, y1)
+    assert sum(v == "int8" for v in fresh.path_report().values()) >= len(fresh.path_report()) - 1

@@ -273,3 +273,26 @@ def test_staged_cache_equals_prefix_rerun_fp_path():
             flat = lambda t: [a for pair in t for a in (pair if isinstance(pair, (list, tuple)) else [pair])]
             for a, b in zip(flat(i0), flat(i1)):
                 assert torch.equal(a, b)
+
+
+def test_tdac_allocation_matches_reference_loops():
+    """f4: Gram-matrix TDAC scores / allocation / assembly == the reference's O(T^2) loops (oracle/tdac_oracle.py)"""
+    import torch
+    from qdiff import tdac
+    from oracle import tdac_oracle
+    g = torch.Generator().manual_seed(3)
+    T_, N = 12, 6
+    base = torch.randn(N, 16, 4, 4, generator=g)
+    feats = [base * (1.0 + 0.35 * k) + 0.8 * torch.randn(N, 16, 4, 4, generator=g) * (k % 3) for k in range(T_)]
+    d0, c0 = tdac_oracle.scores(feats, dense_r=3.0)
+    d1, c1 = tdac.tdac_scores(feats, dense_r=3.0)
+    assert torch.equal(d0, d1) and 0 < int(d0.max()) and int(d0.min()) < int(d0.max())
+    assert torch.allclose(c0, c1, rtol=1e-4, atol=1e-3)
+    for lam in (0.0, 1.0, 2.5):
+        assert torch.equal(tdac_oracle.allocation(feats, lam, 64), tdac.tdac_allocation(feats, lam, 64))
+    t_num = tdac.tdac_allocation(feats, 1.0, 24)
+    traj = [torch.randn(N, 3, 8, 8, generator=g) for _ in range(T_)]
+    calib, t, ts = tdac.tdac_assemble(traj, t_num, N, seq=range(0, 1000, 1000 // T_)[:T_], generator=torch.Generator().manual_seed(9))
+    assert torch.equal(calib, tdac_oracle.assemble(traj, t, N)) and calib.shape[0] == 24
+    assert torch.equal(torch.bincount(t, minlength=T_), t_num)
+    assert ts.shape == t.shape
