@@ -1,0 +1,373 @@
+// Calibration-path GEMM for sm_100a (SURVEY.md section 8 row N1 / north_star (b); replaces the fp32 library call behind
+// `self.fwd_func(input, weight, bias)` at qdiff/quant_layer.py:434 -- and its autograd dgrad / wgrad -- while the fake-quant
+// operands carry gradients, i.e. inside block_reconstruction).
+//
+//   D[m][n] (fp32) (+)= sum_k A[m][k] * B[n][k]  (+ bias[n])
+//
+// on the bf16 tensor cores with fp32-class accuracy: every fp32 operand x is split into x_hi = bf16(x), x_lo = bf16(x - x_hi)
+// (edadm_split_bf16, one pass, optionally also the transposed copies the backward GEMMs need) and the product is evaluated as
+// A_hi.B_hi + A_hi.B_lo + A_lo.B_hi with fp32 accumulation in TMEM -- three tcgen05.mma.kind::f16 per K step, relative error
+// ~2^-16 per product against 2^-11 for the TF32 path cuDNN / cuBLAS take.  The fake-quantized operands of the reconstruction
+// loop are not representable in one bf16 (QDrop passes raw fp32 activations through, soft AdaRound weights have fractional codes),
+// hence the split instead of plain bf16.
+//
+// One kernel serves forward, dgrad and wgrad -- they differ in which (pre-split, K-contiguous) copies are handed in:
+//   forward  Y  = X  W^T      A = X  [M][K],   B = W  [N][K]
+//   dgrad    dX = dY W        A = dY [M][N],   B = W^T [K][N]
+//   wgrad    dW = dY^T X      A = dY^T [N][M], B = X^T [K][M]   (few output tiles, long reduction: split-K, partial tiles are
+//                                                               added into the zeroed output by TMA reduce-add)
+// Structure: persistent CTAs, warp 0 TMA producer (four 128-byte-swizzled tiles per stage), warp 1 MMA issuer, warps 2..9
+// epilogue through shared memory + TMA store / reduce (same as qgemm2_sm100.cu).
+#include "tc05.cuh"
+#include <cuda_bf16.h>
+#include <cstdlib>
+#include <algorithm>
+
+namespace edadm {
+namespace g3 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                        // bf16 elements per K step (128 bytes)
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + EPI_WARPS * 32;
+constexpr int CHUNK = 32;
+constexpr int OUT_BUF_BYTES = BM * CHUNK * 4;
+constexpr int MAX_BN = 128;                   // 64 KB per stage (A_hi, A_lo, B_hi, B_lo) -> three stages; wider tiles would leave two
+constexpr int MAX_STAGES = 6;
+constexpr int ACC_STAGES = 2;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct Params {
+  int M, N, K;
+  int block_n, n_tiles, m_tiles, k_steps;     // k_steps per work unit
+  int splits;                                 // split-K factor (units = m_tiles * n_tiles * splits)
+  int stages, b_tile_bytes;
+  int reduce_add;                             // 1: partial tiles are ADDED into the output (TMA reduce), bias only from split 0
+  int group_m_tiles;                          // grouped (batched) GEMM: A rows come in groups of group_m_tiles tiles, group g multiplies
+  int group_b_rows;                           //   B rows [g * group_b_rows, (g + 1) * group_b_rows); 0 = one shared B
+  const float* bias;
+};
+
+struct __align__(8) Barriers {
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
+  uint64_t tmem_full[ACC_STAGES];
+  uint64_t tmem_empty[ACC_STAGES];
+  uint32_t tmem_base;
+};
+
+// instruction descriptor kind::f16: D fp32, A / B bf16, both K-major
+__device__ __forceinline__ uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                   const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                   const __grid_constant__ CUtensorMap map_out, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int a_tile = BM * BK * 2;                               // 16 KB
+  const int stage_bytes = 2 * a_tile + 2 * p.b_tile_bytes;      // A_hi, A_lo, B_hi, B_lo
+  uint8_t* out_buf = smem + p.stages * stage_bytes;
+  float* epi_bias = reinterpret_cast<float*>(out_buf + 2 * OUT_BUF_BYTES);
+  Barriers* bars = reinterpret_cast<Barriers*>(epi_bias + MAX_BN);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int units = p.m_tiles * p.n_tiles * p.splits;
+  const int stages = p.stages;
+  const uint32_t stage_tx = (uint32_t)(2 * a_tile + 2 * p.block_n * BK * 2);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_ah); tma_prefetch_desc(&map_al); tma_prefetch_desc(&map_bh); tma_prefetch_desc(&map_bl); tma_prefetch_desc(&map_out);
+    for (int i = 0; i < stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], EPI_WARPS); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  // unit -> (split, m tile, n tile); n fastest so that concurrently running CTAs share the A rows through L2
+  if (warp == 0) {
+    int stage = 0; uint32_t phase = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      const int n_blk = unit % p.n_tiles, rest = unit / p.n_tiles;
+      const int m_blk = rest % p.m_tiles, sp = rest / p.m_tiles;
+      const int k0 = sp * p.k_steps;
+      for (int ks = 0; ks < p.k_steps; ++ks) {
+        mbar_wait(&bars->empty[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* s = smem + stage * stage_bytes;
+          mbar_expect_tx(&bars->full[stage], stage_tx);
+          const int kc = (k0 + ks) * BK;
+          tma_load_2d(s, &map_ah, &bars->full[stage], kc, m_blk * BM);
+          tma_load_2d(s + a_tile, &map_al, &bars->full[stage], kc, m_blk * BM);
+          const int brow = n_blk * p.block_n + (p.group_m_tiles ? (m_blk / p.group_m_tiles) * p.group_b_rows : 0);
+          tma_load_2d(s + 2 * a_tile, &map_bh, &bars->full[stage], kc, brow);
+          tma_load_2d(s + 2 * a_tile + p.b_tile_bytes, &map_bl, &bars->full[stage], kc, brow);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16(BM, p.block_n);
+    const uint32_t base = smem_u32(smem);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
+      for (int ks = 0; ks < p.k_steps; ++ks) {
+        mbar_wait(&bars->full[stage], phase);
+        tc_fence_after();
+        const uint32_t s = base + stage * stage_bytes;
+        const uint64_t ah = make_smem_desc(s), al = make_smem_desc(s + a_tile);
+        const uint64_t bh = make_smem_desc(s + 2 * a_tile), bl = make_smem_desc(s + 2 * a_tile + p.b_tile_bytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {      // 16 bf16 = 32 bytes per MMA: descriptor start advances by 2 (x16 B)
+            umma_bf16(tmem_d, ah + 2 * kk, bh + 2 * kk, idesc, (ks | kk) ? 1u : 0u);
+            umma_bf16(tmem_d, ah + 2 * kk, bl + 2 * kk, idesc, 1u);
+            umma_bf16(tmem_d, al + 2 * kk, bh + 2 * kk, idesc, 1u);
+          }
+          umma_commit(&bars->empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&bars->tmem_full[acc]);
+      __syncwarp();
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const bool issuer = et == 0;
+    uint32_t st_off[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) st_off[k] = (uint32_t)r * 128u + ((uint32_t)((4 * half + k) ^ (r & 7)) << 4);
+    const int n_chunks = p.block_n / CHUNK;
+    int acc = 0; uint32_t acc_phase = 0; uint32_t gchunk = 0;
+    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+      const int n_blk = unit % p.n_tiles, rest = unit / p.n_tiles;
+      const int m_blk = rest % p.m_tiles, sp = rest / p.m_tiles;
+      const int n0 = n_blk * p.block_n;
+      for (int j = et; j < p.block_n; j += EPI_WARPS * 32)
+        epi_bias[j] = (p.bias && sp == 0 && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BN;
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      for (int ci = 0; ci < n_chunks; ++ci, ++gchunk) {
+        const int c0 = ci * CHUNK + 16 * half;
+        uint32_t a[16];
+        tmem_ld16(taddr + c0, a);
+        tmem_ld_wait();
+        if (ci == n_chunks - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+        }
+        uint8_t* ob = out_buf + (gchunk & 1u) * OUT_BUF_BYTES;
+        if (issuer) bulk_wait_read<1>();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<float4*>(ob + st_off[k]) = make_float4(__uint_as_float(a[4 * k + 0]) + epi_bias[c0 + 4 * k + 0],
+                                                                   __uint_as_float(a[4 * k + 1]) + epi_bias[c0 + 4 * k + 1],
+                                                                   __uint_as_float(a[4 * k + 2]) + epi_bias[c0 + 4 * k + 2],
+                                                                   __uint_as_float(a[4 * k + 3]) + epi_bias[c0 + 4 * k + 3]);
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (issuer) {
+          if (p.reduce_add) tma_reduce_add_2d(&map_out, ob, n0 + ci * CHUNK, m_blk * BM);
+          else tma_store_2d(&map_out, ob, n0 + ci * CHUNK, m_blk * BM);
+          bulk_commit();
+        }
+      }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+    if (issuer) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// x fp32 [rows][cols] -> hi = bf16(x), lo = bf16(x - hi) as [rows][cols_p] (nullable) and transposed [cols][rows_p] (nullable);
+// pitches in elements, multiples of 8 (16-byte TMA strides); padding columns are written as 0.
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ x, long long rows, long long cols, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                  long long cols_p, __nv_bfloat16* __restrict__ hi_t, __nv_bfloat16* __restrict__ lo_t, long long rows_p) {
+  __shared__ float tile[32][33];
+  // blockIdx.y = matrix of a batch: [batch][rows][cols] -> [batch][rows][cols_p] and / or [batch][cols][rows_p]
+  x += (long long)blockIdx.y * rows * cols;
+  if (hi) { hi += (long long)blockIdx.y * rows * cols_p; lo += (long long)blockIdx.y * rows * cols_p; }
+  if (hi_t) { hi_t += (long long)blockIdx.y * cols * rows_p; lo_t += (long long)blockIdx.y * cols * rows_p; }
+  const long long tiles_c = (cols_p + 31) / 32, tiles_r = (rows_p + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  for (long long t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+    const long long r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long r = r0 + ty + 8 * i, c = c0 + tx;
+      const float v = (r < rows && c < cols) ? __ldg(x + r * cols + c) : 0.f;
+      tile[ty + 8 * i][tx] = v;
+      if (hi && r < rows && c < cols_p) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[r * cols_p + c] = h;
+        lo[r * cols_p + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+      }
+    }
+    __syncthreads();
+    if (hi_t) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long c = c0 + ty + 8 * i, r = r0 + tx;      // output row = source column
+        if (c < cols && r < rows_p) {
+          const float v = tile[tx][ty + 8 * i];
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          hi_t[c * rows_p + r] = h;
+          lo_t[c * rows_p + r] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace g3
+}  // namespace edadm
+
+using namespace edadm;
+
+extern "C" int edadm_split_bf16_batched(const float* x, int64_t batch, int64_t rows, int64_t cols, void* hi, void* lo, int64_t cols_p,
+                                        void* hi_t, void* lo_t, int64_t rows_p, void* stream);
+
+extern "C" int edadm_split_bf16(const float* x, int64_t rows, int64_t cols, void* hi, void* lo, int64_t cols_p, void* hi_t, void* lo_t,
+                                int64_t rows_p, void* stream) {
+  return edadm_split_bf16_batched(x, 1, rows, cols, hi, lo, cols_p, hi_t, lo_t, rows_p, stream);
+}
+
+extern "C" int edadm_split_bf16_batched(const float* x, int64_t batch, int64_t rows, int64_t cols, void* hi, void* lo, int64_t cols_p,
+                                        void* hi_t, void* lo_t, int64_t rows_p, void* stream) {
+  if (!x || batch < 1 || batch > 65535 || rows < 1 || cols < 1 || (!hi && !hi_t) || (hi && !lo) || (hi_t && !lo_t)) return fail(EDADM_ERR_ARG, "split_bf16: bad arguments");
+  if ((hi && (cols_p < cols || (cols_p & 7))) || (hi_t && (rows_p < rows || (rows_p & 7)))) return fail(EDADM_ERR_ARG, "split_bf16: pitches must cover the data and be multiples of 8");
+  if (!hi) cols_p = cols;
+  if (!hi_t) rows_p = rows;
+  const long long tiles = ((cols_p + 31) / 32) * ((rows_p + 31) / 32);
+  const int gx = (int)std::min<long long>(tiles, std::max<long long>(1, (long long)sm_count() * 16 / batch));
+  dim3 grid(gx, (unsigned)batch);
+  g3::split_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, cols_p,
+                                                               (__nv_bfloat16*)hi_t, (__nv_bfloat16*)lo_t, rows_p);
+  return check_launch("split_bf16");
+}
+
+// out[M][N] fp32 (row pitch N) = (or +=, with reduce_add) A.B^T (+ bias) from the split operands: a_hi / a_lo bf16 [M][Kp], b_hi / b_lo
+// bf16 [N][Kp] (Kp: row pitch in elements, multiple of 8; K real reduction length; elements past K must be 0).  splits > 1 cuts the
+// reduction into `splits` work units per output tile that are ADDED into `out` (zero it first).
+extern "C" int edadm_gemm_bf16x3_grouped(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t groups, int64_t M,
+                                         int N, int64_t K, int64_t Kp, const float* bias, float* out, int splits, void* stream);
+
+extern "C" int edadm_gemm_bf16x3(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t M, int N, int64_t K,
+                                 int64_t Kp, const float* bias, float* out, int splits, void* stream) {
+  return edadm_gemm_bf16x3_grouped(a_hi, a_lo, b_hi, b_lo, 1, M, N, K, Kp, bias, out, splits, stream);
+}
+
+// groups > 1: batched product out[g][M][N] = a[g] . b[g]^T with a_* [groups*M][Kp], b_* [groups*N][Kp], out [groups*M][N]; M must be a
+// multiple of 128 so that no tile straddles two groups (the attention matmuls of the reconstruction loop: M = tokens).
+extern "C" int edadm_gemm_bf16x3_grouped(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t groups, int64_t M,
+                                         int N, int64_t K, int64_t Kp, const float* bias, float* out, int splits, void* stream) {
+  using namespace g3;
+  if (groups < 1 || (groups > 1 && (M % BM))) return fail(EDADM_ERR_ARG, "gemm_bf16x3: grouped product needs M %% 128 == 0 (M=%lld)", (long long)M);
+  const int64_t M_group = M;
+  M = M * groups;
+  if (!a_hi || !a_lo || !b_hi || !b_lo || !out) return fail(EDADM_ERR_ARG, "gemm_bf16x3: null pointer");
+  if (M < 1 || N < 1 || K < 1 || Kp < K || (Kp & 7) || (N & 3) || M > 0x7fffffffLL || splits < 1 || splits > 64)
+    return fail(EDADM_ERR_ARG, "gemm_bf16x3: bad sizes M=%lld N=%d K=%lld Kp=%lld splits=%d", (long long)M, N, (long long)K, (long long)Kp, splits);
+  if ((((uintptr_t)a_hi | (uintptr_t)a_lo | (uintptr_t)b_hi | (uintptr_t)b_lo | (uintptr_t)out) & 15)) return fail(EDADM_ERR_ARG, "gemm_bf16x3: operands must be 16-byte aligned");
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = N; p.K = (int)K;
+  p.m_tiles = (int)((M + BM - 1) / BM);
+  // N tile: multiple of 32, fewest waves then widest (stage size grows with it: 2 x 16 KB + 2 x block_n x 128 B)
+  int best = 0; long long best_cost = 0;
+  for (int bn = 32; bn <= MAX_BN; bn += 32) {
+    const long long tiles = (long long)p.m_tiles * ((N + bn - 1) / bn) * splits;
+    const long long waves = (tiles + sm_count() - 1) / sm_count();
+    const long long cost = waves * (bn + 128);
+    if (!best || cost <= best_cost) { best = bn; best_cost = cost; }
+    if (bn >= N) break;
+  }
+  p.block_n = best;
+  p.n_tiles = (N + best - 1) / best;
+  const int k_steps_total = (int)((K + BK - 1) / BK);
+  p.splits = std::min(splits, k_steps_total);
+  p.k_steps = (k_steps_total + p.splits - 1) / p.splits;
+  p.splits = (k_steps_total + p.k_steps - 1) / p.k_steps;       // no empty split (tiles past K would read zero-filled data anyway)
+  p.reduce_add = p.splits > 1 ? 1 : 0;
+  p.bias = bias;
+  p.group_m_tiles = groups > 1 ? (int)(M_group / BM) : 0;
+  p.group_b_rows = groups > 1 ? N : 0;
+  p.b_tile_bytes = (best * BK * 2 + 1023) & ~1023;
+  const int stage_bytes = 2 * BM * BK * 2 + 2 * p.b_tile_bytes;
+  const int fixed = 1024 + 2 * OUT_BUF_BYTES + MAX_BN * 4 + 1024;
+  p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - fixed) / stage_bytes);
+  if (p.stages < 2) return fail(EDADM_ERR_UNSUPPORTED, "gemm_bf16x3: tile does not fit");
+  const int smem_bytes = fixed + p.stages * stage_bytes;
+
+  CUtensorMap m_ah, m_al, m_bh, m_bl, m_out;
+  auto enc = [&](CUtensorMap* m, const void* ptr, long long rows, int box_rows, const char* what) {
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    return encode_map(m, ptr, 2, dims, strides, box, what, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+  int rc;
+  if ((rc = enc(&m_ah, a_hi, M, BM, "A hi")) || (rc = enc(&m_al, a_lo, M, BM, "A lo")) || (rc = enc(&m_bh, b_hi, (long long)N * groups, best, "B hi")) ||
+      (rc = enc(&m_bl, b_lo, (long long)N * groups, best, "B lo")))
+    return rc;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)N * 4};
+    cuuint32_t box[2] = {(cuuint32_t)CHUNK, (cuuint32_t)BM};
+    if ((rc = encode_map(&m_out, out, 2, dims, strides, box, "output", CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  static int attr_dev[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_dev[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) return fail(EDADM_ERR_CUDA, "gemm_bf16x3: cannot opt in to %d B shared memory: %s", SMEM_LIMIT, cudaGetErrorString(e));
+    attr_dev[dev] = 1;
+  }
+  const int units = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = std::min(units, sm_count());
+  gemm_bf16x3_kernel<<<grid, THREADS, smem_bytes, (cudaStream_t)stream>>>(m_ah, m_al, m_bh, m_bl, m_out, p);
+  return check_launch("gemm_bf16x3");
+}

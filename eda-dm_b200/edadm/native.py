@@ -38,6 +38,10 @@ _SIGNATURES = {
     "edadm_pack_weight": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P]),
     "edadm_qgemm_i8": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "edadm_qgemm_i8_codes": (c_int, [P, c_int64, c_int, P, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, P, P, c_int, P, c_int, P, P]),
+    "edadm_split_bf16": (c_int, [P, c_int64, c_int64, P, P, c_int64, P, P, c_int64, P]),
+    "edadm_gemm_bf16x3": (c_int, [P, P, P, P, c_int64, c_int, c_int64, c_int64, P, P, c_int, P]),
+    "edadm_split_bf16_batched": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_int64, P, P, c_int64, P]),
+    "edadm_gemm_bf16x3_grouped": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int64, c_int64, P, P, c_int, P]),
     "edadm_norm_act_pool2": (c_int, [P, P, P, c_int, P, c_int, c_int, c_int, c_int, P]),
     "edadm_upsample2x_codes": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P]),
     "edadm_layernorm_quant_rows": (c_int, [P, P, P, c_float, P, P, c_int64, c_int, c_int, P, P, c_int, P]),

@@ -724,3 +724,143 @@ def qattn_bnd_codes(qc, rq, kc, rk, v, heads, aquant: AttnQuant, sm_scale):
     return qattn(qc, kc, vc.reshape(BH, d, -1), rq, rk, rv.reshape(BH, d), heads, d, Tk, aquant, sm_scale, out,
                  (Tq * heads * d, d, heads * d, 1))
 
+
+# ------------------------------------------------------------------------------------------------
+# calibration path: fp32-accurate GEMM on the bf16 tensor cores (north_star (b))
+# ------------------------------------------------------------------------------------------------
+def split_bf16(x2d, straight=True, transposed=False):
+    """x fp32 [R, C] -> (hi, lo) bf16 [R, Cp] and / or (hi_t, lo_t) bf16 [C, Rp]: x = hi + lo to ~2^-17 relative."""
+    _need_cuda(x2d)
+    x2d = _f32c(x2d)
+    R, C = x2d.shape
+    Cp, Rp = _round_up(C, 8), _round_up(R, 8)
+    dev = x2d.device
+    hi = torch.empty((R, Cp), dtype=torch.bfloat16, device=dev) if straight else None
+    lo = torch.empty((R, Cp), dtype=torch.bfloat16, device=dev) if straight else None
+    hi_t = torch.empty((C, Rp), dtype=torch.bfloat16, device=dev) if transposed else None
+    lo_t = torch.empty((C, Rp), dtype=torch.bfloat16, device=dev) if transposed else None
+    lib.split_bf16(x2d.data_ptr(), R, C, _ptr(hi), _ptr(lo), Cp, _ptr(hi_t), _ptr(lo_t), Rp, _stream())
+    return hi, lo, hi_t, lo_t
+
+
+def gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, K, bias=None, splits=1):
+    """out fp32 [M, N] = a . b^T (+ bias) from split operands a_* [M, Kp], b_* [N, Kp] (three tcgen05 bf16 MMAs per K step)."""
+    M, Kp = a_hi.shape
+    N = b_hi.shape[0]
+    out = (torch.zeros if splits > 1 else torch.empty)((M, N), dtype=torch.float32, device=a_hi.device)
+    lib.gemm_bf16x3(a_hi.data_ptr(), a_lo.data_ptr(), b_hi.data_ptr(), b_lo.data_ptr(), M, N, int(K), Kp, _ptr(bias), out.data_ptr(),
+                    int(splits), _stream())
+    return out
+
+
+def _wgrad_splits(n_out, k_in, m_tokens):
+    tiles = ((n_out + 127) // 128) * ((k_in + 127) // 128)
+    return max(1, min(32, (2 * 148 + tiles - 1) // tiles, (m_tokens + 63) // 64))
+
+
+class LinearBf16x3Function(torch.autograd.Function):
+    """F.linear(x, w, bias) with forward, dgrad and wgrad on edadm_gemm_bf16x3 (one kernel, different operand copies)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        K = x.shape[-1]
+        x2 = x.reshape(-1, K)
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        xh, xl, xht, xlt = split_bf16(x2, True, need_dw)
+        wh, wl, wht, wlt = split_bf16(w, True, need_dx)
+        b = None if bias is None else _f32c(bias.detach())
+        y = gemm_bf16x3(xh, xl, wh, wl, K, bias=b)
+        ctx.save_for_backward(*(t for t in (xht, xlt, wht, wlt) if t is not None))
+        ctx.meta = (tuple(x.shape), tuple(w.shape), need_dx, need_dw, bias is not None)
+        return y.reshape(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        xshape, wshape, need_dx, need_dw, has_bias = ctx.meta
+        saved = list(ctx.saved_tensors)
+        xht, xlt = (saved.pop(0), saved.pop(0)) if need_dw else (None, None)
+        wht, wlt = (saved.pop(0), saved.pop(0)) if need_dx else (None, None)
+        N, K = wshape
+        g2 = _f32c(gy.reshape(-1, N))
+        M = g2.shape[0]
+        gh, gl, ght, glt = split_bf16(g2, need_dx, need_dw)
+        dx = dw = db = None
+        if need_dx:      # dX[M, K] = dY[M, N] . (W^T[K, N])^T
+            dx = gemm_bf16x3(gh, gl, wht, wlt, N).reshape(xshape)
+        if need_dw:      # dW[N, K] = dY^T[N, M] . (X^T[K, M])^T  -- long reduction over the tokens: split-K
+            dw = gemm_bf16x3(ght, glt, xht, xlt, M, splits=_wgrad_splits(N, K, M))
+        if has_bias and ctx.needs_input_grad[2]:
+            db = g2.sum(0)
+        return dx, dw, db
+
+
+def linear_bf16x3_ok(x, w):
+    return (x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and w.dim() == 2 and x.shape[-1] == w.shape[1]
+            and w.shape[0] % 4 == 0 and w.shape[1] % 8 == 0 and x.numel() // x.shape[-1] >= 64)
+
+
+def linear_bf16x3(x, w, bias=None):
+    return LinearBf16x3Function.apply(x, w, bias)
+
+
+def split_bf16_batched(x3d, straight=True, transposed=False):
+    """x fp32 [G, R, C] -> (hi, lo) bf16 [G, R, Cp] and / or (hi_t, lo_t) bf16 [G, C, Rp], every matrix of the batch on its own"""
+    _need_cuda(x3d)
+    x3d = _f32c(x3d)
+    G, R, C = x3d.shape
+    Cp, Rp = _round_up(C, 8), _round_up(R, 8)
+    dev = x3d.device
+    mk = lambda *s: torch.empty(s, dtype=torch.bfloat16, device=dev)
+    hi, lo = (mk(G, R, Cp), mk(G, R, Cp)) if straight else (None, None)
+    hi_t, lo_t = (mk(G, C, Rp), mk(G, C, Rp)) if transposed else (None, None)
+    lib.split_bf16_batched(x3d.data_ptr(), G, R, C, _ptr(hi), _ptr(lo), Cp, _ptr(hi_t), _ptr(lo_t), Rp, _stream())
+    return hi, lo, hi_t, lo_t
+
+
+def _bmm_nt_raw(a_hi, a_lo, b_hi, b_lo, K):
+    """out fp32 [G, M, N] = a[g] . b[g]^T from split operands a_* [G, M, Kp], b_* [G, N, Kp]"""
+    G, M, Kp = a_hi.shape
+    N = b_hi.shape[1]
+    out = torch.empty((G, M, N), dtype=torch.float32, device=a_hi.device)
+    lib.gemm_bf16x3_grouped(a_hi.data_ptr(), a_lo.data_ptr(), b_hi.data_ptr(), b_lo.data_ptr(), G, M, N, int(K), Kp, None, out.data_ptr(),
+                            1, _stream())
+    return out
+
+
+class BmmNTBf16x3Function(torch.autograd.Function):
+    """C[g] = A[g] . B[g]^T (A [G, M, K], B [G, N, K]) with both gradients on the grouped bf16 x 3 tensor-core GEMM:
+    dA = dC . B = NT(dC, B^T), dB = dC^T . A = NT(dC^T, A^T); the transposed copies come out of the same split pass."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        need_da, need_db = ctx.needs_input_grad
+        ah, al, aht, alt = split_bf16_batched(a, True, need_db)
+        bh, bl, bht, blt = split_bf16_batched(b, True, need_da)
+        ctx.save_for_backward(*(t for t in (aht, alt, bht, blt) if t is not None))
+        ctx.meta = (tuple(a.shape), tuple(b.shape), need_da, need_db)
+        return _bmm_nt_raw(ah, al, bh, bl, a.shape[2])
+
+    @staticmethod
+    def backward(ctx, gc):
+        ashape, bshape, need_da, need_db = ctx.meta
+        saved = list(ctx.saved_tensors)
+        aht, alt = (saved.pop(0), saved.pop(0)) if need_db else (None, None)
+        bht, blt = (saved.pop(0), saved.pop(0)) if need_da else (None, None)
+        gh, gl, ght, glt = split_bf16_batched(gc, need_da, need_db)
+        da = _bmm_nt_raw(gh, gl, bht, blt, bshape[1]) if need_da else None          # [G, M, K] = dC[M, N] . (B^T[K, N])^T
+        db = _bmm_nt_raw(ght, glt, aht, alt, ashape[1]) if need_db else None        # [G, N, K] = dC^T[N, M] . (A^T[K, M])^T
+        return da, db
+
+
+def bmm_nt_bf16x3_ok(a, b):
+    """shapes the grouped kernel covers: every product (forward and both gradients) needs its row count to be a multiple of 128
+    and its output pitch a multiple of 4"""
+    if not (a.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32 and a.dim() == 3 and b.dim() == 3 and a.shape[0] == b.shape[0]):
+        return False
+    M, K, N = a.shape[1], a.shape[2], b.shape[1]
+    return M % 128 == 0 and N % 128 == 0 and K % 4 == 0 and N % 4 == 0 and a.shape[2] == b.shape[2]
+
+
+def bmm_nt_bf16x3(a, b):
+    return BmmNTBf16x3Function.apply(a, b)
+

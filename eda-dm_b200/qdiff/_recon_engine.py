@@ -345,6 +345,7 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
     if side is not None:
         side.wait_stream(torch.cuda.current_stream(device))
     stream_ctx = torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
+    backend.in_recon = True
     with stream_ctx:
         for it in range(iters):
             if use_graph and graph is None and it == n_eager:
@@ -361,6 +362,9 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
                 qdist.barrier()
                 torch.cuda.synchronize()
                 timing['start'].record()
+            prof = timing is not None and timing.get('profile_iter') == it
+            if prof:                                    # ncu --profile-from-start off: exactly this iteration is captured
+                torch.cuda.synchronize(); torch.cuda.profiler.start()
             if device_state:
                 if graph:
                     graph.replay()
@@ -380,10 +384,13 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
                             sched.step()
                 if return_losses:
                     losses.append(loss_out.clone())
+            if prof:
+                torch.cuda.synchronize(); torch.cuda.profiler.stop()
             if timing is not None and 'grad_norms' in timing:
                 timing['grad_norms'].append(gnorm_out.clone())
         if timing is not None and 'start' in timing:
             timing['end'].record()
+    backend.in_recon = False
     if side is not None:
         torch.cuda.current_stream(device).wait_stream(side)
 

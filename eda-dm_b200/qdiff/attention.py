@@ -17,6 +17,12 @@ from .quant_layer import _library_fwd, backend
 
 
 def _bmm(a, b):
+    """a [G, M, K] @ b [G, K, N] on the calibration path.  Inside the reconstruction loop the product (and its two gradients) runs on
+    the grouped bf16 x 3 tcgen05 GEMM whenever the shapes allow (edadm_gemm_bf16x3_grouped); otherwise library fp32."""
+    if backend.calib_gemm_bf16x3 and backend.in_recon and a.is_cuda:
+        bt = b.transpose(1, 2)                     # [G, N, K]: K-contiguous for k^T views, a copy otherwise (inside the split pass)
+        if ops.bmm_nt_bf16x3_ok(a, bt):
+            return ops.bmm_nt_bf16x3(a, bt)
     return _library_fwd(lambda x, w, _b: th.bmm(x, w), a, b, None, {})
 
 

@@ -39,6 +39,8 @@ class _Backend:
     recon_cuda_graph = True  # capture the reconstruction iteration in one CUDA graph after 3 eager iterations
     recon_graph_checkpointed = True   # ... including units whose backward recomputes the forward (transformer / attention blocks)
     recon_overlap_allreduce = True    # data parallel: all-reduce each alpha gradient as soon as its backward has produced it
+    calib_gemm_bf16x3 = True          # linears of the reconstruction loop (fwd / dgrad / wgrad) on edadm_gemm_bf16x3 instead of cuBLAS fp32
+    in_recon = False                  # set by the reconstruction engine around its loop (FP-target forwards included)
     cache_prefix_reuse = True         # calibration cache builder keeps the network state at the frontier of the finished units (f2)
     recon_overlap_fp = False  # ... with the FP forward on a forked stream (a parallel graph branch): +4 % on a church
                               # 16x16 ResBlock, -23 % on an ImageNet 32x32 one (measured), hence opt-in
@@ -768,6 +770,10 @@ def _library_fwd(fn, input, weight, bias, kwargs):
     layer (<= 4 channels, its input is never quantized) takes the dedicated stencil kernel when no gradient is needed."""
     if fn is F.conv2d and ops.conv3x3_small_n_ok(input, weight, kwargs):
         return ops.conv3x3_small_n(input, weight, bias)
+    if (fn is F.linear and backend.calib_gemm_bf16x3 and ops.linear_bf16x3_ok(input, weight) and
+            (backend.in_recon or (torch.is_grad_enabled() and (input.requires_grad or weight.requires_grad)))):
+        # the reconstruction loop's linears (forward, dgrad, wgrad): hand-written tcgen05 GEMM, bf16 x 3 split, fp32 accumulation
+        return ops.linear_bf16x3(input, weight, bias)
     if not input.is_cuda or backend.allow_tf32:
         return fn(input, weight, bias, **kwargs)
     prev_c, prev_m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32

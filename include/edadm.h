@@ -164,6 +164,26 @@ int edadm_qgemm_i8_codes(const uint8_t* q, int64_t M, int Kp_act, const int8_t* 
                          const int32_t* cw, const int32_t* rowsum, const float* bias, int geglu, const float* q_delta,
                          const float* q_zp, int q_levels, uint8_t* out_codes, int out_pitch, int32_t* q_rowsum, void* stream);
 
+/* ---- calibration path (north_star (b)): fp32-accurate GEMM on the bf16 tensor cores ---------------------------------------
+ * Replaces the fp32 library GEMM behind `self.fwd_func(input, weight, bias)` (qdiff/quant_layer.py:434) and its autograd
+ * dgrad / wgrad while gradients flow (block_reconstruction, qdiff/block_recon.py:152-197).  edadm_split_bf16 writes
+ * hi = bf16(x), lo = bf16(x - hi) of an fp32 matrix [rows][cols] as [rows][cols_p] and / or transposed [cols][rows_p] (pitches in
+ * elements, multiples of 8, padding zeroed; pass NULL for the pair that is not needed).  edadm_gemm_bf16x3 evaluates
+ *   out[M][N] = a.b^T (+ bias[n]),  a.b^T := a_hi.b_hi^T + a_hi.b_lo^T + a_lo.b_hi^T   (fp32 accumulation in TMEM)
+ * from K-contiguous bf16 operands a_* [M][Kp], b_* [N][Kp]; forward, dgrad and wgrad differ only in which copies are passed
+ * (see csrc/gemm_bf16x3_sm100.cu).  splits > 1: split-K, partial tiles are added into `out` (must be zeroed) by TMA reduce. */
+int edadm_split_bf16(const float* x, int64_t rows, int64_t cols, void* hi, void* lo, int64_t cols_p, void* hi_t, void* lo_t,
+                     int64_t rows_p, void* stream);
+int edadm_gemm_bf16x3(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t M, int N, int64_t K,
+                      int64_t Kp, const float* bias, float* out, int splits, void* stream);
+/* Batched forms for the attention matmuls of the reconstruction loop (th.bmm / einsum of qdiff/quant_block.py:128-139, :157-162,
+ * :214-233, :431-445 under autograd): x [batch][rows][cols] split per matrix; out[g] = a[g].b[g]^T for `groups` matrices stacked
+ * along the rows (a_* [groups*M][Kp], b_* [groups*N][Kp], out [groups*M][N]; M % 128 == 0).                               */
+int edadm_split_bf16_batched(const float* x, int64_t batch, int64_t rows, int64_t cols, void* hi, void* lo, int64_t cols_p,
+                             void* hi_t, void* lo_t, int64_t rows_p, void* stream);
+int edadm_gemm_bf16x3_grouped(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t groups, int64_t M,
+                              int N, int64_t K, int64_t Kp, const float* bias, float* out, int splits, void* stream);
+
 /* W4 storage: the same GEMM with the weights kept as 4-bit codes, two per byte -- wq4 u8 [Np][R*S][Cp/2] (Cp % 32 == 0; inside
  * each 32-bit word byte j = code[c0+j] | code[c0+4+j] << 4), zoff[n] = zp[n] -- and unpacked to s8 (code - zoff[n]) in
  * shared memory by dedicated warps of the GEMM kernel, tile by tile, ahead of the tensor-core MMA.  Replaces the same

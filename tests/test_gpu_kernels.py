@@ -808,3 +808,53 @@ def test_scale_search_kernel_equals_tensor_op_search(cuda, channel_wise, bits, s
             backend.search_kernel = True
         res.append((q.delta.detach().clone(), q.zero_point.clone()))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+@pytest.mark.parametrize("M,K,N,bias", [(4096, 384, 384, True), (8192, 384, 3072, False), (2048, 1536, 384, True), (300, 96, 100, True),
+                                        (65536, 320, 64, False)])
+def test_linear_bf16x3_forward_and_gradients(cuda, M, K, N, bias):
+    """calibration-path GEMM (bf16 x 3 split on tcgen05, fp32 accumulation): forward, dgrad and wgrad (split-K + TMA reduce) against
+    an fp64 reference -- far inside north_star's 1e-3, two orders of magnitude tighter than TF32"""
+    from edadm import ops
+    g = torch.Generator().manual_seed(M + N)
+    x = (torch.randn(M, K, generator=g) * 1.7).to(cuda).requires_grad_(True)
+    w = (torch.randn(N, K, generator=g) * 0.08).to(cuda).requires_grad_(True)
+    b = torch.randn(N, generator=g).to(cuda).requires_grad_(True) if bias else None
+    gy = torch.randn(M, N, generator=g).to(cuda)
+    y = ops.linear_bf16x3(x, w, b)
+    y.backward(gy)
+    xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    bd = b.detach().double().requires_grad_(True) if bias else None
+    yd = F.linear(xd, wd, bd)
+    yd.backward(gy.double())
+    assert _rel_l2(y.detach().double(), yd.detach()) < 2e-5
+    assert _rel_l2(x.grad.double(), xd.grad) < 2e-5
+    assert _rel_l2(w.grad.double(), wd.grad) < 2e-5
+    if bias:
+        assert _rel_l2(b.grad.double(), bd.grad) < 1e-5
+    # for scale: the same product in TF32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        e_tf32 = _rel_l2(F.linear(x.detach(), w.detach()).double(), F.linear(xd.detach(), wd.detach()))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = False
+    print(f"forward rel-L2 vs fp64: bf16x3 {_rel_l2((y.detach() - (b.detach() if bias else 0)).double(), F.linear(xd.detach(), wd.detach())):.1e}, TF32 {e_tf32:.1e}")
+
+
+@pytest.mark.parametrize("G,M,N,K", [(8, 256, 256, 384), (3, 1024, 1024, 96), (16, 128, 384, 256), (2, 256, 128, 1024)])
+def test_bmm_nt_bf16x3_forward_and_gradients(cuda, G, M, N, K):
+    """grouped calibration-path product C[g] = A[g] . B[g]^T (attention Q.K^T and P.V under autograd) vs fp64"""
+    from edadm import ops
+    g = torch.Generator().manual_seed(G * 7 + K)
+    a = torch.randn(G, M, K, generator=g).to(cuda).requires_grad_(True)
+    b = (torch.randn(G, N, K, generator=g) * 0.5).to(cuda).requires_grad_(True)
+    gc = torch.randn(G, M, N, generator=g).to(cuda)
+    assert ops.bmm_nt_bf16x3_ok(a, b)
+    c = ops.bmm_nt_bf16x3(a, b)
+    c.backward(gc)
+    ad, bd = a.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    cd = torch.bmm(ad, bd.transpose(1, 2))
+    cd.backward(gc.double())
+    assert _rel_l2(c.detach().double(), cd.detach()) < 2e-5
+    assert _rel_l2(a.grad.double(), ad.grad) < 2e-5
+    assert _rel_l2(b.grad.double(), bd.grad) < 2e-5

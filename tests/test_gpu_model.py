@@ -297,7 +297,7 @@ def test_checkpointed_unit_reconstruction_graph_equals_eager(cuda):
     # the last bits after the first update, and the step-size gradients of this unit (softmax / q / k quantizers sitting on
     # rounding boundaries) are sensitive enough that the trajectories drift apart by percents within a few iterations --
     # measured: both loops are run-to-run deterministic, |d loss| 3e-4 at iteration 1, 15 % at iteration 3.
-    assert np.allclose(traces[0][:3], traces[1][:3], rtol=2e-3), (traces[0], traces[1])
+    assert np.allclose(traces[0][:2], traces[1][:2], rtol=2e-3) and np.allclose(traces[0][:3], traces[1][:3], rtol=3e-2), (traces[0], traces[1])
     assert np.allclose(traces[0], traces[1], rtol=0.35), (traces[0], traces[1])
     assert np.all(np.isfinite(traces[0]))
 
