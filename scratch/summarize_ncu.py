@@ -76,12 +76,13 @@ def launch_list(path, out_csv, out_json):
     json.dump({"total_us": round(tot, 1), "kernels": summ}, open(out_json, "w"), indent=1)
     for k, v in list(summ.items())[:8]: print(k, v)
 
-G = os.path.join(ROOT, "gpurun_out")
-launch_list(os.path.join(G, "launches_church_dram.csv"), os.path.join(ROOT, "profiles", f"launches_{TAG}_church_b100_eager_step_final.csv"),
-            os.path.join(ROOT, "profiles", f"launches_{TAG}_church_b100_summary.json"))
-if os.path.exists(os.path.join(G, "launches_imagenet_dram.csv")):
-    launch_list(os.path.join(G, "launches_imagenet_dram.csv"), os.path.join(ROOT, "profiles", f"launches_{TAG}_imagenet_b128_eager_step_final.csv"),
-                os.path.join(ROOT, "profiles", f"launches_{TAG}_imagenet_b128_summary.json"))
-summarize(os.path.join(G, "qgemm_c192.ncu-rep"), "qgemm", "church 32x32 conv 3x3, 192->192 channels, batch 100 (M=102400, N=192, K=1728)")
-summarize(os.path.join(G, "qattn_t1024.ncu-rep"), "qattn", "church attention, 800 (batch x heads) x 1024 tokens x 24 channels")
-summarize(os.path.join(G, "actq_tma.ncu-rep"), "actq", "activation producer [128,192,64,64] fp32 -> u8 NHWC codes + halo")
+if __name__ == "__main__":
+    G = os.path.join(ROOT, "gpurun_out")
+    launch_list(os.path.join(G, "launches_church_dram.csv"), os.path.join(ROOT, "profiles", f"launches_{TAG}_church_b100_eager_step_final.csv"),
+                os.path.join(ROOT, "profiles", f"launches_{TAG}_church_b100_summary.json"))
+    if os.path.exists(os.path.join(G, "launches_imagenet_dram.csv")):
+        launch_list(os.path.join(G, "launches_imagenet_dram.csv"), os.path.join(ROOT, "profiles", f"launches_{TAG}_imagenet_b128_eager_step_final.csv"),
+                    os.path.join(ROOT, "profiles", f"launches_{TAG}_imagenet_b128_summary.json"))
+    summarize(os.path.join(G, "qgemm_c192.ncu-rep"), "qgemm", "church 32x32 conv 3x3, 192->192 channels, batch 100 (M=102400, N=192, K=1728)")
+    summarize(os.path.join(G, "qattn_t1024.ncu-rep"), "qattn", "church attention, 800 (batch x heads) x 1024 tokens x 24 channels")
+    summarize(os.path.join(G, "actq_tma.ncu-rep"), "actq", "activation producer [128,192,64,64] fp32 -> u8 NHWC codes + halo")
