@@ -45,6 +45,9 @@ struct Params {
   int reduce_add;                             // 1: partial tiles are ADDED into the output (TMA reduce), bias only from split 0
   int group_m_tiles;                          // grouped (batched) GEMM: A rows come in groups of group_m_tiles tiles, group g multiplies
   int group_b_rows;                           //   B rows [g * group_b_rows, (g + 1) * group_b_rows); 0 = one shared B
+  // convolution mode (conv = 1): A is the halo-padded NHWC tensor [B][Hp][Wp][Cp] read through rank-4 maps, one filter tap x 64
+  // channels per K step (implicit GEMM, as qgemm2_sm100.cu); B is [N][taps * C]; the output is NCHW through a rank-3 map
+  int conv, taps, S, c_chunks, C, Wo, HoWo, out_hw, pxb, px_shift;
   const float* bias;
 };
 
@@ -117,9 +120,18 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
         if (elect_one()) {
           uint8_t* s = smem + stage * stage_bytes;
           mbar_expect_tx(&bars->full[stage], stage_tx);
-          const int kc = (k0 + ks) * BK;
-          tma_load_2d(s, &map_ah, &bars->full[stage], kc, m_blk * BM);
-          tma_load_2d(s + a_tile, &map_al, &bars->full[stage], kc, m_blk * BM);
+          int kc = (k0 + ks) * BK;
+          if (p.conv) {
+            const int tap = ks / p.c_chunks, cc = ks - tap * p.c_chunks;
+            const int kh = tap / p.S, kw = tap - kh * p.S;
+            const int m0 = m_blk * BM, b0 = m0 / p.HoWo, rem = m0 - b0 * p.HoWo, oh0 = rem / p.Wo, ow0 = rem - oh0 * p.Wo;
+            tma_load_4d(s, &map_ah, &bars->full[stage], cc * BK, ow0 + kw, oh0 + kh, b0);
+            tma_load_4d(s + a_tile, &map_al, &bars->full[stage], cc * BK, ow0 + kw, oh0 + kh, b0);
+            kc = tap * p.C + cc * BK;           // weights are [N][tap][channel]
+          } else {
+            tma_load_2d(s, &map_ah, &bars->full[stage], kc, m_blk * BM);
+            tma_load_2d(s + a_tile, &map_al, &bars->full[stage], kc, m_blk * BM);
+          }
           const int brow = n_blk * p.block_n + (p.group_m_tiles ? (m_blk / p.group_m_tiles) * p.group_b_rows : 0);
           tma_load_2d(s + 2 * a_tile, &map_bh, &bars->full[stage], kc, brow);
           tma_load_2d(s + 2 * a_tile + p.b_tile_bytes, &map_bl, &bars->full[stage], kc, brow);
@@ -167,6 +179,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
     uint32_t st_off[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) st_off[k] = (uint32_t)r * 128u + ((uint32_t)((4 * half + k) ^ (r & 7)) << 4);
+    // convolution mode: NCHW staging [image][column][pixel] (see qgemm2_sm100.cu)
+    const uint32_t nchw_cstride = (uint32_t)p.pxb * 4u;
+    const uint32_t nchw_off = p.conv ? ((uint32_t)((r >> p.px_shift) * CHUNK + 16 * half) * p.pxb + (r & (p.pxb - 1))) * 4u : 0u;
     const int n_chunks = p.block_n / CHUNK;
     int acc = 0; uint32_t acc_phase = 0; uint32_t gchunk = 0;
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
@@ -192,16 +207,24 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
         uint8_t* ob = out_buf + (gchunk & 1u) * OUT_BUF_BYTES;
         if (issuer) bulk_wait_read<1>();
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (p.conv) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          *reinterpret_cast<float4*>(ob + st_off[k]) = make_float4(__uint_as_float(a[4 * k + 0]) + epi_bias[c0 + 4 * k + 0],
-                                                                   __uint_as_float(a[4 * k + 1]) + epi_bias[c0 + 4 * k + 1],
-                                                                   __uint_as_float(a[4 * k + 2]) + epi_bias[c0 + 4 * k + 2],
-                                                                   __uint_as_float(a[4 * k + 3]) + epi_bias[c0 + 4 * k + 3]);
+          for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(ob + nchw_off + j * nchw_cstride) = __uint_as_float(a[j]) + epi_bias[c0 + j];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(ob + st_off[k]) = make_float4(__uint_as_float(a[4 * k + 0]) + epi_bias[c0 + 4 * k + 0],
+                                                                     __uint_as_float(a[4 * k + 1]) + epi_bias[c0 + 4 * k + 1],
+                                                                     __uint_as_float(a[4 * k + 2]) + epi_bias[c0 + 4 * k + 2],
+                                                                     __uint_as_float(a[4 * k + 3]) + epi_bias[c0 + 4 * k + 3]);
+        }
         fence_proxy_async();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (issuer) {
-          if (p.reduce_add) tma_reduce_add_2d(&map_out, ob, n0 + ci * CHUNK, m_blk * BM);
+          if (p.conv) {
+            const int m0 = m_blk * BM, img0 = m0 / p.out_hw;
+            tma_store_3d(&map_out, ob, m0 - img0 * p.out_hw, n0 + ci * CHUNK, img0);
+          } else if (p.reduce_add) tma_reduce_add_2d(&map_out, ob, n0 + ci * CHUNK, m_blk * BM);
           else tma_store_2d(&map_out, ob, n0 + ci * CHUNK, m_blk * BM);
           bulk_commit();
         }
@@ -371,3 +394,140 @@ extern "C" int edadm_gemm_bf16x3_grouped(const void* a_hi, const void* a_lo, con
   gemm_bf16x3_kernel<<<grid, THREADS, smem_bytes, (cudaStream_t)stream>>>(m_ah, m_al, m_bh, m_bl, m_out, p);
   return check_launch("gemm_bf16x3");
 }
+
+namespace edadm {
+namespace g3 {
+// x fp32 [B][C][H][W] -> hi / lo bf16 [B][H+2p][W+2p][Cp] (halo and padded channels = 0): NHWC operands of the implicit-GEMM
+// convolution.  One block per (image, row): [C][W] -> [W][C] through shared memory.
+__global__ void __launch_bounds__(256)
+split_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int C, int H, int W, int Cp,
+                       int pad) {
+  __shared__ float tile[32][33];
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const int b = blockIdx.y, hp = blockIdx.x;                    // hp over padded rows
+  const int h = hp - pad;
+  __nv_bfloat16* hrow = hi + ((size_t)b * Hp + hp) * Wp * Cp;
+  __nv_bfloat16* lrow = lo + ((size_t)b * Hp + hp) * Wp * Cp;
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  if (h < 0 || h >= H) {                                        // halo row
+    for (int i = threadIdx.x; i < Wp * Cp; i += blockDim.x) { hrow[i] = zero; lrow[i] = zero; }
+    return;
+  }
+  for (int i = threadIdx.x; i < pad * Cp; i += blockDim.x) {    // halo columns
+    hrow[i] = zero; lrow[i] = zero;
+    hrow[(size_t)(W + pad) * Cp + i] = zero; lrow[(size_t)(W + pad) * Cp + i] = zero;
+  }
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* src = x + ((size_t)b * C * H + h) * W;           // + c * H * W + w
+  for (int c0 = 0; c0 < Cp; c0 += 32)
+    for (int w0 = 0; w0 < W; w0 += 32) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, w = w0 + tx;
+        tile[ty + 8 * i][tx] = (c < C && w < W) ? __ldg(src + (size_t)c * H * W + w) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int w = w0 + ty + 8 * i, c = c0 + tx;
+        if (w < W && c < Cp) {
+          const float v = tile[tx][ty + 8 * i];
+          const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+          const size_t o = (size_t)(w + pad) * Cp + c;
+          hrow[o] = hv;
+          lrow[o] = __float2bfloat16_rn(v - __bfloat162float(hv));
+        }
+      }
+      __syncthreads();
+    }
+}
+}  // namespace g3
+}  // namespace edadm
+
+extern "C" int edadm_split_nhwc_bf16(const float* x, void* hi, void* lo, int B, int C, int H, int W, int Cp, int pad, void* stream) {
+  if (!x || !hi || !lo || B < 1 || B > 65535 || C < 1 || H < 1 || W < 1 || Cp < C || (Cp & 7) || pad < 0)
+    return fail(EDADM_ERR_ARG, "split_nhwc_bf16: bad arguments");
+  dim3 grid((unsigned)(H + 2 * pad), (unsigned)B);
+  g3::split_nhwc_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, C, H, W, Cp, pad);
+  return check_launch("split_nhwc_bf16");
+}
+
+// Stride-1 convolution forward on the bf16 x 3 GEMM: a_hi / a_lo NHWC bf16 [B][Hp][Wp][Cp] (halo included, edadm_split_nhwc_bf16),
+// w_hi / w_lo bf16 [N][R*S*C] (tap-major, channel-minor; row pitch Kp elements), out fp32 NCHW [B][N][Ho][Wo].
+extern "C" int edadm_conv_bf16x3(const void* a_hi, const void* a_lo, int B, int Hp, int Wp, int Cp, const void* w_hi, const void* w_lo, int N,
+                                 int R, int S, int C, int64_t Kp, const float* bias, float* out, void* stream) {
+  using namespace g3;
+  if (!a_hi || !a_lo || !w_hi || !w_lo || !out) return fail(EDADM_ERR_ARG, "conv_bf16x3: null pointer");
+  const int Ho = Hp - R + 1, Wo = Wp - S + 1;
+  if (B < 1 || Ho < 1 || Wo < 1 || N < 1 || (Cp & 7) || Cp < C || (C & 7) || Kp < (int64_t)R * S * C || (Kp & 7))
+    return fail(EDADM_ERR_ARG, "conv_bf16x3: bad geometry");
+  const long long M = (long long)B * Ho * Wo;
+  const int out_hw = Ho * Wo;
+  int box_w, box_h, box_b;
+  if (Wo >= BM) { if (Wo % BM) return fail(EDADM_ERR_UNSUPPORTED, "conv_bf16x3: output width"); box_w = BM; box_h = 1; box_b = 1; }
+  else {
+    if (BM % Wo) return fail(EDADM_ERR_UNSUPPORTED, "conv_bf16x3: output width %d does not divide 128", Wo);
+    box_w = Wo;
+    const int rows = BM / Wo;
+    if (rows <= Ho) { if (Ho % rows) return fail(EDADM_ERR_UNSUPPORTED, "conv_bf16x3: output height"); box_h = rows; box_b = 1; }
+    else { if (rows % Ho) return fail(EDADM_ERR_UNSUPPORTED, "conv_bf16x3: output height"); box_h = Ho; box_b = rows / Ho; }
+  }
+  if (out_hw % 4) return fail(EDADM_ERR_UNSUPPORTED, "conv_bf16x3: output pitch");
+  const int pxb = out_hw >= BM ? BM : out_hw;
+  if ((out_hw >= BM ? out_hw % BM : BM % out_hw) || (pxb & (pxb - 1)) || M % BM) return fail(EDADM_ERR_UNSUPPORTED, "conv_bf16x3: tile geometry");
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = N; p.K = R * S * C;
+  p.m_tiles = (int)(M / BM);
+  int best = 0; long long best_cost = 0;
+  for (int bn = 32; bn <= MAX_BN; bn += 32) {
+    const long long tiles = (long long)p.m_tiles * ((N + bn - 1) / bn);
+    const long long waves = (tiles + sm_count() - 1) / sm_count();
+    const long long cost = waves * (bn + 128);
+    if (!best || cost <= best_cost) { best = bn; best_cost = cost; }
+    if (bn >= N) break;
+  }
+  p.block_n = best; p.n_tiles = (N + best - 1) / best;
+  p.conv = 1; p.taps = R * S; p.S = S; p.C = C; p.c_chunks = (C + BK - 1) / BK;
+  p.k_steps = p.taps * p.c_chunks; p.splits = 1;
+  p.Wo = Wo; p.HoWo = Ho * Wo; p.out_hw = out_hw; p.pxb = pxb;
+  while ((1 << p.px_shift) < pxb) ++p.px_shift;
+  p.bias = bias;
+  p.b_tile_bytes = (best * BK * 2 + 1023) & ~1023;
+  const int stage_bytes = 2 * BM * BK * 2 + 2 * p.b_tile_bytes;
+  const int fixed = 1024 + 2 * OUT_BUF_BYTES + MAX_BN * 4 + 1024;
+  p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - fixed) / stage_bytes);
+  const int smem_bytes = fixed + p.stages * stage_bytes;
+  CUtensorMap m_ah, m_al, m_bh, m_bl, m_out;
+  int rc;
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)Wp * Cp * 2, (cuuint64_t)Hp * Wp * Cp * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_b};
+    if ((rc = encode_map(i ? &m_al : &m_ah, i ? a_lo : a_hi, 4, dims, strides, box, "conv activations", CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)best};
+    if ((rc = encode_map(i ? &m_bl : &m_bh, i ? w_lo : w_hi, 2, dims, strides, box, "conv weights", CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)out_hw, (cuuint64_t)N, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)out_hw * 4, (cuuint64_t)N * out_hw * 4};
+    cuuint32_t box[3] = {(cuuint32_t)pxb, (cuuint32_t)CHUNK, (cuuint32_t)(BM / pxb)};
+    if ((rc = encode_map(&m_out, out, 3, dims, strides, box, "conv output", CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  }
+  static int attr_dev[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_dev[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) return fail(EDADM_ERR_CUDA, "conv_bf16x3: cannot opt in to %d B shared memory: %s", SMEM_LIMIT, cudaGetErrorString(e));
+    attr_dev[dev] = 1;
+  }
+  const int units = p.m_tiles * p.n_tiles;
+  gemm_bf16x3_kernel<<<std::min(units, sm_count()), THREADS, smem_bytes, (cudaStream_t)stream>>>(m_ah, m_al, m_bh, m_bl, m_out, p);
+  return check_launch("conv_bf16x3");
+}
+

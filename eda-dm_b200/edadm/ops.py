@@ -803,6 +803,92 @@ def linear_bf16x3(x, w, bias=None):
     return LinearBf16x3Function.apply(x, w, bias)
 
 
+def split_nhwc_bf16(x, pad):
+    """x fp32 NCHW -> (hi, lo) bf16 NHWC [B, H + 2 pad, W + 2 pad, Cp] with a zero halo"""
+    _need_cuda(x)
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    Cp = _round_up(C, 8)
+    hi = torch.empty((B, H + 2 * pad, W + 2 * pad, Cp), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi)
+    lib.split_nhwc_bf16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), B, C, H, W, Cp, pad, _stream())
+    return hi, lo
+
+
+def _conv_bf16x3_raw(x, w_taps, n_out, R, S, c_in, pad, bias=None):
+    """x fp32 NCHW, w_taps fp32 [n_out, R*S*c_in] (tap-major) -> fp32 NCHW, stride 1"""
+    xh, xl = split_nhwc_bf16(x, pad)
+    wh, wl, _, _ = split_bf16(w_taps)
+    B, Hp, Wp, Cp = xh.shape
+    out = torch.empty((B, n_out, Hp - R + 1, Wp - S + 1), dtype=torch.float32, device=x.device)
+    lib.conv_bf16x3(xh.data_ptr(), xl.data_ptr(), B, Hp, Wp, Cp, wh.data_ptr(), wl.data_ptr(), n_out, R, S, c_in, wh.shape[1],
+                    _ptr(bias), out.data_ptr(), _stream())
+    return out
+
+
+class ConvBf16x3Function(torch.autograd.Function):
+    """F.conv2d(x, w, bias, stride=1, padding=(R-1)/2) with forward and dgrad on edadm_conv_bf16x3 (dgrad = the same convolution
+    of dY with the flipped, transposed filter); wgrad stays on the fp32 library kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        N, C, R, S = w.shape
+        y = _conv_bf16x3_raw(x, w.permute(0, 2, 3, 1).reshape(N, R * S * C), N, R, S, C, (R - 1) // 2,
+                             None if bias is None else _f32c(bias.detach()))
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        N, C, R, S = w.shape
+        gy = _f32c(gy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wt = w.flip(2, 3).permute(1, 2, 3, 0).reshape(C, R * S * N)
+            dx = _conv_bf16x3_raw(gy, wt, C, R, S, N, (R - 1) // 2)
+        if ctx.needs_input_grad[1]:
+            prev = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = False
+            try:
+                pad = (R - 1) // 2
+                dw = torch.ops.aten.convolution_backward(gy, x, w, None, [1, 1], [pad, pad], [1, 1], False, [0, 0], 1,
+                                                         [False, True, False])[1]
+            finally:
+                torch.backends.cudnn.allow_tf32 = prev
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = gy.sum((0, 2, 3))
+        return dx, dw, db
+
+
+def conv_bf16x3_ok(x, w, kwargs):
+    """stride-1 'same' convolutions whose 128-pixel tiles form a W x H x B box, both for the forward and for the dgrad"""
+    if not (x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and x.dim() == 4 and w.dim() == 4):
+        return False
+    st, pd, dl, gr = kwargs.get("stride", 1), kwargs.get("padding", 0), kwargs.get("dilation", 1), kwargs.get("groups", 1)
+    as2 = lambda v: (v, v) if isinstance(v, int) else tuple(v)
+    N, C, R, S = w.shape
+    if as2(st) != (1, 1) or as2(dl) != (1, 1) or gr != 1 or R != S or R % 2 == 0 or as2(pd) != ((R - 1) // 2,) * 2:
+        return False
+    B, _, H, W = x.shape
+    if C % 8 or N % 8 or x.shape[1] != C or (B * H * W) % 128 or (H * W) % 4:
+        return False
+    hw = H * W
+    if (hw % 128 if hw >= 128 else 128 % hw) or (min(hw, 128) & (min(hw, 128) - 1)):
+        return False
+    if W >= 128:
+        return W % 128 == 0
+    if 128 % W:
+        return False
+    rows = 128 // W
+    return (H % rows == 0) if rows <= H else (rows % H == 0 and B % (rows // H) == 0)
+
+
+def conv_bf16x3(x, w, bias=None):
+    return ConvBf16x3Function.apply(x, w, bias)
+
+
 def split_bf16_batched(x3d, straight=True, transposed=False):
     """x fp32 [G, R, C] -> (hi, lo) bf16 [G, R, Cp] and / or (hi_t, lo_t) bf16 [G, C, Rp], every matrix of the batch on its own"""
     _need_cuda(x3d)

@@ -774,6 +774,9 @@ def _library_fwd(fn, input, weight, bias, kwargs):
             (backend.in_recon or (torch.is_grad_enabled() and (input.requires_grad or weight.requires_grad)))):
         # the reconstruction loop's linears (forward, dgrad, wgrad): hand-written tcgen05 GEMM, bf16 x 3 split, fp32 accumulation
         return ops.linear_bf16x3(input, weight, bias)
+    if fn is F.conv2d and backend.calib_gemm_bf16x3 and backend.in_recon and ops.conv_bf16x3_ok(input, weight, kwargs):
+        # the reconstruction loop's stride-1 convolutions: forward and dgrad as implicit GEMMs on the same kernel
+        return ops.conv_bf16x3(input, weight, bias)
     if not input.is_cuda or backend.allow_tf32:
         return fn(input, weight, bias, **kwargs)
     prev_c, prev_m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32

@@ -184,6 +184,15 @@ int edadm_split_bf16_batched(const float* x, int64_t batch, int64_t rows, int64_
 int edadm_gemm_bf16x3_grouped(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, int64_t groups, int64_t M,
                               int N, int64_t K, int64_t Kp, const float* bias, float* out, int splits, void* stream);
 
+/* Convolutions of the reconstruction loop (F.conv2d behind qdiff/quant_layer.py:434 under autograd, stride 1): implicit GEMM on
+ * the same bf16 x 3 kernel.  edadm_split_nhwc_bf16 writes hi / lo of x fp32 NCHW [B][C][H][W] as bf16 NHWC [B][H+2pad][W+2pad][Cp]
+ * with a zero halo; edadm_conv_bf16x3 reads it through rank-4 tensor maps, one filter tap x 64 channels per K step, against
+ * w_* bf16 [N][R*S*C] (tap-major, channel-minor, row pitch Kp) and stores out fp32 NCHW [B][N][Hp-R+1][Wp-S+1] (+ bias[n]).
+ * dgrad is the same call on dY with the flipped, transposed filter.                                                     */
+int edadm_split_nhwc_bf16(const float* x, void* hi, void* lo, int B, int C, int H, int W, int Cp, int pad, void* stream);
+int edadm_conv_bf16x3(const void* a_hi, const void* a_lo, int B, int Hp, int Wp, int Cp, const void* w_hi, const void* w_lo, int N,
+                      int R, int S, int C, int64_t Kp, const float* bias, float* out, void* stream);
+
 /* W4 storage: the same GEMM with the weights kept as 4-bit codes, two per byte -- wq4 u8 [Np][R*S][Cp/2] (Cp % 32 == 0; inside
  * each 32-bit word byte j = code[c0+j] | code[c0+4+j] << 4), zoff[n] = zp[n] -- and unpacked to s8 (code - zoff[n]) in
  * shared memory by dedicated warps of the GEMM kernel, tile by tile, ahead of the tensor-core MMA.  Replaces the same

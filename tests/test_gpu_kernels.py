@@ -841,6 +841,42 @@ def test_linear_bf16x3_forward_and_gradients(cuda, M, K, N, bias):
     print(f"forward rel-L2 vs fp64: bf16x3 {_rel_l2((y.detach() - (b.detach() if bias else 0)).double(), F.linear(xd.detach(), wd.detach())):.1e}, TF32 {e_tf32:.1e}")
 
 
+@pytest.mark.parametrize("B,C,N,H,W,R,bias", [(8, 192, 192, 32, 32, 3, True), (16, 384, 192, 16, 16, 3, True), (32, 576, 384, 8, 8, 3, False),
+                                             (4, 128, 256, 32, 32, 1, True), (2, 64, 72, 64, 64, 3, True), (4, 200, 128, 16, 16, 3, False),
+                                             (1, 32, 32, 128, 128, 3, True)])
+def test_conv_bf16x3_forward_and_dgrad(cuda, B, C, N, H, W, R, bias):
+    """calibration-path convolution (implicit GEMM on the bf16 x 3 kernel, NHWC split producer, NCHW TMA-store epilogue): forward
+    and dgrad against an fp64 convolution; wgrad is the library's and must agree too"""
+    from edadm import ops
+    g = torch.Generator().manual_seed(B * 131 + C)
+    x = (torch.randn(B, C, H, W, generator=g) * 1.3).to(cuda).requires_grad_(True)
+    w = (torch.randn(N, C, R, R, generator=g) * 0.05).to(cuda).requires_grad_(True)
+    b = torch.randn(N, generator=g).to(cuda).requires_grad_(True) if bias else None
+    kw = dict(stride=1, padding=(R - 1) // 2)
+    assert ops.conv_bf16x3_ok(x, w, kw)
+    gy = torch.randn(B, N, H, W, generator=g).to(cuda)
+    y = ops.conv_bf16x3(x, w, b)
+    y.backward(gy)
+    xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    bd = b.detach().double().requires_grad_(True) if bias else None
+    yd = F.conv2d(xd, wd, bd, **kw)
+    yd.backward(gy.double())
+    assert y.shape == yd.shape
+    assert _rel_l2(y.detach().double(), yd.detach()) < 2e-5
+    assert _rel_l2(x.grad.double(), xd.grad) < 2e-5
+    assert _rel_l2(w.grad.double(), wd.grad) < 2e-5
+    if bias:
+        assert _rel_l2(b.grad.double(), bd.grad) < 1e-5
+
+
+def test_conv_bf16x3_guard(cuda):
+    from edadm import ops
+    x = torch.randn(2, 64, 16, 16, device=cuda)
+    assert not ops.conv_bf16x3_ok(x, torch.randn(64, 64, 3, 3, device=cuda), dict(stride=2, padding=1))
+    assert not ops.conv_bf16x3_ok(x, torch.randn(4, 64, 3, 3, device=cuda), dict(stride=1, padding=1))
+    assert not ops.conv_bf16x3_ok(torch.randn(2, 64, 12, 12, device=cuda), torch.randn(64, 64, 3, 3, device=cuda), dict(stride=1, padding=1))
+
+
 @pytest.mark.parametrize("G,M,N,K", [(8, 256, 256, 384), (3, 1024, 1024, 96), (16, 128, 384, 256), (2, 256, 128, 1024)])
 def test_bmm_nt_bf16x3_forward_and_gradients(cuda, G, M, N, K):
     """grouped calibration-path product C[g] = A[g] . B[g]^T (attention Q.K^T and P.V under autograd) vs fp64"""
