@@ -256,7 +256,12 @@ def bench_recon(qnn, kind, shape, ctx, dev, world, iters, modes):
         cali = (x, t, torch.zeros(n_cali * world, dtype=torch.long, device=dev), cond, uncond)
     else:
         cali = (x, t)
-    for mode in modes:
+    from qdiff.quant_layer import backend
+    # the headline blocks run the reference loop literally (FP forward inside every iteration); "weak_memoised_fp_taps" is the
+    # product default, which computes the FP taps once per unit for all cached samples and gathers them per iteration
+    runs = [(m, m, False) for m in modes] + ([("weak_memoised_fp_taps", "weak", True)] if "weak" in modes else [])
+    for key, mode, memo in runs:
+        backend.recon_memoise_fp_taps = memo
         rb = 32 if mode == "weak" else max(1, 32 // world)
         per_unit = {}
         for label, (unit, is_layer) in units.items():
@@ -277,12 +282,15 @@ def bench_recon(qnn, kind, shape, ctx, dev, world, iters, modes):
                 ms_it = float(tt.item())
             per_unit[label] = {"unit": type(unit).__name__, "iters_per_s": 1e3 / ms_it, "ms_per_iter": ms_it,
                                "samples_per_s": world * rb * 1e3 / ms_it, "cuda_graph": timing.get("cuda_graph", False),
-                               "allreduce_bytes_per_iter": timing.get("bucket_bytes", 0) if world > 1 else 0}
+                               "allreduce_bytes_per_iter": timing.get("bucket_bytes", 0) if world > 1 else 0,
+                               "fp_taps_memoised": timing.get("fp_taps_memoised", False)}
             qnn.set_quant_state(True, True)
         gm = math.exp(sum(math.log(u["iters_per_s"]) for u in per_unit.values()) / max(1, len(per_unit)))
-        out[mode] = {"batch_per_gpu": rb, "global_batch": rb * world, "units": per_unit, "geomean_iters_per_s": gm,
+        out[key] = {"batch_per_gpu": rb, "global_batch": rb * world, "units": per_unit, "geomean_iters_per_s": gm,
                      "geomean_samples_per_s": gm * rb * world}
-    out["semantics"] = "reference loop: quant fwd + FP fwd + quant fwd (FBR) + backward + 2 Adam steps, QDrop 0.5"
+    backend.recon_memoise_fp_taps = True
+    out["semantics"] = ("weak / strong: reference loop, quant fwd + FP fwd + quant fwd (FBR) + backward + 2 Adam steps, QDrop 0.5; "
+                        "weak_memoised_fp_taps: same losses and updates, the FP-model taps read from a per-unit table filled before the loop")
     return out
 
 

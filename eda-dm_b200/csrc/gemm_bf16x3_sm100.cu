@@ -444,6 +444,54 @@ split_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ 
 }  // namespace g3
 }  // namespace edadm
 
+namespace edadm {
+namespace g3 {
+// filter w fp32 [N][C][RS] -> forward operand f_* bf16 [N][RS*C (pitch fp)] (tap-major, channel-minor) and / or dgrad operand
+// d_* bf16 [C][RS*N (pitch dp)] with the taps reversed (d[c][t][n] = w[n][c][RS-1-t]).  Blocks [0, N) write the forward rows,
+// blocks [N, N + C) the dgrad rows.
+__global__ void __launch_bounds__(256)
+split_filter_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ f_hi, __nv_bfloat16* __restrict__ f_lo,
+                         __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo, int N, int C, int RS, int fp, int dp,
+                         int n_fwd_blocks) {
+  const int b = blockIdx.x;
+  if (b < n_fwd_blocks) {
+    const int n = b;
+    const float* src = w + (size_t)n * C * RS;
+    for (int i = threadIdx.x; i < fp; i += blockDim.x) {       // i = t * C + c
+      float v = 0.f;
+      if (i < RS * C) { const int t = i / C, c = i - t * C; v = __ldg(src + (size_t)c * RS + t); }
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      f_hi[(size_t)n * fp + i] = h;
+      f_lo[(size_t)n * fp + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  } else {
+    const int c = b - n_fwd_blocks;
+    for (int i = threadIdx.x; i < dp; i += blockDim.x) {       // i = t * N + n
+      float v = 0.f;
+      if (i < RS * N) { const int t = i / N, n = i - t * N; v = __ldg(w + ((size_t)n * C + c) * RS + (RS - 1 - t)); }
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      d_hi[(size_t)c * dp + i] = h;
+      d_lo[(size_t)c * dp + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+}  // namespace g3
+}  // namespace edadm
+
+extern "C" int edadm_split_filter_bf16(const float* w, int N, int C, int R, int S, void* f_hi, void* f_lo, int64_t f_pitch, void* d_hi,
+                                       void* d_lo, int64_t d_pitch, void* stream) {
+  const int RS = R * S;
+  const bool fwd = f_hi && f_lo, dg = d_hi && d_lo;
+  if (!w || N < 1 || C < 1 || RS < 1 || (!fwd && !dg) || (fwd && (f_pitch < (int64_t)RS * C || (f_pitch & 7))) ||
+      (dg && (d_pitch < (int64_t)RS * N || (d_pitch & 7))))
+    return fail(EDADM_ERR_ARG, "split_filter_bf16: bad arguments");
+  const int nf = fwd ? N : 0;
+  g3::split_filter_bf16_kernel<<<nf + (dg ? C : 0), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)f_hi, (__nv_bfloat16*)f_lo,
+                                                                                   (__nv_bfloat16*)d_hi, (__nv_bfloat16*)d_lo, N, C, RS,
+                                                                                   (int)f_pitch, (int)d_pitch, nf);
+  return check_launch("split_filter_bf16");
+}
+
 extern "C" int edadm_split_nhwc_bf16(const float* x, void* hi, void* lo, int B, int C, int H, int W, int Cp, int pad, void* stream) {
   if (!x || !hi || !lo || B < 1 || B > 65535 || C < 1 || H < 1 || W < 1 || Cp < C || (Cp & 7) || pad < 0)
     return fail(EDADM_ERR_ARG, "split_nhwc_bf16: bad arguments");

@@ -815,10 +815,23 @@ def split_nhwc_bf16(x, pad):
     return hi, lo
 
 
-def _conv_bf16x3_raw(x, w_taps, n_out, R, S, c_in, pad, bias=None):
-    """x fp32 NCHW, w_taps fp32 [n_out, R*S*c_in] (tap-major) -> fp32 NCHW, stride 1"""
+def split_filter_bf16(w, forward=True, dgrad=False):
+    """w fp32 [N, C, R, S] -> forward operand (hi, lo) bf16 [N, R*S*C] (tap-major) and / or dgrad operand (hi, lo) bf16 [C, R*S*N]
+    (taps reversed, channels transposed), one launch"""
+    _need_cuda(w)
+    w = _f32c(w)
+    N, C, R, S = w.shape
+    fp, dp = _round_up(R * S * C, 8), _round_up(R * S * N, 8)
+    mk = lambda *s: torch.empty(s, dtype=torch.bfloat16, device=w.device)
+    fh, fl = (mk(N, fp), mk(N, fp)) if forward else (None, None)
+    dh, dl = (mk(C, dp), mk(C, dp)) if dgrad else (None, None)
+    lib.split_filter_bf16(w.data_ptr(), N, C, R, S, _ptr(fh), _ptr(fl), fp, _ptr(dh), _ptr(dl), dp, _stream())
+    return fh, fl, dh, dl
+
+
+def _conv_bf16x3_raw(x, wh, wl, n_out, R, S, c_in, pad, bias=None):
+    """x fp32 NCHW, filter operand (wh, wl) bf16 [n_out, R*S*c_in] (tap-major) -> fp32 NCHW, stride 1"""
     xh, xl = split_nhwc_bf16(x, pad)
-    wh, wl, _, _ = split_bf16(w_taps)
     B, Hp, Wp, Cp = xh.shape
     out = torch.empty((B, n_out, Hp - R + 1, Wp - S + 1), dtype=torch.float32, device=x.device)
     lib.conv_bf16x3(xh.data_ptr(), xl.data_ptr(), B, Hp, Wp, Cp, wh.data_ptr(), wl.data_ptr(), n_out, R, S, c_in, wh.shape[1],
@@ -828,35 +841,33 @@ def _conv_bf16x3_raw(x, w_taps, n_out, R, S, c_in, pad, bias=None):
 
 class ConvBf16x3Function(torch.autograd.Function):
     """F.conv2d(x, w, bias, stride=1, padding=(R-1)/2) with forward and dgrad on edadm_conv_bf16x3 (dgrad = the same convolution
-    of dY with the flipped, transposed filter); wgrad stays on the fp32 library kernel."""
+    of dY with the flipped, transposed filter, prepared by the forward's filter split); wgrad stays on the library kernel."""
 
     @staticmethod
     def forward(ctx, x, w, bias):
         N, C, R, S = w.shape
-        y = _conv_bf16x3_raw(x, w.permute(0, 2, 3, 1).reshape(N, R * S * C), N, R, S, C, (R - 1) // 2,
-                             None if bias is None else _f32c(bias.detach()))
-        ctx.save_for_backward(x, w)
+        need_dx = ctx.needs_input_grad[0]
+        fh, fl, dh, dl = split_filter_bf16(w, True, need_dx)
+        y = _conv_bf16x3_raw(x, fh, fl, N, R, S, C, (R - 1) // 2, None if bias is None else _f32c(bias.detach()))
+        ctx.save_for_backward(x, w, *((dh, dl) if need_dx else ()))
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, w = ctx.saved_tensors
+        x, w = ctx.saved_tensors[:2]
         N, C, R, S = w.shape
         gy = _f32c(gy)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wt = w.flip(2, 3).permute(1, 2, 3, 0).reshape(C, R * S * N)
-            dx = _conv_bf16x3_raw(gy, wt, C, R, S, N, (R - 1) // 2)
+            dh, dl = ctx.saved_tensors[2:]
+            dx = _conv_bf16x3_raw(gy, dh, dl, C, R, S, N, (R - 1) // 2)
         if ctx.needs_input_grad[1]:
-            prev = torch.backends.cudnn.allow_tf32
-            torch.backends.cudnn.allow_tf32 = False
-            try:
-                pad = (R - 1) // 2
-                dw = torch.ops.aten.convolution_backward(gy, x, w, None, [1, 1], [pad, pad], [1, 1], False, [0, 0], 1,
-                                                         [False, True, False])[1]
-            finally:
-                torch.backends.cudnn.allow_tf32 = prev
+            # library wgrad under the ambient torch.backends.cudnn.allow_tf32 (PyTorch's default -- and therefore the reference's --
+            # is TF32 tensor-core wgrad; the fp32 SIMT kernel it falls back to otherwise is 2.5x slower)
+            pad = (R - 1) // 2
+            dw = torch.ops.aten.convolution_backward(gy, x, w, None, [1, 1], [pad, pad], [1, 1], False, [0, 0], 1,
+                                                     [False, True, False])[1]
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = gy.sum((0, 2, 3))
         return dx, dw, db

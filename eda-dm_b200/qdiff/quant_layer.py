@@ -39,6 +39,8 @@ class _Backend:
     recon_cuda_graph = True  # capture the reconstruction iteration in one CUDA graph after 3 eager iterations
     recon_graph_checkpointed = True   # ... including units whose backward recomputes the forward (transformer / attention blocks)
     recon_overlap_allreduce = True    # data parallel: all-reduce each alpha gradient as soon as its backward has produced it
+    recon_memoise_fp_taps = True      # FP-model taps of the per-layer loss: computed once per unit for all cached samples (HBM), not per iteration
+    recon_memoise_bytes = 32 << 30    #   ... as long as they fit in this many bytes
     calib_gemm_bf16x3 = True          # linears of the reconstruction loop (fwd / dgrad / wgrad) on edadm_gemm_bf16x3 instead of cuBLAS fp32
     in_recon = False                  # set by the reconstruction engine around its loop (FP-target forwards included)
     cache_prefix_reuse = True         # calibration cache builder keeps the network state at the frontier of the finished units (f2)

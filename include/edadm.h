@@ -189,6 +189,10 @@ int edadm_gemm_bf16x3_grouped(const void* a_hi, const void* a_lo, const void* b_
  * with a zero halo; edadm_conv_bf16x3 reads it through rank-4 tensor maps, one filter tap x 64 channels per K step, against
  * w_* bf16 [N][R*S*C] (tap-major, channel-minor, row pitch Kp) and stores out fp32 NCHW [B][N][Hp-R+1][Wp-S+1] (+ bias[n]).
  * dgrad is the same call on dY with the flipped, transposed filter.                                                     */
+/* filter w fp32 [N][C][R][S] -> forward operand f_* bf16 [N][f_pitch >= R*S*C] (tap-major) and / or dgrad operand d_* bf16
+ * [C][d_pitch >= R*S*N] (taps reversed, channels transposed); pass NULL for the pair that is not needed.              */
+int edadm_split_filter_bf16(const float* w, int N, int C, int R, int S, void* f_hi, void* f_lo, int64_t f_pitch, void* d_hi, void* d_lo,
+                            int64_t d_pitch, void* stream);
 int edadm_split_nhwc_bf16(const float* x, void* hi, void* lo, int B, int C, int H, int W, int Cp, int pad, void* stream);
 int edadm_conv_bf16x3(const void* a_hi, const void* a_lo, int B, int Hp, int Wp, int Cp, const void* w_hi, const void* w_lo, int N,
                       int R, int S, int C, int64_t Kp, const float* bias, float* out, void* stream);

@@ -1,0 +1,10 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT"
+timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu --tb=short -k "conv_bf16x3 or linear_bf16x3" 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_api.py -x -q -m gpu --tb=short 2>&1 | tail -15
+timeout 900 python bench.py --steps 5 --warmup 3 --no-secondary --no-cpu-baseline --recon-iters 40 > gpurun_out/bench_conv3.json 2> gpurun_out/bench_conv3.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_conv3.json').read().strip().splitlines()[-1])
+print(json.dumps(d.get('recon', d.get('config',{}).get('recon')), indent=1)[:3000])
+PY

@@ -856,7 +856,12 @@ def test_conv_bf16x3_forward_and_dgrad(cuda, B, C, N, H, W, R, bias):
     assert ops.conv_bf16x3_ok(x, w, kw)
     gy = torch.randn(B, N, H, W, generator=g).to(cuda)
     y = ops.conv_bf16x3(x, w, b)
-    y.backward(gy)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the library wgrad in fp32 for the comparison below
+    try:
+        y.backward(gy)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
     xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
     bd = b.detach().double().requires_grad_(True) if bias else None
     yd = F.conv2d(xd, wd, bd, **kw)
