@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT"
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-recon > gpurun_out/bench_p5.json 2> gpurun_out/bench_p5.err
+python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/bench_p5.json').read().strip().splitlines() if l.startswith('{')][-1])
+print('imagenet', d['ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['share_of_eager_step'])
+s=d['secondary']; print('church', s['ms_per_step'], s['value'], s['e2e']['value'], s['roofline']['frac'])
+PY
