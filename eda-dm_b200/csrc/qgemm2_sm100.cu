@@ -72,9 +72,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
 __device__ __forceinline__ uint32_t q_code(float x, float d, float inv_d, float z, float qmax) {
   const float q0 = x * inv_d;
   const float q1 = __fmaf_rn(__fmaf_rn(-d, q0, x), inv_d, q0);
-  short k;
-  asm("cvt.rni.s16.f32 %0, %1;" : "=h"(k) : "f"(q1));
-  return (uint32_t)min(__viaddmax_s32((int)k, (int)z, 0), (int)qmax);
+  const float t = fminf(fmaxf(q1, -z), qmax - z) + 12582912.0f;       // round-to-nearest-even in the low mantissa bits, no conversion pipe
+  return (uint32_t)(__float_as_int(t) - 0x4B400000 + (int)z);
 }
 
 template <int CTAS>

@@ -54,6 +54,8 @@ struct GemmParams {
   int accumulate, silu;
   const float* residual;   // optional fp32 tensor laid out like `out`, added after bias / accumulate / SiLU
   const float* bias_img;   // optional fp32 [images][N]: per-(image, channel) term added like a residual (timestep embedding)
+  const float* post;       // row-major outputs only: optional fp32 [M / post_rows][N] added AFTER the residual, one row per group of
+  int post_rows;           //   post_rows consecutive output rows (the one-key cross-attention term of a transformer block)
   const float* delta_a;     // device scalars (nn.Parameter storage): no host sync on the path
   const float* zp_a;
   const float* delta_w;     // [N]
@@ -407,6 +409,10 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (mm < p.M && ncol < p.N) {
               float4 v = *reinterpret_cast<const float4*>(tile_s + rr * ROW_STAGE_LD + cq);
               if (has_res) { v.x += tres[i].x; v.y += tres[i].y; v.z += tres[i].z; v.w += tres[i].w; }
+              if (p.post) {
+                const float4 pv = __ldg(reinterpret_cast<const float4*>(p.post + (long long)(mm / p.post_rows) * p.N + ncol));
+                v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+              }
               *reinterpret_cast<float4*>(p.out + (long long)mm * p.N + ncol) = v;
             }
           }
@@ -543,7 +549,7 @@ static int launch_qgemm(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int
                         const int32_t* zoff, int N, int Np, int R, int S, int Cp_w, const float* delta_a, const float* zp_a,
                         const float* delta_w, const int32_t* wsum_eff, const int32_t* cw, const int32_t* rowsum,
                         const float* bias, const float* bias_img, const float* residual, float* out, int out_hw, int accumulate,
-                        int silu, void* stream) {
+                        int silu, void* stream, const float* post = nullptr, int post_rows = 0) {
   if (bias_img && (residual || out_hw == 1))
     return fail(EDADM_ERR_UNSUPPORTED, "qgemm_i8: bias_img needs an NCHW output (out_hw > 1) and cannot be combined with residual");
   if (!q || !wq || !delta_a || !zp_a || !delta_w || !wsum_eff || !out) return fail(EDADM_ERR_ARG, "qgemm_i8: null pointer");
@@ -637,6 +643,9 @@ static int launch_qgemm(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int
   if (const char* e = getenv("EDADM_GEMM_STAGES")) { const int v = atoi(e); if (v >= 2 && v < p.stages) p.stages = v; }   // debug
   const int smem_bytes = fixed + p.stages * (BLOCK_M * kbytes + p.b_stage_bytes);
   p.out_hw = out_hw; p.accumulate = accumulate; p.silu = silu; p.residual = residual; p.bias_img = bias_img;
+  p.post = post; p.post_rows = post_rows;
+  if (post && (!p.row_staging || post_rows < 1 || (M % post_rows) || (reinterpret_cast<uintptr_t>(post) & 15)))
+    return fail(EDADM_ERR_UNSUPPORTED, "qgemm_i8: the row-group term needs a staged row-major output (N %% 4 == 0, no rowsum / accumulate) and post_rows dividing M");
   p.delta_a = delta_a; p.zp_a = zp_a; p.delta_w = delta_w; p.wsum_eff = wsum_eff; p.cw = cw; p.rowsum = rowsum;
   p.bias = bias; p.out = out;
   p.trace = g_gemm_trace;
@@ -693,6 +702,17 @@ extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_ac
   }
   return launch_qgemm(q, B, Hp, Wp, Cp_act, a_c_offset, wq, 0, nullptr, N, Np, R, S, Cp_w, delta_a, zp_a, delta_w, wsum_eff, cw,
                       rowsum, bias, bias_img, residual, out, out_hw, accumulate, silu, stream);
+}
+
+// Linear layer (row-major output) whose epilogue adds, after the residual, one fp32 row per group of `post_rows` output rows:
+//   out[m][n] = ((acc * scale + bias[n]) + residual[m][n]) + post[m / post_rows][n]      (each + one fp32 rounding, in this order)
+extern "C" int edadm_qgemm_i8_rows_post(const uint8_t* q, int64_t M, int Kp_act, const int8_t* wq, int N, int Np, int Cp_w,
+                                        const float* delta_a, const float* zp_a, const float* delta_w, const int32_t* wsum_eff,
+                                        const float* bias, const float* residual, const float* post, int post_rows, float* out,
+                                        void* stream) {
+  if (M < 1 || M > 0x7fffffffLL || !post) return fail(EDADM_ERR_ARG, "qgemm_i8_rows_post: bad arguments");
+  return launch_qgemm(q, 1, 1, (int)M, Kp_act, 0, wq, 0, nullptr, N, Np, 1, 1, Cp_w, delta_a, zp_a, delta_w, wsum_eff, nullptr, nullptr,
+                      bias, nullptr, residual, out, 1, 0, 0, stream, post, post_rows);
 }
 
 // Same GEMM with the weights stored as 4-bit codes, two per byte: wq4 [Np][R*S][Cp_w/2] (Cp_w % 32 == 0; inside each 32-bit

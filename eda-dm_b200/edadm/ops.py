@@ -584,6 +584,28 @@ def qgemm_i8(q, pw: PackedWeight, delta_a, zp_a, out, out_hw, bias=None, rowsum=
     return out
 
 
+def qgemm_i8_rows_post(q, pw: PackedWeight, delta_a, zp_a, out, bias, residual, post, post_rows):
+    """Linear GEMM (q [M, Kp] u8 codes -> out fp32 [M, N]) with `+ residual[m]` and then `+ post[m // post_rows]` in the epilogue."""
+    if pw.w4 or pw.needs_rowsum:
+        raise EdadmError("qgemm_i8_rows_post: plain s8 weight tiles without row sums only")
+    if residual is None or residual.dtype != torch.float32 or not residual.is_contiguous() or residual.numel() != out.numel():
+        raise EdadmError("qgemm_i8_rows_post: residual must be a contiguous fp32 tensor of the output's size")
+    post = _f32c(post.detach())
+    dev = q.device
+    da, za = _qparam(delta_a, dev), _qparam(zp_a, dev)
+    prof = gemm_profile
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    lib.qgemm_i8_rows_post(q.data_ptr(), q.shape[0], q.shape[1], pw.wq.data_ptr(), pw.N, pw.Np, pw.wq.shape[2], da.data_ptr(),
+                           za.data_ptr(), pw.delta_w.data_ptr(), pw.wsum_eff.data_ptr(), _ptr(bias), residual.data_ptr(),
+                           post.data_ptr(), int(post_rows), out.data_ptr(), _stream())
+    if prof is not None:
+        ev1.record()
+        prof.append((ev0, ev1, q.shape[0] * pw.N * pw.C * pw.R * pw.S))
+    return out
+
+
 def qgemm_i8_codes(q, pw: PackedWeight, delta_a, zp_a, consumer, bias=None, rowsum=None, geglu=False, want_rowsum=False):
     """Linear GEMM whose epilogue emits the u8 codes of the NEXT activation quantizer (`consumer` = (delta, zero_point,
     n_levels)) instead of fp32 -- optionally through the GEGLU gate.  q: [M, Kp] u8 codes.  Returns (codes [M, Kp_out], rowsum)."""

@@ -96,12 +96,14 @@ def _emb_layers(seq, emb):
     return seq(emb)
 
 
-def _conv_plus(conv, residual, call):
+def _conv_plus(conv, residual, call, post=None):
     """`residual + call()` where `call` runs the QuantModule `conv`; the add moves into the GEMM epilogue unless a hook
-    observes the conv's own output (calibration caches, FBR taps)."""
+    observes the conv's own output (calibration caches, FBR taps).  `post` (optional, [B, 1, N]): one more row per sample,
+    added after the residual -- `(call() + residual) + post` -- in the same epilogue when the layer supports it."""
     if isinstance(conv, QuantModule) and not conv._forward_hooks:
-        return call(residual=residual)
-    return call() + residual
+        return call(residual=residual) if post is None else call(residual=residual, post=post)
+    out = call() + residual
+    return out if post is None else out + post
 
 
 class BaseQuantBlock(nn.Module):
@@ -255,16 +257,17 @@ class QuantAttentionBlock(BaseQuantBlock):
 
 
 # ---- transformer block (ImageNet / Stable Diffusion) -------------------------------------------------------
-def cross_attn_forward(self, x, context=None, mask=None, norm=None, residual=None):
+def cross_attn_forward(self, x, context=None, mask=None, norm=None, residual=None, post=None):
     """Replacement `CrossAttention.forward` with quantized q, k, v and softmax (reference quant_block.py:204-235).
     norm / residual (optional, used by QuantBasicTransformerBlock): compute `attn(norm(x), context) + residual` with the
     LayerNorm folded into the q/k/v activation producers and the add into to_out's GEMM epilogue when nothing observes the
-    intermediate tensors; otherwise module by module."""
+    intermediate tensors; otherwise module by module.  post (optional, with residual): [B, 1, C] row per sample added after the
+    residual (the one-key cross-attention term of the enclosing transformer block)."""
     h = self.heads
     if mask is not None:
         raise NotImplementedError("attention masks are not used by any EDA-DM configuration")
     self_attn = context is None
-    fast = _cross_attn_integer(self, x, context, norm, residual)
+    fast = _cross_attn_integer(self, x, context, norm, residual, post)
     if fast is not None:
         return fast
     if norm is not None:
@@ -294,11 +297,48 @@ def cross_attn_forward(self, x, context=None, mask=None, norm=None, residual=Non
     lin, rest = self.to_out[0], self.to_out[1:]
     drop_active = any(isinstance(m, nn.Dropout) and m.p > 0 and m.training for m in rest)
     if drop_active:
-        return self.to_out(out) + residual
-    return _conv_plus(lin, residual, lambda **kw: lin(out, **kw))
+        y = self.to_out(out) + residual
+        return y if post is None else y + post
+    return _conv_plus(lin, residual, lambda **kw: lin(out, **kw), post)
 
 
-def _cross_attn_integer(attn, x, context, norm, residual):
+def _one_key_row(attn, x, context, norm, residual):
+    """Cross attention over ONE context token (the class embedding of LDM-4 ImageNet, `ClassEmbedder` -> [B, 1, 512]): softmax
+    over a single key is exactly 1 whatever q is, so every query row of a sample gets the same `to_out(Q_w(1) * Q_v(v))`;
+    to_q, its LayerNorm pass and the attention matmuls drop out and to_out runs on B rows instead of B*T.  Returns that row
+    [B, 1, C] (the caller adds it to the residual), or None when the shortcut does not apply."""
+    if th.is_grad_enabled() or norm is None or residual is None or not attn.use_act_quant or not backend.fuse_epilogue:
+        return None
+    if context is None or context.shape[1] != 1:
+        return None
+    lin_out, rest = attn.to_out[0], attn.to_out[1:]
+    if any(isinstance(m, nn.Dropout) and m.p > 0 and m.training for m in rest) or any(m._forward_hooks for m in rest):
+        return None
+    mods = (attn.to_q, attn.to_k, attn.to_v, lin_out)
+    if not all(isinstance(m, QuantModule) for m in mods):
+        return None
+    qs = (attn.act_quantizer_q, attn.act_quantizer_k, attn.act_quantizer_v, attn.act_quantizer_w)
+    if not qattn._fusable((x,), qs):
+        return None
+    if not (lin_out._integer_path_ok(x) and not lin_out._forward_hooks and not lin_out._forward_pre_hooks
+            and not attn.to_q._forward_hooks and not attn.to_q._forward_pre_hooks and not norm._forward_hooks
+            and lin_out._epilogue_residual(residual) is not None):
+        return None
+    v = attn.to_v(context)                                   # [B, 1, h*d]
+    attn.to_k(context)                                       # keeps to_k's hooks / path report alive; its value cannot matter
+    qw, qv = attn.act_quantizer_w, attn.act_quantizer_v
+    one = th.ones(1, dtype=v.dtype, device=v.device)
+    # Q_w(softmax over one key) * Q_v(v), the same row for every query -- in the arithmetic of the fused attention kernel
+    # (integer product of the zero-point-free codes, scaled once by dP*dv) so both routes agree bit for bit
+    p_int = qw.codes(one).to(th.int32) - qw.zero_point.to(th.int32)
+    v_int = qv.codes(v).to(th.int32) - qv.zero_point.to(th.int32)
+    out = (p_int * v_int).to(v.dtype) * (qw.delta.detach() * qv.delta.detach())
+    row = lin_out(out)                                       # [B, 1, C]
+    attn.to_q.last_path = 'elided'                           # (QuantModel.path_report)
+    return row
+
+
+def _cross_attn_integer(attn, x, context, norm, residual, post=None):
     """Integer-path forms of cross_attn_forward (reference quant_block.py:204-235) that never materialise fp32 q / k; None when
     they do not apply (then the module-by-module formulation below runs).
 
@@ -318,21 +358,11 @@ def _cross_attn_integer(attn, x, context, norm, residual):
     qs = (attn.act_quantizer_q, attn.act_quantizer_k, attn.act_quantizer_v, attn.act_quantizer_w)
     if not qattn._fusable((x,), qs):
         return None
-    if context is not None and context.shape[1] == 1 and lin_out._integer_path_ok(x) and not lin_out._forward_hooks \
-            and not lin_out._forward_pre_hooks and not attn.to_q._forward_hooks and not attn.to_q._forward_pre_hooks \
-            and not norm._forward_hooks and lin_out._epilogue_residual(residual) is not None:
-        v = attn.to_v(context)                                   # [B, 1, h*d]
-        attn.to_k(context)                                       # keeps to_k's hooks / path report alive; its value cannot matter
-        qw, qv = attn.act_quantizer_w, attn.act_quantizer_v
-        one = th.ones(1, dtype=v.dtype, device=v.device)
-        # Q_w(softmax over one key) * Q_v(v), the same row for every query -- in the arithmetic of the fused attention kernel
-        # (integer product of the zero-point-free codes, scaled once by dP*dv) so both routes agree bit for bit
-        p_int = qw.codes(one).to(th.int32) - qw.zero_point.to(th.int32)
-        v_int = qv.codes(v).to(th.int32) - qv.zero_point.to(th.int32)
-        out = (p_int * v_int).to(v.dtype) * (qw.delta.detach() * qv.delta.detach())
-        row = lin_out(out)                                       # [B, 1, C]
-        attn.to_q.last_path = 'elided'                           # (QuantModel.path_report)
-        return residual + row
+    if context is not None and context.shape[1] == 1:
+        row = _one_key_row(attn, x, context, norm, residual)
+        if row is not None:
+            y = residual + row
+            return y if post is None else y + post
     if context is None and attn.heads == 1 and backend.fuse_epilogue and all(m.codes_consumer_ok() for m in mods[:3]) \
             and all(m.prenorm_fusable(x, norm) for m in mods[:3]) and attn.to_q.emit_ok(attn.act_quantizer_q) \
             and attn.to_k.emit_ok(attn.act_quantizer_k):
@@ -347,7 +377,7 @@ def _cross_attn_integer(attn, x, context, norm, residual):
         B, T = x.shape[0], x.shape[1]
         out = ops.qattn_bnd_codes(qc.reshape(B, T, -1), qr.reshape(B, T), kc.reshape(B, T, -1), kr.reshape(B, T), v, 1,
                                   qattn._aquant(*qs), attn.scale)
-        return _conv_plus(lin_out, residual, lambda **kw: lin_out(out, **kw))
+        return _conv_plus(lin_out, residual, lambda **kw: lin_out(out, **kw), post)
     return None
 
 
@@ -398,8 +428,14 @@ class QuantBasicTransformerBlock(BaseQuantBlock):
             x, context = x
         # same dataflow as the reference (quant_block.py:254-262): x = attn1(norm1(x)) + x; x = attn2(norm2(x), ctx) + x;
         # x = ff(norm3(x)) + x -- LayerNorms, GEGLU gate and residual adds ride on the neighbouring QuantModules
-        x = self.attn1(x, norm=self.norm1, residual=x)
-        x = self.attn2(x, context=context, norm=self.norm2, residual=x)
+        # one context token: attn2's output is one row per sample that does not depend on x -- computed first and added by
+        # attn1.to_out's epilogue right after its own residual (the same two fp32 additions in the same order)
+        row = _one_key_row(self.attn2, x, context, self.norm2, x) if context is not None else None
+        if row is not None:
+            x = self.attn1(x, norm=self.norm1, residual=x, post=row)
+        else:
+            x = self.attn1(x, norm=self.norm1, residual=x)
+            x = self.attn2(x, context=context, norm=self.norm2, residual=x)
         return _ff_forward(self.ff, x, self.norm3)
 
     def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):

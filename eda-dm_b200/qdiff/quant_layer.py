@@ -524,6 +524,24 @@ class QuantModule(nn.Module):
                                               tokens_out=tokens_out, bias_img=bias_img if fold else None, codes=codes), residual)
         return out if bias_img is None or fold else out + bias_img.reshape(out.shape[0], -1, *([1] * (out.dim() - 2)))
 
+    def forward_upsample2x(self, x):
+        """`self(F.interpolate(x, scale_factor=2, mode="nearest"))` -- the conv of a resampling `Upsample` (openaimodel.py Upsample,
+        ddim/models/diffusion.py Upsample).  Nearest upsampling commutes with the element-wise quantizer, so on the integer path the
+        LOW-resolution tensor is quantized (a quarter of the elements) and the u8 codes are replicated straight into the
+        halo-padded layout the GEMM reads; the 4x larger fp32 tensor never exists."""
+        ok = (backend.fuse_norm and self.fwd_func is F.conv2d and x.dim() == 4 and not self.split and self._integer_path_ok(x)
+              and not self._forward_hooks and not self._forward_pre_hooks and int(self.fwd_kwargs['stride'][0]) == 1
+              and not any(p.needs_rowsum for p in self._packed_weights()))
+        if not ok:
+            return self(F.interpolate(x, scale_factor=2, mode="nearest"))
+        self.last_path = 'int8'
+        _, aqs = self._quantizers()
+        aq = ops.ActQuant(aqs[0].delta, aqs[0].zero_point, aqs[0].n_levels)
+        pw0 = self._packed_weights()[0]
+        q_lo, _ = ops.act_quant_nhwc(x, aq, 0, cp=pw0.Cp)
+        codes = ops.upsample2x_codes(q_lo, x.shape[1], int(self.fwd_kwargs['padding'][0]), aq)
+        return self._finish(self._forward_int8(x, codes=codes), None)
+
     def forward_geglu(self, h, residual=None):
         """`self(a * gelu(g))` with (a, g) = h.chunk(2, -1): the GEGLU gate (ldm/modules/attention.py GEGLU.forward) folded
         into this linear's activation producer (edadm_geglu_quant_rows) on the integer path."""
@@ -579,6 +597,15 @@ class QuantModule(nn.Module):
             return self._forward_int8(None, rows=('codes', q, rowsum, lead), emit=emit)
         return self._finish(self._forward_int8(None, rows=('codes', q, rowsum, lead), residual=self._epilogue_residual(residual)), residual)
 
+    def _post_ok(self, input, post):
+        """the row-group term of edadm_qgemm_i8_rows_post applies: a plain integer-path linear, one weight pack, no row sums"""
+        if self.fwd_func is not F.linear or self.split or not self._integer_path_ok(input) or input.dim() != 3:
+            return False
+        packs = self._packed_weights()
+        N = packs[0].N
+        return (len(packs) == 1 and not packs[0].needs_rowsum and not packs[0].w4 and N % 4 == 0 and post.dim() == 3
+                and post.shape == (input.shape[0], 1, N) and post.dtype == torch.float32)
+
     def _epilogue_residual(self, residual):
         """`residual` if the GEMM epilogue may add it (nothing but a StraightThrough sits between conv and add)."""
         return residual if isinstance(self.activation_function, StraightThrough) else None
@@ -589,7 +616,7 @@ class QuantModule(nn.Module):
             out = out + residual
         return out
 
-    def _forward_int8(self, input, affine=None, residual=None, rows=None, tokens_out=False, bias_img=None, codes=None, emit=None):
+    def _forward_int8(self, input, affine=None, residual=None, rows=None, tokens_out=False, bias_img=None, codes=None, emit=None, post=None):
         """Exact integer GEMM: out = dA*dW[n]*sum (qa-za)(qw-zw) + bias  == the reference's fp32 conv of the
         dequantised tensors (quant_layer.py:414-434) without its per-product rounding."""
         packs = self._packed_weights()
@@ -636,7 +663,10 @@ class QuantModule(nn.Module):
             out = torch.empty((q.shape[0], N), dtype=torch.float32, device=q.device)
             if residual is not None:
                 residual = residual.reshape(-1, N).contiguous()
-            if q.shape[0] > 0:
+            if q.shape[0] > 0 and post is not None:
+                ops.qgemm_i8_rows_post(q, pw0, aqs[0].delta, aqs[0].zero_point, out, bias, residual, post.reshape(-1, N),
+                                       q.shape[0] // post.shape[0])
+            elif q.shape[0] > 0:
                 self._gemm_chain(q, packs, aqs, out, 1, bias, rowsum, residual)
             return out.reshape(*lead, N)
         x4 = input.unsqueeze(2) if self.fwd_func is F.conv1d else input
@@ -689,10 +719,16 @@ class QuantModule(nn.Module):
             c_off += pw.C
 
     # ---- forward -------------------------------------------------------------------------------------
-    def forward(self, input: torch.Tensor, split: int = 0, residual=None, bias_img=None):
+    def forward(self, input: torch.Tensor, split: int = 0, residual=None, bias_img=None, post=None):
         """`residual` (optional, not in the reference signature): a tensor of the output's shape that is added to the
         result -- `conv(x) + residual` -- inside the GEMM epilogue on the integer path, as a plain add elsewhere.
-        `bias_img` (optional, convs): [B, N(,1,1)] added per (image, channel) -- the ResBlock's `h + emb_out`."""
+        `bias_img` (optional, convs): [B, N(,1,1)] added per (image, channel) -- the ResBlock's `h + emb_out`.
+        `post` (optional, linears with a residual): [B, 1, N], one row per sample added after the residual."""
+        if post is not None:
+            if not (residual is not None and self._post_ok(input, post) and self._epilogue_residual(residual) is not None):
+                return self.forward(input, split=split, residual=residual) + post
+            self.last_path = 'int8'
+            return self._finish(self._forward_int8(input, residual=residual, post=post), residual)
         if bias_img is not None:
             fold = (residual is None and self.fwd_func is F.conv2d and self._integer_path_ok(input)
                     and self._epilogue_residual(bias_img) is not None)

@@ -39,6 +39,8 @@ class Upsample(nn.Module):
             self.conv = nn.Conv2d(ch, ch, 3, 1, 1)
 
     def forward(self, x):
+        if self.with_conv and hasattr(self.conv, "forward_upsample2x"):    # QuantModule: upsample the u8 codes, not the fp32 tensor
+            return self.conv.forward_upsample2x(x)
         x = F.interpolate(x, scale_factor=2.0, mode="nearest")
         return self.conv(x) if self.with_conv else x
 

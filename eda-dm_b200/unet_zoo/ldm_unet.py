@@ -47,6 +47,8 @@ class Upsample(nn.Module):
             self.conv = nn.Conv2d(channels, self.out_channels, 3, padding=padding)
 
     def forward(self, x):
+        if self.use_conv and hasattr(self.conv, "forward_upsample2x"):     # QuantModule: upsample the u8 codes, not the fp32 tensor
+            return self.conv.forward_upsample2x(x)
         x = F.interpolate(x, scale_factor=2, mode="nearest")
         return self.conv(x) if self.use_conv else x
 

@@ -164,6 +164,14 @@ int edadm_qgemm_i8_codes(const uint8_t* q, int64_t M, int Kp_act, const int8_t* 
                          const int32_t* cw, const int32_t* rowsum, const float* bias, int geglu, const float* q_delta,
                          const float* q_zp, int q_levels, uint8_t* out_codes, int out_pitch, int32_t* q_rowsum, void* stream);
 
+/* Linear layer with a row-group term after the residual: out[m][n] = ((acc*scale + bias[n]) + residual[m][n]) + post[m / post_rows][n].
+ * Replaces `x = attn1(norm1(x)) + x; x = attn2(norm2(x), context) + x` (quant_block.py:254-262) when the context has ONE token
+ * (LDM-4 ImageNet class conditioning): softmax over one key is 1, attn2's output is one row per sample, independent of x, and
+ * rides on attn1.to_out's epilogue (same fp32 additions in the same order as the two separate statements).                  */
+int edadm_qgemm_i8_rows_post(const uint8_t* q, int64_t M, int Kp_act, const int8_t* wq, int N, int Np, int Cp_w, const float* delta_a,
+                             const float* zp_a, const float* delta_w, const int32_t* wsum_eff, const float* bias,
+                             const float* residual, const float* post, int post_rows, float* out, void* stream);
+
 /* ---- calibration path (north_star (b)): fp32-accurate GEMM on the bf16 tensor cores ---------------------------------------
  * Replaces the fp32 library GEMM behind `self.fwd_func(input, weight, bias)` (qdiff/quant_layer.py:434) and its autograd
  * dgrad / wgrad while gradients flow (block_reconstruction, qdiff/block_recon.py:152-197).  edadm_split_bf16 writes

@@ -786,6 +786,39 @@ def test_transformer_epilogue_fusions_are_exact(cuda, ctx_tokens, heads):
     assert torch.equal(y1, y0)
 
 
+def test_conv_upsample_on_codes_is_exact(cuda):
+    """`Upsample` with a conv (openaimodel.py Upsample): quantizing the low-resolution tensor and replicating the u8 codes equals
+    quantizing the interpolated tensor, bit for bit, through the whole QuantModule"""
+    from qdiff import QuantModel, set_weight_quantize_params, set_act_quantize_params
+    from unet_zoo.ldm_unet import UNetModel, Upsample
+    torch.manual_seed(23)
+    model = UNetModel(image_size=16, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=1,
+                      attention_resolutions=(), channel_mult=(1, 2), num_heads=1).to(cuda).eval()
+    for p in model.parameters():
+        if p.dim() > 1 and float(p.detach().abs().max()) == 0:
+            torch.nn.init.normal_(p, std=0.02)
+    wq = dict(n_bits=4, symmetric=True, channel_wise=True, scale_method='mse')
+    aq = dict(n_bits=8, symmetric=True, channel_wise=False, scale_method='mse', leaf_param=True, prob=1.0)
+    qnn = QuantModel(model, wq, aq, sm_abit=8).to(cuda).eval()
+    qnn.set_first_last_layer_to_8bit()
+    qnn.disable_network_output_quantization()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(8, 4, 16, 16, generator=g).to(cuda)
+    t = torch.randint(0, 1000, (8,), generator=g).to(cuda)
+    with torch.no_grad():
+        set_weight_quantize_params(qnn, (x, t))
+        set_act_quantize_params(qnn, (x, t))
+        qnn.set_quant_state(True, True)
+        ups = [m for m in qnn.modules() if isinstance(m, Upsample) and m.use_conv]
+        assert ups
+        conv = ups[0].conv
+        h = (torch.randn(8, conv.weight.shape[1], 8, 8, generator=g) * 0.7).to(cuda)
+        y1 = conv.forward_upsample2x(h)
+        assert conv.last_path == 'int8'
+        y0 = conv(F.interpolate(h, scale_factor=2, mode="nearest"))
+    assert y1.shape == y0.shape and torch.equal(y1, y0)
+
+
 @pytest.mark.parametrize("channel_wise,bits,shape,shift", [(False, 8, (8, 64, 16, 16), 0.0), (False, 8, (4, 77, 320), 1.5), (True, 4, (96, 64, 3, 3), 0.0),
                                                             (True, 8, (40, 130), 0.0), (False, 8, (2, 8, 64, 64), 3.0)])
 def test_scale_search_kernel_equals_tensor_op_search(cuda, channel_wise, bits, shape, shift):
