@@ -453,18 +453,21 @@ namespace edadm {
 constexpr int kSearchElems = 16;        // elements a thread keeps in registers per sweep over the candidates
 constexpr int kSearchMaxCand = 128;
 
-// x: [segments][inner]; candidate k of segment s quantizes with (delta[s*K+k], zp[s*K+k]).  scores[s*K+k] += sum_i |Q(x_i) - x_i|^p
-// (fp64; the caller divides by `inner`).  grid = (blocks per segment, segments).
+// x: [segments][inner]; candidate k of segment s quantizes with (delta[s*K+k], zp[s*K+k]).
+// partial[(s * gridDim.x + block) * K + k] = this block's share of sum_i |Q(x_i) - x_i|^p (fp64; the caller divides by `inner`).
+// grid = (blocks per segment, segments).  Every sum has a fixed order (per-warp slots, then warps, then blocks in
+// mse_search_finish_kernel): the scores -- and with them the arg-min over candidates -- are reproducible run to run.
 __global__ void __launch_bounds__(256)
 mse_search_kernel(const float* __restrict__ x, long long inner, const float* __restrict__ delta, const float* __restrict__ zp,
-                  int K, float qmax, float p, double* __restrict__ scores) {
-  __shared__ double acc[kSearchMaxCand];
+                  int K, float qmax, float p, double* __restrict__ partial) {
+  __shared__ double acc[8][kSearchMaxCand];
   __shared__ float sd[kSearchMaxCand], sz[kSearchMaxCand];
   const int seg = blockIdx.y;
   const float* xs = x + (long long)seg * inner;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) { acc[k] = 0.0; sd[k] = __ldg(delta + (long long)seg * K + k); sz[k] = __ldg(zp + (long long)seg * K + k); }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) { sd[k] = __ldg(delta + (long long)seg * K + k); sz[k] = __ldg(zp + (long long)seg * K + k); }
+  for (int i = threadIdx.x; i < 8 * kSearchMaxCand; i += blockDim.x) (&acc[0][0])[i] = 0.0;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long stride = (long long)gridDim.x * blockDim.x * kSearchElems;
   // the trip count is warp-uniform (the shuffles below use the full mask); lanes past the end carry zeros
   for (long long wb = ((long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) * kSearchElems; wb < inner; wb += stride) {
@@ -485,11 +488,26 @@ mse_search_kernel(const float* __restrict__ x, long long inner, const float* __r
       double sdbl = (double)s;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sdbl += __shfl_xor_sync(0xffffffffu, sdbl, o);
-      if (lane == 0) atomicAdd(&acc[k], sdbl);
+      if (lane == 0) acc[warp][k] += sdbl;                 // this warp's own slot
     }
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) if (acc[k] != 0.0) atomicAdd(scores + (long long)seg * K + k, acc[k]);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += acc[w][k];
+    partial[((long long)seg * gridDim.x + blockIdx.x) * K + k] = t;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+mse_search_finish_kernel(const double* __restrict__ partial, int blocks, int K, double* __restrict__ scores) {
+  const int seg = blockIdx.x;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    double t = 0.0;
+    for (int b = 0; b < blocks; ++b) t += partial[((long long)seg * blocks + b) * K + k];
+    scores[(long long)seg * K + k] += t;
+  }
 }
 
 }  // namespace edadm
@@ -506,6 +524,12 @@ extern "C" int edadm_mse_search_scores(const float* x, int64_t segments, int64_t
   const long long cap = std::max<long long>(1, (long long)sm_count() * 8 / segments);
   if (per_seg > cap) per_seg = cap;
   dim3 grid((unsigned)per_seg, (unsigned)segments);
-  mse_search_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, inner, delta, zp, K, (float)(n_levels - 1), p, scores);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* partial = nullptr;                     // stream-ordered scratch: [segments][blocks][K] block partials
+  cudaError_t e = cudaMallocAsync((void**)&partial, sizeof(double) * (size_t)segments * per_seg * K, st);
+  if (e != cudaSuccess) return fail(EDADM_ERR_CUDA, "mse_search_scores: scratch allocation failed: %s", cudaGetErrorString(e));
+  mse_search_kernel<<<grid, 256, 0, st>>>(x, inner, delta, zp, K, (float)(n_levels - 1), p, partial);
+  mse_search_finish_kernel<<<(unsigned)segments, 128, 0, st>>>(partial, (int)per_seg, K, scores);
+  cudaFreeAsync(partial, st);
   return check_launch("mse_search_scores");
 }

@@ -374,9 +374,69 @@ def _batch_strided(x):
     return _f32c(x), 0
 
 
+class CatPair:
+    """`th.cat([a, b], dim=1)` that was never materialised: the skip concatenation of the UNet's up path handed to a ResBlock whose
+    consumers (GroupNorm statistics, the two activation producers) read the two sources in place.  Quacks like a tensor for the
+    shape / device checks on the way; `materialize()` gives the real concatenation wherever a consumer needs one."""
+
+    def __init__(self, a, b):
+        assert a.shape[0] == b.shape[0] and a.shape[2:] == b.shape[2:] and a.dtype == b.dtype
+        self.a, self.b = a, b
+        self._full = None
+        self.shape = torch.Size((a.shape[0], a.shape[1] + b.shape[1]) + tuple(a.shape[2:]))
+        self.dtype, self.device, self.is_cuda, self.requires_grad = a.dtype, a.device, a.is_cuda, a.requires_grad or b.requires_grad
+
+    def dim(self):
+        return len(self.shape)
+
+    def numel(self):
+        return self.a.numel() + self.b.numel()
+
+    def size(self, i=None):
+        return self.shape if i is None else self.shape[i]
+
+    def materialize(self):
+        if self._full is None:
+            self._full = torch.cat([self.a, self.b], dim=1)
+        return self._full
+
+
+def cat_slices_ok(x, split):
+    """a CatPair whose two sources can be quantized into channel slices of one code tensor: boundary on a 16-channel multiple and,
+    when the consumer has split quantizers, exactly at the split"""
+    c0 = x.a.shape[1]
+    return c0 % 16 == 0 and (not split or split == c0) and x.a.dtype == torch.float32 and x.is_cuda
+
+
+def _act_quant_nhwc_cat(x: CatPair, aff, silu, aq: ActQuant, pad: int, cp: int):
+    a, b = _f32c(x.a), _f32c(x.b)
+    B, C0, H, W = a.shape
+    C1 = b.shape[1]
+    C = C0 + C1
+    Cp = max(_round_up(C, 16), int(cp))
+    dev = a.device
+    q = torch.empty((B, H + 2 * pad, W + 2 * pad, Cp), dtype=torch.uint8, device=dev)
+    d0, z0 = _qparam(aq.delta0, dev), _qparam(aq.zp0, dev)
+    d1, z1, l1 = (_qparam(aq.delta1, dev), _qparam(aq.zp1, dev), aq.levels1) if aq.split else (d0, z0, aq.levels0)
+    fa = fs = None
+    if aff is not None:
+        fa, fs = aff
+    for src, coff, cs, d, z, lv in ((a, 0, C0, d0, z0, aq.levels0), (b, C0, Cp - C0, d1, z1, l1)):
+        pa = None if fa is None else fa.data_ptr() + 4 * coff
+        ps = None if fs is None else fs.data_ptr() + 4 * coff
+        lib.act_quant_nhwc_slice(src.data_ptr(), pa, ps, C, int(silu), q.data_ptr(), Cp, coff, B, src.shape[1], H, W, cs, pad,
+                                 d.data_ptr(), z.data_ptr(), lv, _stream())
+    return q, None
+
+
 def act_quant_nhwc(x, aq: ActQuant, pad: int, want_chsum=False, cp: int = 0):
     """x fp32 [B,C,H,W] -> u8 codes [B,H+2p,W+2p,Cp] (halo = zero-point code); Cp = cp or C rounded up to 16."""
     _need_cuda(x)
+    if isinstance(x, CatPair):
+        if want_chsum or aq.prescale != 1.0 or not cat_slices_ok(x, aq.split):
+            x = x.materialize()
+        else:
+            return _act_quant_nhwc_cat(x, None, 0, aq, pad, cp)
     x, bstride = _batch_strided(x)
     B, C, H, W = x.shape
     Cp = max(_round_up(C, 16), int(cp))
@@ -405,14 +465,20 @@ def _cond_rows(scale, shift, B, C):
 def gn_fold(x, gamma, beta, groups, eps, scale=None, shift=None):
     """GroupNorm statistics of x [B,C,...] folded into per-(sample, channel) affine (a, s), both [B, C]."""
     _need_cuda(x)
-    x = _f32c(x)
-    B, C = x.shape[0], x.shape[1]
-    HW = x.numel() // (B * C)
+    pair = x if isinstance(x, CatPair) else None
+    x = _f32c(x.a) if pair is not None else _f32c(x)
+    B, C = x.shape[0], (pair.shape[1] if pair is not None else x.shape[1])
+    HW = x.numel() // (B * x.shape[1])
     a = torch.empty((B, C), dtype=torch.float32, device=x.device)
     s = torch.empty((B, C), dtype=torch.float32, device=x.device)
     g = None if gamma is None else _f32c(gamma.detach())
     b = None if beta is None else _f32c(beta.detach())
     sc, sh, cond_stride = _cond_rows(scale, shift, B, C)
+    if pair is not None:
+        x1 = _f32c(pair.b)
+        lib.gn_fold_cat(x.data_ptr(), x.shape[1], x1.data_ptr(), _ptr(g), _ptr(b), _ptr(sc), _ptr(sh), cond_stride, B, C, HW,
+                        int(groups), float(eps), a.data_ptr(), s.data_ptr(), _stream())
+        return a, s
     lib.gn_fold(x.data_ptr(), _ptr(g), _ptr(b), _ptr(sc), _ptr(sh), cond_stride, B, C, HW, int(groups), float(eps),
                 a.data_ptr(), s.data_ptr(), _stream())
     return a, s
@@ -421,6 +487,11 @@ def gn_fold(x, gamma, beta, groups, eps, scale=None, shift=None):
 def norm_act_quant_nhwc(x, aff_a, aff_s, silu, aq: ActQuant, pad: int, want_chsum=False, cp: int = 0):
     """silu(a*x+s) -> u8 codes [B,H+2p,W+2p,Cp] in one pass (GroupNorm + SiLU + activation quantizer)."""
     _need_cuda(x)
+    if isinstance(x, CatPair):
+        if want_chsum or not cat_slices_ok(x, aq.split):
+            x = x.materialize()
+        else:
+            return _act_quant_nhwc_cat(x, (aff_a, aff_s), silu, aq, pad, cp)
     x = _f32c(x)
     B, C, H, W = x.shape
     Cp = max(_round_up(C, 16), int(cp))

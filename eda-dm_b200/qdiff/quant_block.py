@@ -153,6 +153,29 @@ class QuantResBlock(BaseQuantBlock, *_TimestepBases):
             self.split = split
         return _quant_resblock_forward(self, x, emb, self.split if split != 0 else 0)
 
+    def lazy_cat(self, h, skip, split=0):
+        """The UNet's `th.cat([h, hs.pop()], dim=1)` in front of this block (openaimodel.py UNetModel.forward) as an
+        `edadm.ops.CatPair` -- the concatenation is never written: GroupNorm statistics and both activation producers (in_layers'
+        conv, the split skip_connection) read the two sources in place.  None whenever anything needs the real tensor (hooks of
+        the calibration cache / reconstruction, gradients, fake-quant or FP state, resampling blocks, 8-bit weight row sums)."""
+        from edadm import ops
+        if (th.is_grad_enabled() or self._forward_hooks or self._forward_pre_hooks or self.updown or not backend.fuse_norm or not backend.lazy_cat
+                or not (th.is_tensor(h) and th.is_tensor(skip) and h.is_cuda and h.dtype == th.float32 and skip.dtype == th.float32
+                        and h.dim() == 4 and h.shape[0] == skip.shape[0] and h.shape[2:] == skip.shape[2:])):
+            return None
+        in_conv, out_conv, sc = self.in_layers[-1], self.out_layers[-1], self.skip_connection
+        if not (_prenorm_ok(in_conv, self) and _prenorm_ok(out_conv, self) and isinstance(sc, QuantModule)):
+            return None
+        pair = ops.CatPair(h, skip)
+        c0 = h.shape[1]
+        if not ops.cat_slices_ok(pair, 0) or (split and split != c0) or sc.split != (split or 0) or in_conv.split:
+            return None
+        if sc._forward_hooks or sc._forward_pre_hooks or not sc._integer_path_ok(pair) or not in_conv.prenorm_fusable(pair, self.in_layers[0]):
+            return None
+        if any(p.needs_rowsum or p.w4 for m in (in_conv, sc) for p in m._packed_weights()):
+            return None
+        return pair
+
 
 def _quant_resblock_forward(blk, x, emb, split=0):
     """Dataflow of the LDM ResBlock (reference quant_block.py:86-116) with GroupNorm + SiLU folded into the activation

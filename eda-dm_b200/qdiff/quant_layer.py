@@ -34,6 +34,7 @@ class _Backend:
                              # the codes move by one step); False: ATen's exact forms, codes equal the module-by-module CUDA path
     fused_attention = True   # quantized attention as one tcgen05 kernel (edadm_qattn_fwd); False: fake-quant kernels around library bmm
     search_kernel = True     # scale search: all 100 clipping candidates scored in one pass (edadm_mse_search_scores); False: tensor ops
+    lazy_cat = True          # the up path's skip concatenation is never written: its consumers read the two sources in place (QuantResBlock.lazy_cat)
     fuse_epilogue = True     # linears whose only consumer is the next activation quantizer emit its u8 codes from the GEMM epilogue
     # (4-bit weight storage with in-smem unpack: `edadm.ops.w4_storage`)
     recon_cuda_graph = True  # capture the reconstruction iteration in one CUDA graph after 3 eager iterations
@@ -465,6 +466,9 @@ class QuantModule(nn.Module):
         if split != 0 and self.split == 0:
             self.split = split
             self.set_split()
+        if isinstance(x, ops.CatPair) and not (self.prenorm_fusable(x, norm) and isinstance(norm, nn.GroupNorm) and resample is None
+                                                and not tokens_out):
+            x = x.materialize()
         if not self.prenorm_fusable(x, norm):
             if (backend.fuse_norm and isinstance(norm, nn.GroupNorm) and scale is None and split == 0 and self.split == 0
                     and residual is None and bias_img is None and resample is None and not tokens_out
@@ -724,6 +728,8 @@ class QuantModule(nn.Module):
         result -- `conv(x) + residual` -- inside the GEMM epilogue on the integer path, as a plain add elsewhere.
         `bias_img` (optional, convs): [B, N(,1,1)] added per (image, channel) -- the ResBlock's `h + emb_out`.
         `post` (optional, linears with a residual): [B, 1, N], one row per sample added after the residual."""
+        if isinstance(input, ops.CatPair) and not (self.fwd_func is F.conv2d and self._integer_path_ok(input)):
+            input = input.materialize()
         if post is not None:
             if not (residual is not None and self._post_ok(input, post) and self._epilogue_residual(residual) is not None):
                 return self.forward(input, split=split, residual=residual) + post

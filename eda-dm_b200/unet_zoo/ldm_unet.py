@@ -359,7 +359,12 @@ class UNetModel(nn.Module):
             module = self.output_blocks[k - n_in - 2]
             h = st["h"]
             split = h.shape[1] if self.split_shortcut else 0
-            st["h"] = module(torch.cat([h, st["hs"][-1]], dim=1), st["emb"], st["context"], split=split)
+            # a quantized ResBlock on the integer path reads the two sources of the skip concatenation in place (lazy_cat)
+            lazy = getattr(module[0], "lazy_cat", None) if not (module._forward_hooks or module._forward_pre_hooks) else None
+            inp = lazy(h, st["hs"][-1], split) if lazy is not None else None
+            if inp is None:
+                inp = torch.cat([h, st["hs"][-1]], dim=1)
+            st["h"] = module(inp, st["emb"], st["context"], split=split)
             st["hs"] = st["hs"][:-1]
         else:
             h = st["h"]

@@ -164,6 +164,18 @@ int edadm_qgemm_i8_codes(const uint8_t* q, int64_t M, int Kp_act, const int8_t* 
                          const int32_t* cw, const int32_t* rowsum, const float* bias, int geglu, const float* q_delta,
                          const float* q_zp, int q_levels, uint8_t* out_codes, int out_pitch, int32_t* q_rowsum, void* stream);
 
+/* Skip concatenation without the copy (`h = th.cat([h, hs.pop()], dim=1)` of UNetModel.forward, openaimodel.py, feeding a ResBlock):
+ * edadm_gn_fold_cat = edadm_gn_fold over the virtual concatenation [x0 (C0 channels) | x1 (C - C0)] (a group may straddle both);
+ * edadm_act_quant_nhwc_slice quantizes ONE source into channels [q_c_offset, q_c_offset + Cs) of the shared NHWC code tensor
+ * q [B][H+2p][W+2p][q_pitch] (optional fused affine aff_* [B][aff_pitch], pre-offset to the source's first channel, + SiLU);
+ * called once per source -- with the split quantizers of quant_layer.py:415-419 each source has exactly one quantizer.        */
+int edadm_gn_fold_cat(const float* x0, int C0, const float* x1, const float* gamma, const float* beta, const float* scale,
+                      const float* shift, int64_t cond_stride, int B, int C, int HW, int G, float eps, float* a_out, float* s_out,
+                      void* stream);
+int edadm_act_quant_nhwc_slice(const float* x, const float* aff_a, const float* aff_s, int aff_pitch, int silu, uint8_t* q,
+                               int q_pitch, int q_c_offset, int B, int C, int H, int W, int Cs, int pad, const float* delta,
+                               const float* zp, int n_levels, void* stream);
+
 /* Linear layer with a row-group term after the residual: out[m][n] = ((acc*scale + bias[n]) + residual[m][n]) + post[m / post_rows][n].
  * Replaces `x = attn1(norm1(x)) + x; x = attn2(norm2(x), context) + x` (quant_block.py:254-262) when the context has ONE token
  * (LDM-4 ImageNet class conditioning): softmax over one key is 1, attn2's output is one row per sample, independent of x, and

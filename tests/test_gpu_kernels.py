@@ -786,6 +786,73 @@ def test_transformer_epilogue_fusions_are_exact(cuda, ctx_tokens, heads):
     assert torch.equal(y1, y0)
 
 
+@pytest.mark.parametrize("split", [True, False])
+def test_lazy_skip_concatenation_is_exact(cuda, split):
+    """up path of an LDM UNet with the skip concatenation never materialised (two-source GroupNorm statistics, one producer launch
+    per source into channel slices of the code tensor, split quantizers at the boundary) vs th.cat: identical output"""
+    from qdiff import QuantModel, set_weight_quantize_params, set_act_quantize_params
+    from qdiff.quant_layer import backend
+    from edadm import ops
+    from unet_zoo.ldm_unet import UNetModel
+    torch.manual_seed(29)
+    model = UNetModel(image_size=16, in_channels=4, model_channels=64, out_channels=4, num_res_blocks=2,
+                      attention_resolutions=(), channel_mult=(1, 2, 3), num_heads=1).to(cuda).eval()
+    for p in model.parameters():
+        if p.dim() > 1 and float(p.detach().abs().max()) == 0:
+            torch.nn.init.normal_(p, std=0.02)
+    model.split_shortcut = split
+    wq = dict(n_bits=4, symmetric=True, channel_wise=True, scale_method='mse')
+    aq = dict(n_bits=8, symmetric=True, channel_wise=False, scale_method='mse', leaf_param=True, prob=1.0)
+    qnn = QuantModel(model, wq, aq, sm_abit=8).to(cuda).eval()
+    qnn.set_first_last_layer_to_8bit()
+    qnn.disable_network_output_quantization()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(8, 4, 16, 16, generator=g).to(cuda)
+    t = torch.randint(0, 1000, (8,), generator=g).to(cuda)
+    made = []
+    orig = ops.CatPair.__init__
+    with torch.no_grad():
+        set_weight_quantize_params(qnn, (x, t))
+        set_act_quantize_params(qnn, (x, t), all_attention=True)
+        qnn.set_quant_state(True, True)
+        ops.CatPair.__init__ = lambda self, a, b: (made.append(1), orig(self, a, b))[1]
+        try:
+            y1 = qnn(x, t)
+        finally:
+            ops.CatPair.__init__ = orig
+        n_lazy = len(made)
+        backend.lazy_cat = False
+        try:
+            y0 = qnn(x, t)
+        finally:
+            backend.lazy_cat = True
+    assert n_lazy >= 4, n_lazy                 # the up path really took the two-source route
+    assert torch.equal(y1, y0)
+
+
+def test_scale_search_is_reproducible(cuda):
+    """the one-pass candidate scoring sums in a fixed order: scores (and the chosen step size) are bit-identical run to run, so a
+    quantizer initialised twice on the same tensor gets the same (delta, zero_point)"""
+    from edadm import ops
+    from qdiff.quant_layer import UniformAffineQuantizer
+    g = torch.Generator().manual_seed(41)
+    x = (torch.randn(6, 192, 40, 40, generator=g) * 0.8).to(cuda)
+    res = []
+    for i in range(5):
+        junk = torch.empty(1 << (20 + i), device=cuda).normal_()          # different allocator / scheduling state per round
+        q = UniformAffineQuantizer(n_bits=8, symmetric=True, channel_wise=False, scale_method='mse', leaf_param=True)
+        q(x)
+        res.append((q.delta.detach().clone(), q.zero_point.clone()))
+        del junk
+    assert all(torch.equal(r[0], res[0][0]) and torch.equal(r[1], res[0][1]) for r in res[1:])
+    K = 100
+    delta = (torch.linspace(0.2, 1.0, K) * (x.abs().max().item() * 2 / 255)).to(cuda)
+    zp = torch.full((K,), 128.0, device=cuda)
+    s0 = ops.mse_search_scores(x.reshape(1, -1), delta.reshape(1, K), zp.reshape(1, K), 256, 2.4)
+    for _ in range(4):
+        assert torch.equal(ops.mse_search_scores(x.reshape(1, -1), delta.reshape(1, K), zp.reshape(1, K), 256, 2.4), s0)
+
+
 def test_conv_upsample_on_codes_is_exact(cuda):
     """`Upsample` with a conv (openaimodel.py Upsample): quantizing the low-resolution tensor and replicating the u8 codes equals
     quantizing the interpolated tensor, bit for bit, through the whole QuantModule"""
