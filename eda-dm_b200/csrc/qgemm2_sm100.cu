@@ -76,6 +76,25 @@ __device__ __forceinline__ uint32_t q_code(float x, float d, float inv_d, float 
   return (uint32_t)(__float_as_int(t) - 0x4B400000 + (int)z);
 }
 
+// v[j] = (acc[j] + zterm[j] (+ cw[j] * rowsum)) * scale[j] + bias[j] for 16 consecutive columns (pointers 16-byte aligned)
+__device__ __forceinline__ void dequant16(const uint32_t (&acc)[16], float (&v)[16], const int* __restrict__ zterm,
+                                          const float* __restrict__ scale, const float* __restrict__ bias, const int* __restrict__ cw, int rs) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int4 z = reinterpret_cast<const int4*>(zterm)[k];
+    const float4 s4 = reinterpret_cast<const float4*>(scale)[k];
+    const float4 b4 = reinterpret_cast<const float4*>(bias)[k];
+    if (cw) {                                     // 8-bit weight codes with a zero-point off 128: warp-uniform, rare
+      const int4 c4 = reinterpret_cast<const int4*>(cw)[k];
+      z.x += c4.x * rs; z.y += c4.y * rs; z.z += c4.z * rs; z.w += c4.w * rs;
+    }
+    v[4 * k + 0] = fmaf((float)((int)acc[4 * k + 0] + z.x), s4.x, b4.x);
+    v[4 * k + 1] = fmaf((float)((int)acc[4 * k + 1] + z.y), s4.y, b4.y);
+    v[4 * k + 2] = fmaf((float)((int)acc[4 * k + 2] + z.z), s4.z, b4.z);
+    v[4 * k + 3] = fmaf((float)((int)acc[4 * k + 3] + z.w), s4.w, b4.w);
+  }
+}
+
 template <int CTAS>
 __global__ void __launch_bounds__(THREADS, 1)
 qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -302,11 +321,8 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             else mbar_arrive(&bars->tmem_empty[acc]);
           }
         }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int iv = (int)a[j] + epi_zterm[c0 + j] + (has_cw ? epi_cw[c0 + j] * rs : 0);
-          v[j] = fmaf((float)iv, epi_scale[c0 + j], epi_bias[c0 + j]);
-        }
+        // dequantise: exact int32 zero-point fold, one fp32 FMA; the per-column constants come as 128-bit broadcast loads
+        dequant16(a, v, epi_zterm + c0, epi_scale + c0, epi_bias + c0, has_cw ? epi_cw + c0 : nullptr, rs);
         uint8_t* ob = out_buf + (gchunk & 1u) * OUT_BUF_BYTES;
         if (p.res_mode == 1) {
           const int rb = (int)((rchunk + ci) % (uint32_t)p.res_bufs);
@@ -330,13 +346,11 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         uint32_t codes[4];
         if (mode >= OUT_U8_ROWS) {
           if (mode == OUT_U8_GEGLU) {
+            const int cg = p.block_n / 2 + c0;
+            float gate[16];
+            dequant16(g, gate, epi_zterm + cg, epi_scale + cg, epi_bias + cg, has_cw ? epi_cw + cg : nullptr, rs);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int cg = p.block_n / 2 + c0 + j;
-              const int ig = (int)g[j] + epi_zterm[cg] + (has_cw ? epi_cw[cg] * rs : 0);
-              const float gate = fmaf((float)ig, epi_scale[cg], epi_bias[cg]);
-              v[j] = v[j] * gelu_erf(gate);
-            }
+            for (int j = 0; j < 16; ++j) v[j] = v[j] * gelu_erf(gate[j]);
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k)
