@@ -262,6 +262,7 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t gchunk = 0;                          // running chunk counter: staging buffer = gchunk & 1
+    uint32_t tile_par = 0;                        // code outputs: staging buffer of the current tile
     uint32_t rchunk = 0;                          // running residual chunk counter: buffer = rchunk % res_bufs
     uint32_t rphase_bits = 0;                     // phase bit per residual buffer
     for (int unit = unit0; unit < num_units; unit += unit_step) {
@@ -295,6 +296,10 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       if (p.res_mode == 1 && issuer) {
         for (int ci = 0; ci < p.res_bufs && ci < n_chunks; ++ci) issue_res(ci);
       }
+      // code outputs: the whole tile is staged in one buffer (alternating per tile); the store that used it two tiles ago has drained
+      const int wout = n_chunks * CHUNK;
+      uint8_t* tile_buf = out_buf + (tile_par & 1u) * OUT_BUF_BYTES;
+      if (mode >= OUT_U8_ROWS && issuer) bulk_wait_read<1>();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const int m = m0 + r;
       const int rs = (has_cw && m < p.M) ? __ldg(p.rowsum + m) : 0;
@@ -367,6 +372,10 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             }
           }
         }
+        if (mode >= OUT_U8_ROWS) {                // tile-wide staging: no per-chunk synchronisation, one store after the loop
+          *reinterpret_cast<uint4*>(tile_buf + r * wout + ci * CHUNK + 16 * half) = make_uint4(codes[0], codes[1], codes[2], codes[3]);
+          continue;
+        }
         if (issuer) bulk_wait_read<1>();          // the store issued two chunks ago has drained its staging buffer
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (mode == OUT_F32_ROWS) {
@@ -375,8 +384,6 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         } else if (mode == OUT_F32_NCHW) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(ob + nchw_off + j * nchw_cstride) = v[j];
-        } else {
-          *reinterpret_cast<uint4*>(ob + r * CHUNK + 16 * half) = make_uint4(codes[0], codes[1], codes[2], codes[3]);
         }
         fence_proxy_async();
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -386,6 +393,12 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           bulk_commit();
           if (p.res_mode == 1 && ci + p.res_bufs < n_chunks) issue_res(ci + p.res_bufs);
         }
+      }
+      if (mode >= OUT_U8_ROWS) {
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (issuer) { tma_store_2d(&map_out, tile_buf, co0, co1); bulk_commit(); }
+        ++tile_par;
       }
       if (p.res_mode == 1) rchunk += (uint32_t)n_chunks;
       if (p.q_rowsum && mode >= OUT_U8_ROWS) {
@@ -408,10 +421,10 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 
 // N tile (multiple of 32, <= 256): fewest waves first, then the widest tile (per-MMA cost is nearly flat below N = 192,
 // profiles/int8_peak_r02.txt), i.e. the same wave/bytes model as the first-generation kernel
-static int pick_block_n(int N, int m_units, int workers, int step) {
+static int pick_block_n(int N, int m_units, int workers, int step, int max_bn = MAX_BN) {
   int best = 0;
   long long best_cost = 0;
-  for (int bn = step; bn <= MAX_BN; bn += step) {
+  for (int bn = step; bn <= max_bn; bn += step) {
     const long long tiles = (long long)m_units * ((N + bn - 1) / bn);
     const long long waves = (tiles + workers - 1) / workers;
     const long long cost = waves * (bn + 192);
@@ -476,8 +489,11 @@ int launch_qgemm2(const Gemm2Args& a, void* stream) {
   }
 
   const int m_tiles = (int)((M + BM - 1) / BM);
-  // CTA pairs when there is enough work to keep 74 pairs busy for at least two rounds
-  int ctas = (m_tiles >= 2 * 148) ? 2 : 1;
+  // CTA pairs when there is enough work to keep 74 pairs busy for at least two rounds AND the main loop is long enough for the
+  // halved weight traffic to matter: with a handful of K steps per tile (the transformer linears, K = 384 .. 960) the tile time is
+  // its epilogue and the pair's cluster handshakes only cost (measured: 131072 x 3072 x 384 GEGLU 588 -> 533 us with single CTAs)
+  const int k_steps_128 = a.R * a.S * ((a.Cp_w + 127) / 128);
+  int ctas = (m_tiles >= 2 * 148 && k_steps_128 >= 8) ? 2 : 1;
   if (const char* e = getenv("EDADM_GEMM_CTAS")) { const int v = atoi(e); if (v == 1 || v == 2) ctas = v; }
   const int sms = sm_count();
   const int workers = ctas == 2 ? sms / 2 : sms;
@@ -488,7 +504,8 @@ int launch_qgemm2(const Gemm2Args& a, void* stream) {
     const int bh = (h % 128 == 0) ? 128 : (h % 96 == 0) ? 96 : (h % 64 == 0) ? 64 : 32;
     block_n = 2 * bh;
   } else {
-    block_n = pick_block_n(a.N, m_units, workers, 32);
+    // code outputs stage a whole tile (128 rows x block_n bytes <= one 16 KB buffer) and leave with ONE TMA store per tile
+    block_n = pick_block_n(a.N, m_units, workers, 32, mode == OUT_U8_ROWS ? 128 : MAX_BN);
   }
   const int n_tiles = mode == OUT_U8_GEGLU ? (a.N / 2) / (block_n / 2) : (a.N + block_n - 1) / block_n;
   if (a.Np < a.N) return fail(EDADM_ERR_ARG, "qgemm2: weight rows Np=%d < N=%d", a.Np, a.N);
@@ -532,7 +549,7 @@ int launch_qgemm2(const Gemm2Args& a, void* stream) {
   } else {
     cuuint64_t dims[2] = {(cuuint64_t)a.out_pitch, (cuuint64_t)M};
     cuuint64_t strides[1] = {(cuuint64_t)a.out_pitch};
-    cuuint32_t box[2] = {(cuuint32_t)CHUNK, (cuuint32_t)BM};
+    cuuint32_t box[2] = {(cuuint32_t)(mode == OUT_U8_GEGLU ? block_n / 2 : block_n), (cuuint32_t)BM};
     int rc = encode_map(&map_out, a.out, 2, dims, strides, box, "codes", CU_TENSOR_MAP_DATA_TYPE_UINT8, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
     map_res = map_out;

@@ -56,6 +56,7 @@ struct GemmParams {
   const float* bias_img;   // optional fp32 [images][N]: per-(image, channel) term added like a residual (timestep embedding)
   const float* post;       // row-major outputs only: optional fp32 [M / post_rows][N] added AFTER the residual, one row per group of
   int post_rows;           //   post_rows consecutive output rows (the one-key cross-attention term of a transformer block)
+  int post_shift;          //   log2(post_rows) when it is a power of two, else -1
   const float* delta_a;     // device scalars (nn.Parameter storage): no host sync on the path
   const float* zp_a;
   const float* delta_w;     // [N]
@@ -410,7 +411,8 @@ qgemm_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               float4 v = *reinterpret_cast<const float4*>(tile_s + rr * ROW_STAGE_LD + cq);
               if (has_res) { v.x += tres[i].x; v.y += tres[i].y; v.z += tres[i].z; v.w += tres[i].w; }
               if (p.post) {
-                const float4 pv = __ldg(reinterpret_cast<const float4*>(p.post + (long long)(mm / p.post_rows) * p.N + ncol));
+                const int grp = p.post_shift >= 0 ? (mm >> p.post_shift) : mm / p.post_rows;      // (token counts are powers of two)
+                const float4 pv = __ldg(reinterpret_cast<const float4*>(p.post + (long long)grp * p.N + ncol));
                 v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
               }
               *reinterpret_cast<float4*>(p.out + (long long)mm * p.N + ncol) = v;
@@ -643,7 +645,8 @@ static int launch_qgemm(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int
   if (const char* e = getenv("EDADM_GEMM_STAGES")) { const int v = atoi(e); if (v >= 2 && v < p.stages) p.stages = v; }   // debug
   const int smem_bytes = fixed + p.stages * (BLOCK_M * kbytes + p.b_stage_bytes);
   p.out_hw = out_hw; p.accumulate = accumulate; p.silu = silu; p.residual = residual; p.bias_img = bias_img;
-  p.post = post; p.post_rows = post_rows;
+  p.post = post; p.post_rows = post_rows; p.post_shift = -1;
+  if (post_rows > 0 && (post_rows & (post_rows - 1)) == 0) { p.post_shift = 0; while ((1 << p.post_shift) < post_rows) ++p.post_shift; }
   if (post && (!p.row_staging || post_rows < 1 || (M % post_rows) || (reinterpret_cast<uintptr_t>(post) & 15)))
     return fail(EDADM_ERR_UNSUPPORTED, "qgemm_i8: the row-group term needs a staged row-major output (N %% 4 == 0, no rowsum / accumulate) and post_rows dividing M");
   p.delta_a = delta_a; p.zp_a = zp_a; p.delta_w = delta_w; p.wsum_eff = wsum_eff; p.cw = cw; p.rowsum = rowsum;
