@@ -4,6 +4,8 @@
 // memory-bound stencil that library implicit-GEMM kernels handle poorly (one 0.49 ms launch in the LSUN-church step);
 // here a block owns an 8 x 32 pixel tile, four thread groups split the input channels, and every thread keeps the 27..36
 // weights of a channel in registers for four horizontally adjacent pixels (7 + 18 shared-memory loads per 108 FMAs).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace edadm {
@@ -42,46 +44,92 @@ conv3x3_small_n_kernel(const float* __restrict__ x, const float* __restrict__ w,
   const int steps = (c_per_group + CS_CCH - 1) / CS_CCH;             // same trip count for every group (block barriers)
   // patch elements of one step handled by this thread (CS_CCH * CS_PH * 34 = 1360 values over 64 threads -> 22 each); the
   // values of step s+1 are requested into registers before step s is computed, so global latency overlaps the FMAs.
-  // Optional per-(image, channel) affine + SiLU on load: the GroupNorm + SiLU in front of the output conv (edadm_gn_fold).
+  // Where each patch element lives does not depend on the step: a table built once per block holds its offset inside the
+  // step's 4-channel slab (packed with the channel index, -1 outside the image), so a fetch is one table read + one load.
+  // Optional per-(image, channel) affine + SiLU on load: the GroupNorm + SiLU in front of the output conv (edadm_gn_fold),
+  // in the same branch-free arithmetic as the activation producers (pack.cu norm_act_m).
   constexpr int PER_T = (CS_CCH * CS_PH * 34 + 63) / 64;
+  __shared__ int tbl[CS_CCH * CS_PH * 34];
+  for (int i = threadIdx.x; i < CS_CCH * CS_PH * 34; i += 256) {
+    const int col = i % 34, r = i / 34, row = r % CS_PH, cc = r / CS_PH;
+    const int iy = ty0 + row - 1, ix = tx0 + col - 1;
+    tbl[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? (((cc * H + iy) * W + ix) << 2 | cc) : -1;
+  }
+  __syncthreads();
   float stage[PER_T];
+  // fetch: raw loads only (they stay in flight while the previous step's FMAs run); the activation is applied when the values
+  // are committed to shared memory one step later
   auto fetch = [&](int s) {
     const int c0 = cbeg + s * CS_CCH;
+    const float* xs = xb + (size_t)c0 * H * W;
+    const int live = cend - c0;                                       // channels of this step that exist (<= 0 .. CS_CCH)
 #pragma unroll
     for (int u = 0; u < PER_T; ++u) {
       const int i = tg + u * 64;
       float v = 0.f;
       if (i < CS_CCH * CS_PH * 34) {
-        const int col = i % 34, r = i / 34, row = r % CS_PH, cc = r / CS_PH;
-        const int c = c0 + cc, iy = ty0 + row - 1, ix = tx0 + col - 1;
-        if (c < cend && iy >= 0 && iy < H && ix >= 0 && ix < W) {
-          v = __ldg(xb + ((size_t)c * H + iy) * W + ix);
-          if (aff_a) {
-            v = fmaf(v, __ldg(aff_a + (size_t)b * C + c), __ldg(aff_s + (size_t)b * C + c));
-            if (silu & 16) v = __fdividef(v, 1.0f + __expf(-v));
-            else if (silu == 2) v = v * (1.0f / (1.0f + expf(-v)));
-            else if (silu) v = v / (1.0f + expf(-v));
-          }
-        }
+        const int e = tbl[i];
+        if (e >= 0 && (e & 3) < live) v = __ldg(xs + (e >> 2));
       }
       stage[u] = v;
     }
   };
-  auto commit = [&]() {
+  auto commit_mode = [&](int s, auto mode_tag) {
+    constexpr int MODE = decltype(mode_tag)::value;
+    const int c0 = cbeg + s * CS_CCH;
+    const int live = cend - c0;
+    float a4[CS_CCH], s4[CS_CCH];
+#pragma unroll
+    for (int cc = 0; cc < CS_CCH; ++cc) {
+      const bool ok = MODE >= 0 && cc < live;
+      a4[cc] = ok ? __ldg(aff_a + (size_t)b * C + c0 + cc) : 1.f;
+      s4[cc] = ok ? __ldg(aff_s + (size_t)b * C + c0 + cc) : 0.f;
+    }
 #pragma unroll
     for (int u = 0; u < PER_T; ++u) {
       const int i = tg + u * 64;
       if (i < CS_CCH * CS_PH * 34) {
-        const int col = i % 34, r = i / 34, row = r % CS_PH, cc = r / CS_PH;
-        pg[(cc * CS_PH + row) * CS_PW + col] = stage[u];
+        float v = stage[u];
+        const int e = tbl[i];
+        const int cc = e & 3;
+        if (MODE >= 0 && e >= 0 && cc < live) {                      // zero padding applies AFTER the activation
+          v = fmaf(v, a4[cc], s4[cc]);
+          if (MODE == 17) v = __fdividef(v, 1.0f + __expf(-v));
+          else if (MODE == 1) {            // v / (1 + expf(-v)), IEEE quotient (see pack.cu)
+            const float d = fminf(__fadd_rn(1.0f, expf(-v)), 8.507059e37f);
+            float r;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+            r = fmaf(r, fmaf(-d, r, 1.0f), r);
+            const float q0 = __fmul_rn(v, r);
+            v = fmaf(fmaf(-d, q0, v), r, q0);
+          } else if (MODE == 2) {          // v * sigmoid(v) with the IEEE reciprocal
+            const float d = fminf(__fadd_rn(1.0f, expf(-v)), 8.507059e37f);
+            float r;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+            r = fmaf(r, fmaf(-d, r, 1.0f), r);
+            v = __fmul_rn(v, r);
+          }
+        }
+        const int col = i % 34, rr = i / 34;                          // rr = cc * CS_PH + row
+        pg[rr * CS_PW + col] = v;
       }
+    }
+  };
+  const int mode = !aff_a ? -1 : ((silu & 16) ? ((silu & 3) ? 17 : 0) : silu);
+  auto commit = [&](int s) {
+    switch (mode) {
+      case -1: commit_mode(s, std::integral_constant<int, -1>{}); break;
+      case 0: commit_mode(s, std::integral_constant<int, 0>{}); break;
+      case 1: commit_mode(s, std::integral_constant<int, 1>{}); break;
+      case 2: commit_mode(s, std::integral_constant<int, 2>{}); break;
+      default: commit_mode(s, std::integral_constant<int, 17>{}); break;
     }
   };
   fetch(0);
   for (int s = 0; s < steps; ++s) {
     const int c0 = cbeg + s * CS_CCH;
     __syncthreads();                 // previous step's reads of the patch are done
-    commit();
+    commit(s);
     __syncthreads();
     if (s + 1 < steps) fetch(s + 1);
 #pragma unroll
