@@ -45,8 +45,8 @@ __device__ __forceinline__ uint32_t pack_sat_u8(int a, int b, uint32_t c) {
 constexpr int ATT_M = 128;
 constexpr int ATT_S = 128;
 constexpr int ATT_KB = 128;
-constexpr int QK_STAGES = 3;
-constexpr int V_STAGES = 2;
+constexpr int QK_STAGES = 8;                    // upper bound of the K (or Q+K) smem ring; the launch picks what fits
+constexpr int V_STAGES = 2;                     // upper bound; 1 when a V tile is larger than 32 KB
 constexpr int ATT_TILE_BYTES = 128 * 128;       // 16 KB: Q chunk, K chunk, P tile
 constexpr int V_TILE_BYTES = 256 * 128;         // 32 KB
 constexpr int SM_PARTS = 4;                 // softmax threads per query row
@@ -60,7 +60,10 @@ struct AttnParams {
   int k_chunks, k_last_mmas, s_tiles;
   int d_chunk, heads;
   int s_bufs;                // S accumulators in TMEM: 2 (d_chunk <= 256) or 1 (d_chunk <= 384, O takes columns [128, 512))
-  int qk_stages;             // Q / K smem ring depth (3, or 2 when the V tiles are 48 KB)
+  int qk_stages;             // K (q_resident) or Q+K smem ring depth
+  int q_resident;            // 1: the CTA's Q tile (k_chunks x 16 KB) is loaded once and stays in smem; 0: Q chunks ride with the K chunks
+  int v_stages;              // V smem ring depth (2, or 1 for tiles above 32 KB)
+  int q_bytes;               // smem reserved for Q: k_chunks x 16 KB (resident) or qk_stages x 16 KB (streamed)
   int v_halves;              // 1, or 2 when d_chunk > 256: V tile loaded and multiplied as two halves (TMA box / UMMA N <= 256)
   int v_stage_bytes;
   long long o_sb, o_sh, o_st, o_sc;
@@ -76,7 +79,7 @@ struct __align__(8) AttnBarriers {
   uint64_t v_full[V_STAGES], v_empty[V_STAGES];
   uint64_t s_full[2], s_empty[2];
   uint64_t p_full[2], p_empty[2];
-  uint64_t o_full;
+  uint64_t o_full, q_full;
   uint32_t tmem_base;
 };
 
@@ -93,9 +96,9 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer (LDS/STS)
   uint8_t* smem_q = smem;
-  uint8_t* smem_k = smem_q + p.qk_stages * ATT_TILE_BYTES;
+  uint8_t* smem_k = smem_q + p.q_bytes;
   uint8_t* smem_v = smem_k + p.qk_stages * ATT_TILE_BYTES;
-  uint8_t* smem_p = smem_v + V_STAGES * p.v_stage_bytes;
+  uint8_t* smem_p = smem_v + p.v_stages * p.v_stage_bytes;
   AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(smem_p + 2 * ATT_TILE_BYTES);
   int* colint = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [s_tiles*128]: bias - zq*rk[s]
 
@@ -115,6 +118,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
       mbar_init(&bars->p_full[i], SM_WARPS); mbar_init(&bars->p_empty[i], 1);
     }
     mbar_init(&bars->o_full, 1);
+    mbar_init(&bars->q_full, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -133,13 +137,20 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0;
     int vs = 0; uint32_t vphase = 0;
+    if (p.q_resident) {            // the CTA's queries: loaded once, read by every S = Q.K^T of both passes
+      if (elect_one()) {
+        mbar_expect_tx(&bars->q_full, (uint32_t)p.k_chunks * ATT_TILE_BYTES);
+        for (int kc = 0; kc < p.k_chunks; ++kc) tma_load_3d(smem_q + kc * ATT_TILE_BYTES, &map_q, &bars->q_full, kc * ATT_KB, q0, bh);
+      }
+      __syncwarp();
+    }
     for (int pass = 0; pass < 2; ++pass) {
       for (int j = 0; j < p.s_tiles; ++j) {
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           mbar_wait(&bars->qk_empty[stage], phase ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(&bars->qk_full[stage], 2 * ATT_TILE_BYTES);
-            tma_load_3d(smem_q + stage * ATT_TILE_BYTES, &map_q, &bars->qk_full[stage], kc * ATT_KB, q0, bh);
+            mbar_expect_tx(&bars->qk_full[stage], (p.q_resident ? 1 : 2) * ATT_TILE_BYTES);
+            if (!p.q_resident) tma_load_3d(smem_q + stage * ATT_TILE_BYTES, &map_q, &bars->qk_full[stage], kc * ATT_KB, q0, bh);
             tma_load_3d(smem_k + stage * ATT_TILE_BYTES, &map_k, &bars->qk_full[stage], kc * ATT_KB, j * ATT_S, bh);
           }
           __syncwarp();
@@ -155,7 +166,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
               tma_load_3d(smem_v + vs * p.v_stage_bytes + vrows * ATT_KB, &map_v, &bars->v_full[vs], j * ATT_S, dc * p.d_chunk + vrows, bh);
           }
           __syncwarp();
-          if (++vs == V_STAGES) { vs = 0; vphase ^= 1; }
+          if (++vs == p.v_stages) { vs = 0; vphase ^= 1; }
         }
       }
     }
@@ -191,8 +202,9 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         umma_commit(&bars->p_empty[pb]);
       }
       __syncwarp();
-      if (++vs == V_STAGES) { vs = 0; vphase ^= 1; }
+      if (++vs == p.v_stages) { vs = 0; vphase ^= 1; }
     };
+    if (p.q_resident) { mbar_wait(&bars->q_full, 0); tc_fence_after(); }
     int g = 0;
     for (int pass = 0; pass < 2; ++pass) {
       for (int j = 0; j < p.s_tiles; ++j, ++g) {
@@ -204,7 +216,7 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
           const int nmma = (kc == p.k_chunks - 1) ? p.k_last_mmas : ATT_KB / UMMA_K;
           mbar_wait(&bars->qk_full[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc(q_base + stage * ATT_TILE_BYTES);
+          const uint64_t adesc = make_smem_desc(q_base + (p.q_resident ? kc : stage) * ATT_TILE_BYTES);
           const uint64_t bdesc = make_smem_desc(k_base + stage * ATT_TILE_BYTES);
           if (elect_one()) {
             umma_i8(tmem_s, adesc, bdesc, idesc_s, kc ? 1u : 0u);
@@ -448,15 +460,36 @@ qattn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     const int b = bh / p.heads, h = bh - b * p.heads;
     float* obase = p.out + b * p.o_sb + h * p.o_sh + (long long)t * p.o_st;
     const int row_o = p.Tk * zp_i * zv - zv * rp;
+    // channel-contiguous outputs ([B, T, heads*d]): a thread owns 16 consecutive floats of its row per step -> four 16-byte stores
+    // (the scalar form costs one 32-byte sector transaction per element: 49 152 per CTA at d = 384)
+    const bool vec_out = p.o_sc == 1 && ((p.o_sb | p.o_sh | p.o_st) & 3) == 0 && (p.d & 3) == 0 && (p.d_chunk & 3) == 0 &&
+                         (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
     for (int c0 = part * 16; c0 < p.d_chunk; c0 += 16 * SM_PARTS) {
       uint32_t raw[16];
       tmem_ld16(lane_addr + 128u * p.s_bufs + c0, raw);
       tmem_ld_wait();
       if (row_ok) {
+        const int cb = dc * p.d_chunk + c0;
+        if (vec_out) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c = dc * p.d_chunk + c0 + i;
-          if (c < p.d) obase[(long long)c * p.o_sc] = (float)((int)raw[i] + row_o - zp_i * __ldg(rv + c)) * oscale;
+          for (int k = 0; k < 4; ++k) {
+            const int c = cb + 4 * k;
+            if (c < p.d) {                                              // d % 4 == 0: the four channels are all inside
+              const int4 r4 = __ldg(reinterpret_cast<const int4*>(rv + c));
+              float4 o;
+              o.x = (float)((int)raw[4 * k + 0] + row_o - zp_i * r4.x) * oscale;
+              o.y = (float)((int)raw[4 * k + 1] + row_o - zp_i * r4.y) * oscale;
+              o.z = (float)((int)raw[4 * k + 2] + row_o - zp_i * r4.z) * oscale;
+              o.w = (float)((int)raw[4 * k + 3] + row_o - zp_i * r4.w) * oscale;
+              *reinterpret_cast<float4*>(obase + c) = o;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = cb + i;
+            if (c < p.d) obase[(long long)c * p.o_sc] = (float)((int)raw[i] + row_o - zp_i * __ldg(rv + c)) * oscale;
+          }
         }
       }
     }
@@ -506,9 +539,23 @@ extern "C" int edadm_qattn_fwd(const uint8_t* qc, const uint8_t* kc, const uint8
   p.v_halves = p.d_chunk > 256 ? 2 : 1;
   if (p.v_halves == 2) p.d_chunk = (p.d_chunk + 31) & ~31;
   p.v_stage_bytes = (p.d_chunk * ATT_KB + 1023) & ~1023;
-  p.qk_stages = QK_STAGES;
-  while (p.qk_stages > 2 && 1024 + p.qk_stages * 2 * ATT_TILE_BYTES + V_STAGES * p.v_stage_bytes + 2 * ATT_TILE_BYTES + 256 + ATT_MAX_KEYS * 4 > ATT_SMEM_BYTES) --p.qk_stages;
-  const int att_smem = 1024 + p.qk_stages * 2 * ATT_TILE_BYTES + V_STAGES * p.v_stage_bytes + 2 * ATT_TILE_BYTES + 256 + ATT_MAX_KEYS * 4;
+  // shared memory: [Q][K ring][V ring][2 P tiles][barriers][per-key terms].  The queries of the CTA stay resident when their
+  // k_chunks x 16 KB leave room for a K ring of at least 3 tiles (every S tile of both passes re-reads them: streaming them with
+  // the K chunks doubled the operand traffic and halved the useful bytes in flight); V is double-buffered up to 32 KB tiles.
+  p.v_stages = p.v_stage_bytes > 32 * 1024 ? 1 : V_STAGES;
+  const int colint_bytes = p.s_tiles * ATT_S * 4;
+  const int fixed_smem = 1024 + p.v_stages * p.v_stage_bytes + 2 * ATT_TILE_BYTES + 256 + colint_bytes;
+  p.q_resident = (ATT_SMEM_BYTES - fixed_smem - p.k_chunks * ATT_TILE_BYTES) / ATT_TILE_BYTES >= 3 ? 1 : 0;
+  if (const char* e = getenv("EDADM_ATTN_QRES")) p.q_resident = atoi(e) && p.q_resident;
+  if (p.q_resident) {
+    p.qk_stages = std::min(QK_STAGES, (ATT_SMEM_BYTES - fixed_smem - p.k_chunks * ATT_TILE_BYTES) / ATT_TILE_BYTES);
+    p.q_bytes = p.k_chunks * ATT_TILE_BYTES;
+  } else {
+    p.qk_stages = std::min(QK_STAGES, (ATT_SMEM_BYTES - fixed_smem) / (2 * ATT_TILE_BYTES));
+    p.q_bytes = p.qk_stages * ATT_TILE_BYTES;
+  }
+  const int att_smem = fixed_smem + p.q_bytes + p.qk_stages * ATT_TILE_BYTES;
+  if (p.qk_stages < 2) return fail(EDADM_ERR_UNSUPPORTED, "qattn_fwd: shared memory budget exceeded (d_chunk %d)", p.d_chunk);
   if (att_smem > ATT_SMEM_BYTES) return fail(EDADM_ERR_UNSUPPORTED, "qattn_fwd: shared memory budget exceeded (d_chunk %d)", p.d_chunk);
   p.heads = heads;
   p.o_sb = o_sb; p.o_sh = o_sh; p.o_st = o_st; p.o_sc = o_sc;
