@@ -38,6 +38,10 @@ struct Params {
   int M, N, taps, S;
   int kbytes, k_chunks, k_last_mmas;
   int a_c_offset;
+  // split shortcut (two quantizer pairs along K, quant_layer.py:415-432): a second K range with its own weights / scales, summed
+  // into a second TMEM accumulator (columns + block_n) and combined in the epilogue -- one launch, no fp32 round trip between them
+  int dual, k_chunks1, k_last_mmas1, a_c_offset1;
+  const float* delta_a1; const float* zp_a1; const float* delta_w1; const int32_t* wsum_eff1;
   int Wo, HoWo;
   int block_n, n_tiles, m_units;            // m_units = ceil(m_tiles / CTAS): scheduling units along M
   int stages, a_stage_bytes, b_stage_bytes;
@@ -98,7 +102,8 @@ __device__ __forceinline__ void dequant16(const uint32_t (&acc)[16], float (&v)[
 template <int CTAS>
 __global__ void __launch_bounds__(THREADS, 1)
 qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-              const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, Params p) {
+              const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
+              const __grid_constant__ CUtensorMap map_b1, Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
@@ -117,7 +122,8 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   const int unit0 = CTAS == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
   const int unit_step = CTAS == 2 ? (int)num_clusters_x() : (int)gridDim.x;
   const int num_units = p.m_units * p.n_tiles;
-  const int k_iters = p.taps * p.k_chunks;
+  const int k_iters0 = p.taps * p.k_chunks;
+  const int k_iters = k_iters0 + (p.dual ? p.taps * p.k_chunks1 : 0);
   const int stages = p.stages;
   const int bn_cta = p.block_n / CTAS;                        // weight rows staged by this CTA
   const uint32_t stage_tx = (uint32_t)p.a_stage_bytes + (uint32_t)bn_cta * p.kbytes;
@@ -125,6 +131,7 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (p.dual) tma_prefetch_desc(&map_b1);
     tma_prefetch_desc(&map_out);
     if (p.res_mode == 1) tma_prefetch_desc(&map_res);
     for (int i = 0; i < stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
@@ -163,25 +170,30 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       const int nrow0 = geglu ? n_blk * (p.block_n / 2) + ((CTAS == 2 && rank) ? p.geglu_half : 0) : n_blk * p.block_n + (int)rank * bn_cta;
       const int nrow1 = nrow0 + p.geglu_half;                          // second box (GEGLU on a single CTA)
       const int b_half_bytes = (p.block_n / 2) * p.kbytes;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const int kh = tap / p.S, kw = tap - kh * p.S;
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait(&bars->empty[stage], phase ^ 1);
-          if (elect_one()) {
-            if (CTAS == 2) {
-              const uint32_t fb = mapa_shared(smem_u32(&bars->full[stage]), 0);
-              if (rank == 0) mbar_expect_tx(&bars->full[stage], 2u * stage_tx);
-              tma_load_4d_pair(smem_a + stage * p.a_stage_bytes, &map_a, fb, p.a_c_offset + kc * p.kbytes, ow0 + kw, oh0 + kh, b0);
-              tma_load_3d_pair(smem_b + stage * p.b_stage_bytes, &map_b, fb, kc * p.kbytes, tap, nrow0);
-            } else {
-              mbar_expect_tx(&bars->full[stage], stage_tx);
-              tma_load_4d(smem_a + stage * p.a_stage_bytes, &map_a, &bars->full[stage], p.a_c_offset + kc * p.kbytes, ow0 + kw, oh0 + kh, b0);
-              tma_load_3d(smem_b + stage * p.b_stage_bytes, &map_b, &bars->full[stage], kc * p.kbytes, tap, nrow0);
-              if (geglu) tma_load_3d(smem_b + stage * p.b_stage_bytes + b_half_bytes, &map_b, &bars->full[stage], kc * p.kbytes, tap, nrow1);
+      for (int range = 0; range <= p.dual; ++range) {
+        const CUtensorMap* mb = range ? &map_b1 : &map_b;
+        const int c_off = range ? p.a_c_offset1 : p.a_c_offset;
+        const int kcs = range ? p.k_chunks1 : p.k_chunks;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int kh = tap / p.S, kw = tap - kh * p.S;
+          for (int kc = 0; kc < kcs; ++kc) {
+            mbar_wait(&bars->empty[stage], phase ^ 1);
+            if (elect_one()) {
+              if (CTAS == 2) {
+                const uint32_t fb = mapa_shared(smem_u32(&bars->full[stage]), 0);
+                if (rank == 0) mbar_expect_tx(&bars->full[stage], 2u * stage_tx);
+                tma_load_4d_pair(smem_a + stage * p.a_stage_bytes, &map_a, fb, c_off + kc * p.kbytes, ow0 + kw, oh0 + kh, b0);
+                tma_load_3d_pair(smem_b + stage * p.b_stage_bytes, mb, fb, kc * p.kbytes, tap, nrow0);
+              } else {
+                mbar_expect_tx(&bars->full[stage], stage_tx);
+                tma_load_4d(smem_a + stage * p.a_stage_bytes, &map_a, &bars->full[stage], c_off + kc * p.kbytes, ow0 + kw, oh0 + kh, b0);
+                tma_load_3d(smem_b + stage * p.b_stage_bytes, mb, &bars->full[stage], kc * p.kbytes, tap, nrow0);
+                if (geglu) tma_load_3d(smem_b + stage * p.b_stage_bytes + b_half_bytes, mb, &bars->full[stage], kc * p.kbytes, tap, nrow1);
+              }
             }
+            __syncwarp();
+            if (++stage == stages) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -198,11 +210,14 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       for (int unit = unit0; unit < num_units; unit += unit_step) {
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
-        int kc = 0;
-        for (int it = 0; it < k_iters; ++it) {
-          const int nmma = (kc == p.k_chunks - 1) ? p.k_last_mmas : p.kbytes / UMMA_K;
-          if (++kc == p.k_chunks) kc = 0;
+        uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
+        int kc = 0, kcs = p.k_chunks, klast = p.k_last_mmas, it_r = 0;
+        for (int it = 0; it < k_iters; ++it, ++it_r) {
+          if (it == k_iters0 && p.dual) {         // second K range: its own accumulator, block_n columns further
+            tmem_d += (uint32_t)p.block_n; kc = 0; kcs = p.k_chunks1; klast = p.k_last_mmas1; it_r = 0;
+          }
+          const int nmma = (kc == kcs - 1) ? klast : p.kbytes / UMMA_K;
+          if (++kc == kcs) kc = 0;
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
           const uint32_t aaddr = a_base + stage * p.a_stage_bytes, baddr = b_base + stage * p.b_stage_bytes;
@@ -210,13 +225,13 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           const uint64_t bdesc = sw64 ? make_smem_desc_sw64(baddr) : make_smem_desc(baddr);
           if (elect_one()) {
             if (CTAS == 2) {
-              umma_i8_pair(tmem_d, adesc, bdesc, idesc, it ? 1u : 0u);
+              umma_i8_pair(tmem_d, adesc, bdesc, idesc, it_r ? 1u : 0u);
               if (nmma > 1) umma_i8_pair(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
               if (nmma > 2) umma_i8_pair(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
               if (nmma > 3) umma_i8_pair(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
               umma_commit_pair(&bars->empty[stage], 3);
             } else {
-              umma_i8(tmem_d, adesc, bdesc, idesc, it ? 1u : 0u);
+              umma_i8(tmem_d, adesc, bdesc, idesc, it_r ? 1u : 0u);
               if (nmma > 1) umma_i8(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
               if (nmma > 2) umma_i8(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
               if (nmma > 3) umma_i8(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
@@ -243,6 +258,8 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     const bool issuer = et == 0;
     const float da = __ldg(p.delta_a);
     const int za = (int)__ldg(p.zp_a);
+    const float da1 = p.dual ? __ldg(p.delta_a1) : 0.f;
+    const int za1 = p.dual ? (int)__ldg(p.zp_a1) : 0;
     const int mode = p.out_mode;
     const bool has_cw = p.cw != nullptr;
     float qd = 1.f, qinv = 1.f, qz = 0.f;
@@ -278,6 +295,11 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         epi_zterm[j] = ok ? -za * __ldg(p.wsum_eff + n) : 0;
         epi_cw[j] = (ok && has_cw) ? __ldg(p.cw + n) : 0;
         epi_bias[j] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+        if (p.dual) {                             // second range: constants in the upper half of the vectors (block_n <= 128)
+          epi_scale[MAX_BN / 2 + j] = ok ? da1 * __ldg(p.delta_w1 + n) : 0.f;
+          epi_zterm[MAX_BN / 2 + j] = ok ? -za1 * __ldg(p.wsum_eff1 + n) : 0;
+          epi_bias[MAX_BN / 2 + j] = 0.f;
+        }
       }
       // coordinates of this tile in the output / residual maps
       int co0, co1, co2;                          // NCHW: (pixel, channel, image); rows: (column, row)
@@ -317,6 +339,7 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         tmem_ld16(taddr + c0, a);
         uint32_t g[16];
         if (mode == OUT_U8_GEGLU) tmem_ld16(taddr + p.block_n / 2 + c0, g);
+        else if (p.dual) tmem_ld16(taddr + p.block_n + c0, g);
         tmem_ld_wait();
         if (ci == n_chunks - 1) {                 // accumulator fully read: hand the TMEM stage back to the MMA issuer
           tc_fence_before();
@@ -328,6 +351,12 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         }
         // dequantise: exact int32 zero-point fold, one fp32 FMA; the per-column constants come as 128-bit broadcast loads
         dequant16(a, v, epi_zterm + c0, epi_scale + c0, epi_bias + c0, has_cw ? epi_cw + c0 : nullptr, rs);
+        if (p.dual) {                             // + the second range's rounded product, as the accumulating second launch adds it
+          float v1[16];
+          dequant16(g, v1, epi_zterm + MAX_BN / 2 + c0, epi_scale + MAX_BN / 2 + c0, epi_bias + MAX_BN / 2 + c0, nullptr, 0);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = v1[j] + v[j];
+        }
         uint8_t* ob = out_buf + (gchunk & 1u) * OUT_BUF_BYTES;
         if (p.res_mode == 1) {
           const int rb = (int)((rchunk + ci) % (uint32_t)p.res_bufs);
@@ -444,6 +473,9 @@ struct Gemm2Args {
   void* out; int out_hw; int accumulate;
   int out_mode;                 // g2::OutMode
   const float* q_delta; const float* q_zp; int q_levels; int32_t* q_rowsum; int out_pitch;   // code-emitting modes: consumer quantizer, u8 row pitch
+  // optional second K range (split shortcut): channels [a_c_offset1, ...) of q against a second weight pack
+  const void* wq1 = nullptr; int Cp_w1 = 0; int a_c_offset1 = 0;
+  const float* delta_a1 = nullptr; const float* zp_a1 = nullptr; const float* delta_w1 = nullptr; const int32_t* wsum_eff1 = nullptr;
 };
 
 // returns EDADM_OK, an error, or +1 when this kernel does not cover the case (the caller falls back to the first-generation kernel)
@@ -453,6 +485,9 @@ int launch_qgemm2(const Gemm2Args& a, void* stream) {
   const long long M = (long long)a.B * Ho * Wo;
   if (M > 0x7fffffffLL || M < 1) return 1;
   const bool codes_out = a.out_mode >= OUT_U8_ROWS;
+  const bool dual = a.wq1 != nullptr;
+  if (dual && (codes_out || a.cw || a.accumulate || a.residual || a.bias_img || !a.delta_a1 || !a.zp_a1 || !a.delta_w1 || !a.wsum_eff1 || (a.Cp_w1 & 15) || a.Cp_w1 < 16 ||
+               (((uintptr_t)a.wq1) & 15))) return 1;
   if (a.accumulate && (a.residual || a.bias_img || codes_out)) return 1;
   if (a.residual && a.bias_img) return 1;
   if ((((uintptr_t)a.out) & 15) || (a.residual && (((uintptr_t)a.residual) & 15))) return 1;
@@ -492,7 +527,7 @@ int launch_qgemm2(const Gemm2Args& a, void* stream) {
   // CTA pairs when there is enough work to keep 74 pairs busy for at least two rounds AND the main loop is long enough for the
   // halved weight traffic to matter: with a handful of K steps per tile (the transformer linears, K = 384 .. 960) the tile time is
   // its epilogue and the pair's cluster handshakes only cost (measured: 131072 x 3072 x 384 GEGLU 588 -> 533 us with single CTAs)
-  const int k_steps_128 = a.R * a.S * ((a.Cp_w + 127) / 128);
+  const int k_steps_128 = a.R * a.S * ((a.Cp_w + 127) / 128 + (dual ? (a.Cp_w1 + 127) / 128 : 0));
   int ctas = (m_tiles >= 2 * 148 && k_steps_128 >= 8) ? 2 : 1;
   if (const char* e = getenv("EDADM_GEMM_CTAS")) { const int v = atoi(e); if (v == 1 || v == 2) ctas = v; }
   const int sms = sm_count();
@@ -505,7 +540,7 @@ int launch_qgemm2(const Gemm2Args& a, void* stream) {
     block_n = 2 * bh;
   } else {
     // code outputs stage a whole tile (128 rows x block_n bytes <= one 16 KB buffer) and leave with ONE TMA store per tile
-    block_n = pick_block_n(a.N, m_units, workers, 32, mode == OUT_U8_ROWS ? 128 : MAX_BN);
+    block_n = pick_block_n(a.N, m_units, workers, 32, (mode == OUT_U8_ROWS || dual) ? 128 : MAX_BN);      // dual: two accumulators per tile
   }
   const int n_tiles = mode == OUT_U8_GEGLU ? (a.N / 2) / (block_n / 2) : (a.N + block_n - 1) / block_n;
   if (a.Np < a.N) return fail(EDADM_ERR_ARG, "qgemm2: weight rows Np=%d < N=%d", a.Np, a.N);
@@ -526,6 +561,14 @@ int launch_qgemm2(const Gemm2Args& a, void* stream) {
     cuuint64_t strides[2] = {(cuuint64_t)a.Cp_w, (cuuint64_t)a.R * a.S * a.Cp_w};
     cuuint32_t box[3] = {(cuuint32_t)kbytes, 1u, (cuuint32_t)(mode == OUT_U8_GEGLU ? block_n / 2 : block_n / ctas)};
     int rc = encode_map(&map_b, a.wq, 3, dims, strides, box, "weights", CU_TENSOR_MAP_DATA_TYPE_UINT8, ksw);
+    if (rc) return rc;
+  }
+  CUtensorMap map_b1 = map_b;
+  if (dual) {
+    cuuint64_t dims[3] = {(cuuint64_t)a.Cp_w1, (cuuint64_t)(a.R * a.S), (cuuint64_t)a.Np};
+    cuuint64_t strides[2] = {(cuuint64_t)a.Cp_w1, (cuuint64_t)a.R * a.S * a.Cp_w1};
+    cuuint32_t box[3] = {(cuuint32_t)kbytes, 1u, (cuuint32_t)(block_n / ctas)};
+    int rc = encode_map(&map_b1, a.wq1, 3, dims, strides, box, "weights (second range)", CU_TENSOR_MAP_DATA_TYPE_UINT8, ksw);
     if (rc) return rc;
   }
   const float* res_src = a.accumulate ? (const float*)a.out : a.residual;
@@ -563,6 +606,13 @@ int launch_qgemm2(const Gemm2Args& a, void* stream) {
   const int last_bytes = a.Cp_w - (p.k_chunks - 1) * kbytes;
   p.k_last_mmas = (last_bytes + UMMA_K - 1) / UMMA_K;
   p.a_c_offset = a.a_c_offset;
+  if (dual) {
+    p.dual = 1;
+    p.k_chunks1 = (a.Cp_w1 + kbytes - 1) / kbytes;
+    p.k_last_mmas1 = (a.Cp_w1 - (p.k_chunks1 - 1) * kbytes + UMMA_K - 1) / UMMA_K;
+    p.a_c_offset1 = a.a_c_offset1;
+    p.delta_a1 = a.delta_a1; p.zp_a1 = a.zp_a1; p.delta_w1 = a.delta_w1; p.wsum_eff1 = a.wsum_eff1;
+  }
   p.Wo = flat ? (1 << 30) : Wo;
   p.HoWo = flat ? (1 << 30) : Ho * Wo;
   p.block_n = block_n; p.n_tiles = n_tiles; p.m_units = m_units;
@@ -605,11 +655,11 @@ int launch_qgemm2(const Gemm2Args& a, void* stream) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, qgemm2_kernel<2>, map_a, map_b, map_out, map_res, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, qgemm2_kernel<2>, map_a, map_b, map_out, map_res, map_b1, p);
     if (e != cudaSuccess) return fail(EDADM_ERR_CUDA, "qgemm2 (pairs): %s", cudaGetErrorString(e));
   } else {
     const int grid = units < sms ? units : sms;
-    qgemm2_kernel<1><<<grid, THREADS, smem_bytes, (cudaStream_t)stream>>>(map_a, map_b, map_out, map_res, p);
+    qgemm2_kernel<1><<<grid, THREADS, smem_bytes, (cudaStream_t)stream>>>(map_a, map_b, map_out, map_res, map_b1, p);
   }
   return check_launch("qgemm2");
 }

@@ -678,6 +678,8 @@ struct Gemm2Args {
   void* out; int out_hw; int accumulate;
   int out_mode;
   const float* q_delta; const float* q_zp; int q_levels; int32_t* q_rowsum; int out_pitch;
+  const void* wq1 = nullptr; int Cp_w1 = 0; int a_c_offset1 = 0;
+  const float* delta_a1 = nullptr; const float* zp_a1 = nullptr; const float* delta_w1 = nullptr; const int32_t* wsum_eff1 = nullptr;
 };
 int launch_qgemm2(const Gemm2Args& a, void* stream);     // qgemm2_sm100.cu; +1 = case not covered
 }
@@ -705,6 +707,34 @@ extern "C" int edadm_qgemm_i8(const uint8_t* q, int B, int Hp, int Wp, int Cp_ac
   }
   return launch_qgemm(q, B, Hp, Wp, Cp_act, a_c_offset, wq, 0, nullptr, N, Np, R, S, Cp_w, delta_a, zp_a, delta_w, wsum_eff, cw,
                       rowsum, bias, bias_img, residual, out, out_hw, accumulate, silu, stream);
+}
+
+// Split shortcut (quant_layer.py:415-432: the input channels [0, split) and [split, C) have their own activation AND weight
+// quantizers): out = conv(x[:, :split], w0) + conv(x[:, split:], w1) (+ bias) (+ residual) as ONE launch -- both K ranges of the
+// same NHWC code tensor, two TMEM accumulators combined in the epilogue exactly as the two-launch form (second launch accumulating
+// onto the first one's fp32 output) rounds: fma(acc0, s0, bias) + round(acc1 * s1).  Falls back to those two launches when the
+// second-generation kernel does not cover the geometry.
+extern "C" int edadm_qgemm_i8_split(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, const int8_t* wq0, const int8_t* wq1, int N,
+                                    int Np, int R, int S, int Cp_w0, int Cp_w1, int a_c_offset1, const float* delta_a0,
+                                    const float* zp_a0, const float* delta_a1, const float* zp_a1, const float* delta_w0,
+                                    const float* delta_w1, const int32_t* wsum_eff0, const int32_t* wsum_eff1, const float* bias,
+                                    const float* bias_img, const float* residual, float* out, int out_hw, void* stream) {
+  if (!q || !wq0 || !wq1 || !delta_a0 || !zp_a0 || !delta_a1 || !zp_a1 || !delta_w0 || !delta_w1 || !wsum_eff0 || !wsum_eff1 || !out)
+    return fail(EDADM_ERR_ARG, "qgemm_i8_split: null pointer");
+  if (getenv("EDADM_GEMM_V1") == nullptr && B >= 1 && Hp >= R && Wp >= S && R >= 1 && S >= 1 && N >= 1 && !(Cp_act & 15) && !(Cp_w0 & 15) &&
+      Cp_w0 >= 16 && !(((uintptr_t)q) & 15) && !(((uintptr_t)wq0) & 15) && out_hw >= 1 && !(bias_img && out_hw == 1)) {
+    Gemm2Args a{q, B, Hp, Wp, Cp_act, 0, wq0, N, Np, R, S, Cp_w0, delta_a0, zp_a0, delta_w0, wsum_eff0, nullptr, nullptr, bias, bias_img,
+                residual, out, out_hw, 0, 0, nullptr, nullptr, 0, nullptr, 0};
+    a.wq1 = wq1; a.Cp_w1 = Cp_w1; a.a_c_offset1 = a_c_offset1;
+    a.delta_a1 = delta_a1; a.zp_a1 = zp_a1; a.delta_w1 = delta_w1; a.wsum_eff1 = wsum_eff1;
+    const int rc = launch_qgemm2(a, stream);
+    if (rc <= 0) return rc;
+  }
+  int rc = edadm_qgemm_i8(q, B, Hp, Wp, Cp_act, 0, wq0, N, Np, R, S, Cp_w0, delta_a0, zp_a0, delta_w0, wsum_eff0, nullptr, nullptr, bias,
+                          nullptr, nullptr, out, out_hw, 0, 0, stream);
+  if (rc) return rc;
+  return edadm_qgemm_i8(q, B, Hp, Wp, Cp_act, a_c_offset1, wq1, N, Np, R, S, Cp_w1, delta_a1, zp_a1, delta_w1, wsum_eff1, nullptr, nullptr,
+                        nullptr, bias_img, residual, out, out_hw, 1, 0, stream);
 }
 
 // Linear layer (row-major output) whose epilogue adds, after the residual, one fp32 row per group of `post_rows` output rows:

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "edadm_split_bf16_batched": (c_int, [P, c_int64, c_int64, c_int64, P, P, c_int64, P, P, c_int64, P]),
     "edadm_gn_fold_cat": (c_int, [P, c_int, P, P, P, P, P, c_int64, c_int, c_int, c_int, c_int, c_float, P, P, P]),
     "edadm_act_quant_nhwc_slice": (c_int, [P, P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P]),
+    "edadm_qgemm_i8_split": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P,
+                                     P, P, P, P, c_int, P]),
     "edadm_qgemm_i8_rows_post": (c_int, [P, c_int64, c_int, P, c_int, c_int, c_int, P, P, P, P, P, P, P, c_int, P, P]),
     "edadm_split_filter_bf16": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_int64, P, P, c_int64, P]),
     "edadm_split_nhwc_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),

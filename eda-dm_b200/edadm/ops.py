@@ -655,6 +655,37 @@ def qgemm_i8(q, pw: PackedWeight, delta_a, zp_a, out, out_hw, bias=None, rowsum=
     return out
 
 
+def qgemm_i8_split(q, pw0: PackedWeight, pw1: PackedWeight, aq0, aq1, out, out_hw, bias=None, residual=None, bias_img=None):
+    """Split shortcut as one launch: the two K ranges of the code tensor q [B,Hp,Wp,Cp] (channels [0, pw0.C) / [pw0.C, ...)) against
+    their own weight packs and (delta, zero_point) pairs aq0 / aq1, summed in the epilogue (falls back to two launches in C)."""
+    if pw0.w4 or pw1.w4 or pw0.needs_rowsum or pw1.needs_rowsum:
+        raise EdadmError("qgemm_i8_split: plain s8 weight tiles without row sums only")
+    if bias_img is not None:
+        bias_img = _f32c(bias_img.detach().reshape(-1, pw0.N))
+    if residual is not None and (residual.dtype != torch.float32 or not residual.is_contiguous() or residual.numel() != out.numel()):
+        raise EdadmError("qgemm_i8_split: residual must be a contiguous fp32 tensor of the output's size")
+    if q.dim() == 2:
+        B, Hp, Wp, Cp_act = 1, 1, q.shape[0], q.shape[1]
+    else:
+        B, Hp, Wp, Cp_act = q.shape
+    dev = q.device
+    d0, z0 = _qparam(aq0[0], dev), _qparam(aq0[1], dev)
+    d1, z1 = _qparam(aq1[0], dev), _qparam(aq1[1], dev)
+    prof = gemm_profile
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    lib.qgemm_i8_split(q.data_ptr(), B, Hp, Wp, Cp_act, pw0.wq.data_ptr(), pw1.wq.data_ptr(), pw0.N, pw0.Np, pw0.R, pw0.S,
+                       pw0.wq.shape[2], pw1.wq.shape[2], pw0.C, d0.data_ptr(), z0.data_ptr(), d1.data_ptr(), z1.data_ptr(),
+                       pw0.delta_w.data_ptr(), pw1.delta_w.data_ptr(), pw0.wsum_eff.data_ptr(), pw1.wsum_eff.data_ptr(), _ptr(bias),
+                       _ptr(bias_img), _ptr(residual), out.data_ptr(), int(out_hw), _stream())
+    if prof is not None:
+        ev1.record()
+        m = B * (Hp - pw0.R + 1) * (Wp - pw0.S + 1)
+        prof.append((ev0, ev1, m * pw0.N * (pw0.C + pw1.C) * pw0.R * pw0.S))
+    return out
+
+
 def qgemm_i8_rows_post(q, pw: PackedWeight, delta_a, zp_a, out, bias, residual, post, post_rows):
     """Linear GEMM (q [M, Kp] u8 codes -> out fp32 [M, N]) with `+ residual[m]` and then `+ post[m // post_rows]` in the epilogue."""
     if pw.w4 or pw.needs_rowsum:

@@ -714,6 +714,12 @@ class QuantModule(nn.Module):
         return out.flatten(2).permute(0, 2, 1) if tokens_out else out
 
     def _gemm_chain(self, q, packs, aqs, out, out_hw, bias, rowsum, residual=None, bias_img=None):
+        if (len(packs) == 2 and rowsum is None and packs[0].Np == packs[1].Np and not any(p.w4 or p.needs_rowsum for p in packs)
+                and backend.fuse_epilogue):
+            # split shortcut: both K ranges in one launch, two TMEM accumulators combined in the epilogue
+            ops.qgemm_i8_split(q, packs[0], packs[1], (aqs[0].delta, aqs[0].zero_point), (aqs[1].delta, aqs[1].zero_point), out, out_hw,
+                               bias=bias, residual=residual, bias_img=bias_img)
+            return
         c_off = 0
         last = len(packs) - 1
         for i, (pw, aqz) in enumerate(zip(packs, aqs)):

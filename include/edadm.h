@@ -176,6 +176,17 @@ int edadm_act_quant_nhwc_slice(const float* x, const float* aff_a, const float* 
                                int q_pitch, int q_c_offset, int B, int C, int H, int W, int Cs, int pad, const float* delta,
                                const float* zp, int n_levels, void* stream);
 
+/* Split shortcut in one launch: out = conv(q[..., :split], w0) + conv(q[..., split:], w1) + bias, the two K ranges of ONE NHWC code
+ * tensor q (channels [0, a_c_offset1) quantized with (delta_a0, zp_a0), the rest with (delta_a1, zp_a1)) against their own weight
+ * packs, accumulated in two TMEM accumulators and combined in the epilogue with the roundings of the two-launch form
+ * (edadm_qgemm_i8, then edadm_qgemm_i8 with accumulate = 1), which it falls back to where the geometry is not covered.
+ * Replaces quant_layer.py:415-434 with `self.split != 0` (the skip_connection / nin_shortcut of the UNet's up path).       */
+int edadm_qgemm_i8_split(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, const int8_t* wq0, const int8_t* wq1, int N, int Np, int R,
+                         int S, int Cp_w0, int Cp_w1, int a_c_offset1, const float* delta_a0, const float* zp_a0, const float* delta_a1,
+                         const float* zp_a1, const float* delta_w0, const float* delta_w1, const int32_t* wsum_eff0,
+                         const int32_t* wsum_eff1, const float* bias, const float* bias_img, const float* residual, float* out,
+                         int out_hw, void* stream);
+
 /* Linear layer with a row-group term after the residual: out[m][n] = ((acc*scale + bias[n]) + residual[m][n]) + post[m / post_rows][n].
  * Replaces `x = attn1(norm1(x)) + x; x = attn2(norm2(x), context) + x` (quant_block.py:254-262) when the context has ONE token
  * (LDM-4 ImageNet class conditioning): softmax over one key is 1, attn2's output is one row per sample, independent of x, and

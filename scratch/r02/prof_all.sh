@@ -23,4 +23,6 @@ run qgemm2_geglu_codes qgemm2_kernel 2 gemm_geglu
 run qgemm_i8_lin_res qgemm_i8_kernel 2 gemm_lin
 run qattn_imagenet qattn_kernel 2 attn_in
 run qattn_church qattn_kernel 2 attn_church
+run gemm_bf16x3_conv gemm_bf16x3_kernel 2 bf16x3_conv
+run gemm_bf16x3_linear gemm_bf16x3_kernel 2 bf16x3_lin
 ls -la gpurun_out/r02/ncu/*.ncu-rep | wc -l; du -sh gpurun_out/r02/ncu

@@ -27,6 +27,8 @@ CASES={
  "qgemm2_geglu_codes": ("GEGLU projection with the gate + next quantizer in the epilogue (u8 codes out), M=131072, N=3072, K=384", None, 2*131072*3072*384),
  "qgemm_i8_lin_res": ("first-generation int8 GEMM, ff.net[2] linear with residual epilogue, M=131072, N=384, K=1536 (fp32 row-major out)", None, 2*131072*384*1536),
  "qattn_imagenet": ("fused quantized attention, ImageNet self-attention T=1024, d=384, 128 (batch x head): single S accumulator, one pass per CTA", None, 4*128*1024*1024*384),
+ "gemm_bf16x3_conv": ("reconstruction-loop convolution on the bf16 x 3 tcgen05 kernel (implicit GEMM, NHWC split operands, NCHW TMA store): 3x3 576->576 at 16x16, batch 32 (M=8192, N=576, K=5184); flops counted 3x (hi.hi + hi.lo + lo.hi)", None, 3*2*8192*576*5184),
+ "gemm_bf16x3_linear": ("reconstruction-loop linear on the bf16 x 3 tcgen05 kernel: M=32768, N=3072, K=384; flops counted 3x", None, 3*2*32768*3072*384),
  "qattn_church": ("fused quantized attention, church T=1024, d=24, 800 (batch x head)", None, 4*800*1024*1024*24),
 }
 for name,(note,nbytes,nops) in CASES.items():
@@ -39,6 +41,7 @@ for name,(note,nbytes,nops) in CASES.items():
     dur=float(m.group(1).replace(",",""))*{"us":1e-6,"usecond":1e-6,"ms":1e-3,"msecond":1e-3,"ns":1e-9,"nsecond":1e-9}.get(m.group(2),1e-6)
     extra=[]
     if nbytes: extra.append(f"algorithmic bytes {nbytes/1e6:.1f} MB / {dur*1e6:.1f} us = {nbytes/dur/1e9:.0f} GB/s = {nbytes/dur/1e9/HBM:.2f} of the measured 6546 GB/s copy bandwidth (ncu run: cold L2, serialised)")
-    if nops: extra.append(f"algorithmic ops {nops/1e9:.1f} GOP / {dur*1e6:.1f} us = {nops/dur/1e12:.0f} TOP/s = {nops/dur/1e12/3410.6:.2f} of the measured 3411 TOP/s int8 burst peak (profiles/int8_peak_r02.txt)")
+    if nops and name.startswith("gemm_bf16x3"): extra.append(f"executed flops (3 products) {nops/1e9:.1f} GFLOP / {dur*1e6:.1f} us = {nops/dur/1e12:.0f} TFLOP/s = {nops/dur/1e12/2112.2:.2f} of the measured 2112 TFLOP/s bf16 tcgen05 burst peak (profiles/int8_peak_r02.txt)")
+    elif nops: extra.append(f"algorithmic ops {nops/1e9:.1f} GOP / {dur*1e6:.1f} us = {nops/dur/1e12:.0f} TOP/s = {nops/dur/1e12/3410.6:.2f} of the measured 3411 TOP/s int8 burst peak (profiles/int8_peak_r02.txt)")
     open(out,"a").write("\n".join(extra)+"\n")
     print("   ", " | ".join(extra))
