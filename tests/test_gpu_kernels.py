@@ -887,6 +887,22 @@ def test_split_shortcut_single_launch_is_exact(cuda, B, C0, C1, H, N, k):
     assert _rel_l2(out1.double(), o0.double() + o1.double()) < 1e-6
 
 
+@pytest.mark.parametrize("zp", [128.0, 127.0, 0.0, 1.0])
+def test_nhwc_producer_ties_round_to_even_quotient(cuda, zp):
+    """x / delta exactly half-way between two integers must round to the EVEN quotient whatever the parity of the zero-point
+    (torch.round semantics, quant_layer.py:267): the producers fold the zero-point into their magic-number rounding only when
+    that keeps the tie rule"""
+    from edadm import ops
+    delta = 0.25
+    k = torch.arange(-140, 140, dtype=torch.float32)
+    vals = torch.cat([(k + 0.5) * delta, k * delta, (k + 0.25) * delta])              # ties, exact integers, plain values
+    x = vals.repeat(64 * 16 * 16 * 4 // vals.numel() + 1)[:4 * 64 * 16 * 16].reshape(4, 64, 16, 16).to(cuda)
+    d, z = torch.tensor([delta], device=cuda), torch.tensor([zp], device=cuda)
+    q, _ = ops.act_quant_nhwc(x, ops.ActQuant(d, z, 256), 1)
+    ref = torch.clamp(torch.round(x / d) + z, 0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+    assert torch.equal(q[:, 1:-1, 1:-1, :64], ref)
+
+
 def test_conv_upsample_on_codes_is_exact(cuda):
     """`Upsample` with a conv (openaimodel.py Upsample): quantizing the low-resolution tensor and replicating the u8 codes equals
     quantizing the interpolated tensor, bit for bit, through the whole QuantModule"""
