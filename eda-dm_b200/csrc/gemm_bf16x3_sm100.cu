@@ -48,6 +48,10 @@ struct Params {
   // convolution mode (conv = 1): A is the halo-padded NHWC tensor [B][Hp][Wp][Cp] read through rank-4 maps, one filter tap x 64
   // channels per K step (implicit GEMM, as qgemm2_sm100.cu); B is [N][taps * C]; the output is NCHW through a rank-3 map
   int conv, taps, S, c_chunks, C, Wo, HoWo, out_hw, pxb, px_shift;
+  // convolution wgrad (conv = 2): dW[tap][n][c] = sum over pixels dY[b][n][pixel] * X[b][c][pixel shifted by the tap] -- both operands
+  // are pixel-contiguous in NCHW: A = dY through a rank-3 map {HW, N, B}, B = X through a rank-4 map {W, H, C, B} whose box start is
+  // moved by the tap offset (out-of-range pixels are zero-filled by TMA = the convolution's zero padding); one K step = 64 pixels
+  int wg_cpi, wg_W, wg_pad, wg_B;               // K chunks per image, image width, padding, batch
   const float* bias;
 };
 
@@ -70,6 +74,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
@@ -88,7 +96,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
   Barriers* bars = reinterpret_cast<Barriers*>(epi_bias + MAX_BN);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int units = p.m_tiles * p.n_tiles * p.splits;
+  const int units = p.m_tiles * p.n_tiles * p.splits * (p.conv == 2 ? p.taps : 1);
   const int stages = p.stages;
   const uint32_t stage_tx = (uint32_t)(2 * a_tile + 2 * p.block_n * BK * 2);
 
@@ -113,7 +121,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
     int stage = 0; uint32_t phase = 0;
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
       const int n_blk = unit % p.n_tiles, rest = unit / p.n_tiles;
-      const int m_blk = rest % p.m_tiles, sp = rest / p.m_tiles;
+      const int m_blk = rest % p.m_tiles, rest2 = rest / p.m_tiles;
+      const int sp = rest2 % p.splits, tap_u = rest2 / p.splits;        // (tap_u: wgrad only)
       const int k0 = sp * p.k_steps;
       for (int ks = 0; ks < p.k_steps; ++ks) {
         mbar_wait(&bars->empty[stage], phase ^ 1);
@@ -121,6 +130,19 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
           uint8_t* s = smem + stage * stage_bytes;
           mbar_expect_tx(&bars->full[stage], stage_tx);
           int kc = (k0 + ks) * BK;
+          if (p.conv == 2) {
+            const int kg = k0 + ks, b = kg / p.wg_cpi, p0 = (kg - b * p.wg_cpi) * BK;
+            const int kh = tap_u / p.S, kw = tap_u - kh * p.S;
+            tma_load_3d(s, &map_ah, &bars->full[stage], p0, m_blk * BM, b);
+            tma_load_3d(s + a_tile, &map_al, &bars->full[stage], p0, m_blk * BM, b);
+            // X comes as S copies pre-shifted along W (a TMA box must start on a 16-byte boundary of the innermost dimension, which a
+            // +-1 pixel offset is not): copy kw sits at batch index kw * B + b; the row shift is a plain (possibly out-of-range) coordinate
+            // and the row shift is a whole number of rows on the flattened pixel axis (W % 8 == 0 keeps it 16-byte aligned); pixels before
+            // the first / after the last row are out of range = zero-filled = the vertical zero padding
+            const int px = p0 + (kh - p.wg_pad) * p.wg_W;
+            tma_load_3d(s + 2 * a_tile, &map_bh, &bars->full[stage], px, n_blk * p.block_n, kw * p.wg_B + b);
+            tma_load_3d(s + 2 * a_tile + p.b_tile_bytes, &map_bl, &bars->full[stage], px, n_blk * p.block_n, kw * p.wg_B + b);
+          } else {
           if (p.conv) {
             const int tap = ks / p.c_chunks, cc = ks - tap * p.c_chunks;
             const int kh = tap / p.S, kw = tap - kh * p.S;
@@ -135,6 +157,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
           const int brow = n_blk * p.block_n + (p.group_m_tiles ? (m_blk / p.group_m_tiles) * p.group_b_rows : 0);
           tma_load_2d(s + 2 * a_tile, &map_bh, &bars->full[stage], kc, brow);
           tma_load_2d(s + 2 * a_tile + p.b_tile_bytes, &map_bl, &bars->full[stage], kc, brow);
+          }
         }
         __syncwarp();
         if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -181,12 +204,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
     for (int k = 0; k < 4; ++k) st_off[k] = (uint32_t)r * 128u + ((uint32_t)((4 * half + k) ^ (r & 7)) << 4);
     // convolution mode: NCHW staging [image][column][pixel] (see qgemm2_sm100.cu)
     const uint32_t nchw_cstride = (uint32_t)p.pxb * 4u;
-    const uint32_t nchw_off = p.conv ? ((uint32_t)((r >> p.px_shift) * CHUNK + 16 * half) * p.pxb + (r & (p.pxb - 1))) * 4u : 0u;
+    const uint32_t nchw_off = p.conv == 1 ? ((uint32_t)((r >> p.px_shift) * CHUNK + 16 * half) * p.pxb + (r & (p.pxb - 1))) * 4u : 0u;
     const int n_chunks = p.block_n / CHUNK;
     int acc = 0; uint32_t acc_phase = 0; uint32_t gchunk = 0;
     for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
       const int n_blk = unit % p.n_tiles, rest = unit / p.n_tiles;
-      const int m_blk = rest % p.m_tiles, sp = rest / p.m_tiles;
+      const int m_blk = rest % p.m_tiles, rest2 = rest / p.m_tiles;
+      const int sp = rest2 % p.splits, tap_u = rest2 / p.splits;
       const int n0 = n_blk * p.block_n;
       for (int j = et; j < p.block_n; j += EPI_WARPS * 32)
         epi_bias[j] = (p.bias && sp == 0 && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
@@ -207,7 +231,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
         uint8_t* ob = out_buf + (gchunk & 1u) * OUT_BUF_BYTES;
         if (issuer) bulk_wait_read<1>();
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (p.conv) {
+        if (p.conv == 1) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(ob + nchw_off + j * nchw_cstride) = __uint_as_float(a[j]) + epi_bias[c0 + j];
         } else {
@@ -221,7 +245,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
         fence_proxy_async();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (issuer) {
-          if (p.conv) {
+          if (p.conv == 2) {
+            if (p.reduce_add) tma_reduce_add_3d(&map_out, ob, n0 + ci * CHUNK, m_blk * BM, tap_u);
+            else tma_store_3d(&map_out, ob, n0 + ci * CHUNK, m_blk * BM, tap_u);
+          } else if (p.conv) {
             const int m0 = m_blk * BM, img0 = m0 / p.out_hw;
             tma_store_3d(&map_out, ob, m0 - img0 * p.out_hw, n0 + ci * CHUNK, img0);
           } else if (p.reduce_add) tma_reduce_add_2d(&map_out, ob, n0 + ci * CHUNK, m_blk * BM);
@@ -577,5 +604,97 @@ extern "C" int edadm_conv_bf16x3(const void* a_hi, const void* a_lo, int B, int 
   const int units = p.m_tiles * p.n_tiles;
   gemm_bf16x3_kernel<<<std::min(units, sm_count()), THREADS, smem_bytes, (cudaStream_t)stream>>>(m_ah, m_al, m_bh, m_bl, m_out, p);
   return check_launch("conv_bf16x3");
+}
+
+namespace edadm {
+namespace g3 {
+// x fp32 [rows][W] -> hi / lo bf16 [S][rows][W], copy s shifted along the row: out[s][r][w] = x[r][w + s - pad] (0 outside)
+__global__ void __launch_bounds__(256)
+split_shift_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long rows, int W,
+                        int S, int pad) {
+  const long long total = rows * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / W;
+    const int w = (int)(i - r * W);
+    for (int sft = 0; sft < S; ++sft) {
+      const int ws = w + sft - pad;
+      const float v = (ws >= 0 && ws < W) ? __ldg(x + r * W + ws) : 0.f;
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[(long long)sft * total + i] = h;
+      lo[(long long)sft * total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+}  // namespace g3
+}  // namespace edadm
+
+extern "C" int edadm_split_shift_bf16(const float* x, void* hi, void* lo, int64_t rows, int W, int S, int pad, void* stream) {
+  if (!x || !hi || !lo || rows < 1 || W < 1 || S < 1 || pad < 0) return fail(EDADM_ERR_ARG, "split_shift_bf16: bad arguments");
+  const long long total = rows * W;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
+  g3::split_shift_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, rows, W, S, pad);
+  return check_launch("split_shift_bf16");
+}
+
+// Convolution weight gradient on the same kernel: dW[tap][n][c] = sum_{b, pixel} dY[b][n][pixel] * X[b][c][pixel + tap offset].
+// dy_* bf16 [B][N][H*W] (hi / lo of the NCHW tensor as it is, edadm_split_bf16 over [B*N][H*W] rows); x_* bf16 [S][B][C][H][W]: S copies
+// of the input pre-shifted along W by kw - pad with zero fill (edadm_split_shift_bf16),
+// stride 1, padding `pad`, filter R x S (output size == input size: 2 * pad == R - 1).  out fp32 [R*S][N][C]; splits > 1 adds
+// partial sums into `out` (zeroed by the caller) by TMA reduce.
+extern "C" int edadm_conv_wgrad_bf16x3(const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, int B, int N, int C, int H,
+                                       int W, int R, int S, int pad, float* out, int splits, void* stream) {
+  using namespace g3;
+  if (!dy_hi || !dy_lo || !x_hi || !x_lo || !out) return fail(EDADM_ERR_ARG, "conv_wgrad_bf16x3: null pointer");
+  const int HW = H * W;
+  if (B < 1 || N < 1 || C < 1 || R < 1 || S < 1 || 2 * pad != R - 1 || R != S || (HW % BK) || (W % 8) || (C % 4))
+    return fail(EDADM_ERR_UNSUPPORTED, "conv_wgrad_bf16x3: geometry B=%d N=%d C=%d H=%d W=%d R=%d pad=%d", B, N, C, H, W, R, pad);
+  const int cpi = HW / BK;
+  const int k_total = B * cpi;
+  if (splits < 1 || (k_total % splits)) return fail(EDADM_ERR_ARG, "conv_wgrad_bf16x3: splits must divide %d", k_total);
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = N; p.N = C; p.K = B * HW;
+  p.m_tiles = (N + BM - 1) / BM;
+  p.block_n = C >= 128 ? 128 : ((C + 31) / 32) * 32;
+  if (C > 128 && C % 128 && C % 96 == 0) p.block_n = 96;
+  p.n_tiles = (C + p.block_n - 1) / p.block_n;
+  p.splits = splits; p.k_steps = k_total / splits; p.reduce_add = splits > 1;
+  p.conv = 2; p.taps = R * S; p.S = S; p.wg_cpi = cpi; p.wg_W = W; p.wg_pad = pad; p.wg_B = B;
+  p.b_tile_bytes = (p.block_n * BK * 2 + 1023) & ~1023;
+  const int stage_bytes = 2 * BM * BK * 2 + 2 * p.b_tile_bytes;
+  const int fixed = 1024 + 2 * OUT_BUF_BYTES + MAX_BN * 4 + 1024;
+  p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - fixed) / stage_bytes);
+  const int smem_bytes = fixed + p.stages * stage_bytes;
+  CUtensorMap m_ah, m_al, m_bh, m_bl, m_out;
+  int rc;
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)N, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)HW * 2, (cuuint64_t)N * HW * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1u};
+    if ((rc = encode_map(i ? &m_al : &m_ah, i ? dy_lo : dy_hi, 3, dims, strides, box, "wgrad dY", CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B * S};
+    cuuint64_t strides[2] = {(cuuint64_t)HW * 2, (cuuint64_t)C * HW * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)p.block_n, 1u};
+    if ((rc = encode_map(i ? &m_bl : &m_bh, i ? x_lo : x_hi, 3, dims, strides, box, "wgrad X", CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)(R * S)};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)N * C * 4};
+    cuuint32_t box[3] = {(cuuint32_t)CHUNK, (cuuint32_t)BM, 1u};
+    if ((rc = encode_map(&m_out, out, 3, dims, strides, box, "wgrad output", CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  static int attr_dev[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_dev[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) return fail(EDADM_ERR_CUDA, "conv_wgrad_bf16x3: cannot opt in to %d B shared memory: %s", SMEM_LIMIT, cudaGetErrorString(e));
+    attr_dev[dev] = 1;
+  }
+  const int units = p.m_tiles * p.n_tiles * p.splits * p.taps;
+  gemm_bf16x3_kernel<<<std::min(units, sm_count()), THREADS, smem_bytes, (cudaStream_t)stream>>>(m_ah, m_al, m_bh, m_bl, m_out, p);
+  return check_launch("conv_wgrad_bf16x3");
 }
 

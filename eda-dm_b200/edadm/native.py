@@ -49,6 +49,8 @@ _SIGNATURES = {
     "edadm_split_filter_bf16": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_int64, P, P, c_int64, P]),
     "edadm_split_nhwc_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "edadm_conv_bf16x3": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, c_int, c_int, c_int64, P, P, P]),
+    "edadm_split_shift_bf16": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, P]),
+    "edadm_conv_wgrad_bf16x3": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P]),
     "edadm_gemm_bf16x3_grouped": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int64, c_int64, P, P, c_int, P]),
     "edadm_norm_act_pool2": (c_int, [P, P, P, c_int, P, c_int, c_int, c_int, c_int, P]),
     "edadm_upsample2x_codes": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P]),

@@ -965,7 +965,7 @@ def _conv_bf16x3_raw(x, wh, wl, n_out, R, S, c_in, pad, bias=None):
 
 class ConvBf16x3Function(torch.autograd.Function):
     """F.conv2d(x, w, bias, stride=1, padding=(R-1)/2) with forward and dgrad on edadm_conv_bf16x3 (dgrad = the same convolution
-    of dY with the flipped, transposed filter, prepared by the forward's filter split); wgrad stays on the library kernel."""
+    of dY with the flipped, transposed filter, prepared by the forward's filter split) and wgrad on edadm_conv_wgrad_bf16x3."""
 
     @staticmethod
     def forward(ctx, x, w, bias):
@@ -987,14 +987,35 @@ class ConvBf16x3Function(torch.autograd.Function):
             dh, dl = ctx.saved_tensors[2:]
             dx = _conv_bf16x3_raw(gy, dh, dl, C, R, S, N, (R - 1) // 2)
         if ctx.needs_input_grad[1]:
-            # library wgrad under the ambient torch.backends.cudnn.allow_tf32 (PyTorch's default -- and therefore the reference's --
-            # is TF32 tensor-core wgrad; the fp32 SIMT kernel it falls back to otherwise is 2.5x slower)
-            pad = (R - 1) // 2
-            dw = torch.ops.aten.convolution_backward(gy, x, w, None, [1, 1], [pad, pad], [1, 1], False, [0, 0], 1,
-                                                     [False, True, False])[1]
+            dw = conv_wgrad_bf16x3(gy, x, R)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = gy.sum((0, 2, 3))
         return dx, dw, db
+
+
+def conv_wgrad_bf16x3(gy, x, R):
+    """dW [N, C, R, R] of a stride-1 'same' convolution from dY [B, N, H, W] and X [B, C, H, W] on the bf16 x 3 kernel (pixels are
+    the reduction dimension; few output tiles -> split-K over the pixels with TMA reduce-add)"""
+    gy, x = _f32c(gy), _f32c(x)
+    B, N, H, W = gy.shape
+    C = x.shape[1]
+    HW = H * W
+    gh, gl, _, _ = split_bf16(gy.reshape(B * N, HW))
+    xh = torch.empty((R, B, C, H, W), dtype=torch.bfloat16, device=x.device)      # R copies shifted along W (see edadm_conv_wgrad_bf16x3)
+    xl = torch.empty_like(xh)
+    lib.split_shift_bf16(x.data_ptr(), xh.data_ptr(), xl.data_ptr(), B * C * H, W, R, (R - 1) // 2, _stream())
+    taps = R * R
+    tiles = taps * ((N + 127) // 128) * ((C + 127) // 128)
+    k_total = B * (HW // 64)
+    # split-K over the pixels: enough units for 148 SMs, and at most 2048 pixels per accumulator -- the tensor core's fp32
+    # accumulation truncates, its error grows linearly with the reduction length (measured 2.8e-5 at 8192 pixels)
+    splits = 1
+    while k_total % (splits * 2) == 0 and k_total // (splits * 2) >= 4 and (tiles * splits < 2 * 148 or k_total // splits > 32):
+        splits *= 2
+    out = (torch.zeros if splits > 1 else torch.empty)((taps, N, C), dtype=torch.float32, device=gy.device)
+    lib.conv_wgrad_bf16x3(gh.data_ptr(), gl.data_ptr(), xh.data_ptr(), xl.data_ptr(), B, N, C, H, W, R, R, (R - 1) // 2, out.data_ptr(),
+                          splits, _stream())
+    return out.permute(1, 2, 0).reshape(N, C, R, R)
 
 
 def conv_bf16x3_ok(x, w, kwargs):
@@ -1007,7 +1028,7 @@ def conv_bf16x3_ok(x, w, kwargs):
     if as2(st) != (1, 1) or as2(dl) != (1, 1) or gr != 1 or R != S or R % 2 == 0 or as2(pd) != ((R - 1) // 2,) * 2:
         return False
     B, _, H, W = x.shape
-    if C % 8 or N % 8 or x.shape[1] != C or (B * H * W) % 128 or (H * W) % 4:
+    if C % 8 or N % 8 or x.shape[1] != C or (B * H * W) % 128 or (H * W) % 64 or W % 8:
         return False
     hw = H * W
     if (hw % 128 if hw >= 128 else 128 % hw) or (min(hw, 128) & (min(hw, 128) - 1)):

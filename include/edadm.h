@@ -228,6 +228,16 @@ int edadm_split_nhwc_bf16(const float* x, void* hi, void* lo, int B, int C, int 
 int edadm_conv_bf16x3(const void* a_hi, const void* a_lo, int B, int Hp, int Wp, int Cp, const void* w_hi, const void* w_lo, int N,
                       int R, int S, int C, int64_t Kp, const float* bias, float* out, void* stream);
 
+/* Weight gradient of the same convolutions: dW[tap][n][c] = sum over (b, pixel) dY[b][n][pixel] * X[b][c][pixel shifted by the tap].
+ * dy_* is the bf16 hi / lo split of the NCHW gradient as it lies ([B][N][H*W]; edadm_split_bf16 over the flattened rows); x_* holds S
+ * copies [S][B][C][H][W] of the input pre-shifted along W by kw - pad with zero fill (edadm_split_shift_bf16: a TMA box must start
+ * on a 16-byte boundary of the innermost dimension); both GEMM operands are pixel-contiguous, the row shift is a coordinate offset of
+ * the rank-4 tensor map of X and the vertical zero padding is TMA's out-of-bounds fill.  out fp32 [R*S][N][C] (the caller permutes to [N][C][R][S]); splits > 1 = split-K
+ * over the pixels with TMA reduce-add into the zeroed output.  Replaces autograd's convolution wgrad behind quant_layer.py:434.  */
+int edadm_split_shift_bf16(const float* x, void* hi, void* lo, int64_t rows, int W, int S, int pad, void* stream);
+int edadm_conv_wgrad_bf16x3(const void* dy_hi, const void* dy_lo, const void* x_hi, const void* x_lo, int B, int N, int C, int H, int W,
+                            int R, int S, int pad, float* out, int splits, void* stream);
+
 /* W4 storage: the same GEMM with the weights kept as 4-bit codes, two per byte -- wq4 u8 [Np][R*S][Cp/2] (Cp % 32 == 0; inside
  * each 32-bit word byte j = code[c0+j] | code[c0+4+j] << 4), zoff[n] = zp[n] -- and unpacked to s8 (code - zoff[n]) in
  * shared memory by dedicated warps of the GEMM kernel, tile by tile, ahead of the tensor-core MMA.  Replaces the same

@@ -995,8 +995,8 @@ def test_linear_bf16x3_forward_and_gradients(cuda, M, K, N, bias):
                                              (4, 128, 256, 32, 32, 1, True), (2, 64, 72, 64, 64, 3, True), (4, 200, 128, 16, 16, 3, False),
                                              (1, 32, 32, 128, 128, 3, True)])
 def test_conv_bf16x3_forward_and_dgrad(cuda, B, C, N, H, W, R, bias):
-    """calibration-path convolution (implicit GEMM on the bf16 x 3 kernel, NHWC split producer, NCHW TMA-store epilogue): forward
-    and dgrad against an fp64 convolution; wgrad is the library's and must agree too"""
+    """calibration-path convolution (implicit GEMM on the bf16 x 3 kernel, NHWC split producer, NCHW TMA-store epilogue): forward,
+    dgrad and wgrad (pixel-contiguous operands, tap shift by tensor-map coordinates, split-K reduce) against an fp64 convolution"""
     from edadm import ops
     g = torch.Generator().manual_seed(B * 131 + C)
     x = (torch.randn(B, C, H, W, generator=g) * 1.3).to(cuda).requires_grad_(True)
@@ -1006,12 +1006,7 @@ def test_conv_bf16x3_forward_and_dgrad(cuda, B, C, N, H, W, R, bias):
     assert ops.conv_bf16x3_ok(x, w, kw)
     gy = torch.randn(B, N, H, W, generator=g).to(cuda)
     y = ops.conv_bf16x3(x, w, b)
-    prev = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False          # the library wgrad in fp32 for the comparison below
-    try:
-        y.backward(gy)
-    finally:
-        torch.backends.cudnn.allow_tf32 = prev
+    y.backward(gy)
     xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
     bd = b.detach().double().requires_grad_(True) if bias else None
     yd = F.conv2d(xd, wd, bd, **kw)
