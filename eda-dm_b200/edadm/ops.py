@@ -963,6 +963,9 @@ def _conv_bf16x3_raw(x, wh, wl, n_out, R, S, c_in, pad, bias=None):
     return out
 
 
+conv_wgrad_on_tensor_cores = True     # mirrored from qdiff.quant_layer.backend.calib_conv_wgrad_bf16x3 by the layer
+
+
 class ConvBf16x3Function(torch.autograd.Function):
     """F.conv2d(x, w, bias, stride=1, padding=(R-1)/2) with forward and dgrad on edadm_conv_bf16x3 (dgrad = the same convolution
     of dY with the flipped, transposed filter, prepared by the forward's filter split) and wgrad on edadm_conv_wgrad_bf16x3."""
@@ -987,7 +990,12 @@ class ConvBf16x3Function(torch.autograd.Function):
             dh, dl = ctx.saved_tensors[2:]
             dx = _conv_bf16x3_raw(gy, dh, dl, C, R, S, N, (R - 1) // 2)
         if ctx.needs_input_grad[1]:
-            dw = conv_wgrad_bf16x3(gy, x, R)
+            if conv_wgrad_on_tensor_cores:
+                dw = conv_wgrad_bf16x3(gy, x, R)
+            else:       # library wgrad under the ambient torch.backends.cudnn.allow_tf32 (PyTorch's default: TF32)
+                pad = (R - 1) // 2
+                dw = torch.ops.aten.convolution_backward(gy, x, w, None, [1, 1], [pad, pad], [1, 1], False, [0, 0], 1,
+                                                         [False, True, False])[1]
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = gy.sum((0, 2, 3))
         return dx, dw, db

@@ -43,6 +43,8 @@ class _Backend:
     recon_memoise_fp_taps = True      # FP-model taps of the per-layer loss: computed once per unit for all cached samples (HBM), not per iteration
     recon_memoise_bytes = 32 << 30    #   ... as long as they fit in this many bytes
     calib_gemm_bf16x3 = True          # linears of the reconstruction loop (fwd / dgrad / wgrad) on edadm_gemm_bf16x3 instead of cuBLAS fp32
+    calib_conv_wgrad_bf16x3 = True    # ... including the convolution wgrad (False: cuDNN's, TF32 by torch's default -- 6-10 % faster on the
+                                      # 576-channel ImageNet ResBlocks, 10-18 % slower on church's, 50x less accurate)
     in_recon = False                  # set by the reconstruction engine around its loop (FP-target forwards included)
     cache_prefix_reuse = True         # calibration cache builder keeps the network state at the frontier of the finished units (f2)
     recon_overlap_fp = False  # ... with the FP forward on a forked stream (a parallel graph branch): +4 % on a church
@@ -825,7 +827,8 @@ def _library_fwd(fn, input, weight, bias, kwargs):
         # the reconstruction loop's linears (forward, dgrad, wgrad): hand-written tcgen05 GEMM, bf16 x 3 split, fp32 accumulation
         return ops.linear_bf16x3(input, weight, bias)
     if fn is F.conv2d and backend.calib_gemm_bf16x3 and backend.in_recon and ops.conv_bf16x3_ok(input, weight, kwargs):
-        # the reconstruction loop's stride-1 convolutions: forward and dgrad as implicit GEMMs on the same kernel
+        # the reconstruction loop's stride-1 convolutions: forward, dgrad and wgrad on the same bf16 x 3 kernel
+        ops.conv_wgrad_on_tensor_cores = backend.calib_conv_wgrad_bf16x3
         return ops.conv_bf16x3(input, weight, bias)
     if not input.is_cuda or backend.allow_tf32:
         return fn(input, weight, bias, **kwargs)
