@@ -319,6 +319,8 @@ using namespace edadm;
 extern "C" int edadm_split_bf16_batched(const float* x, int64_t batch, int64_t rows, int64_t cols, void* hi, void* lo, int64_t cols_p,
                                         void* hi_t, void* lo_t, int64_t rows_p, void* stream);
 
+extern "C" int edadm_split_shift_bf16(const float* x, void* hi, void* lo, int64_t rows, int W, int S, int pad, void* stream);
+
 extern "C" int edadm_split_bf16(const float* x, int64_t rows, int64_t cols, void* hi, void* lo, int64_t cols_p, void* hi_t, void* lo_t,
                                 int64_t rows_p, void* stream) {
   return edadm_split_bf16_batched(x, 1, rows, cols, hi, lo, cols_p, hi_t, lo_t, rows_p, stream);
@@ -328,6 +330,9 @@ extern "C" int edadm_split_bf16_batched(const float* x, int64_t batch, int64_t r
                                         void* hi_t, void* lo_t, int64_t rows_p, void* stream) {
   if (!x || batch < 1 || batch > 65535 || rows < 1 || cols < 1 || (!hi && !hi_t) || (hi && !lo) || (hi_t && !lo_t)) return fail(EDADM_ERR_ARG, "split_bf16: bad arguments");
   if ((hi && (cols_p < cols || (cols_p & 7))) || (hi_t && (rows_p < rows || (rows_p & 7)))) return fail(EDADM_ERR_ARG, "split_bf16: pitches must cover the data and be multiples of 8");
+  if (hi && !hi_t && cols_p == cols && (cols & 7) == 0 &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0)
+    return edadm_split_shift_bf16(x, hi, lo, batch * rows, (int)cols, 1, 0, stream);     // straight copy only: the 16-byte streaming form
   if (!hi) cols_p = cols;
   if (!hi_t) rows_p = rows;
   const long long tiles = ((cols_p + 31) / 32) * ((rows_p + 31) / 32);
@@ -608,7 +613,46 @@ extern "C" int edadm_conv_bf16x3(const void* a_hi, const void* a_lo, int B, int 
 
 namespace edadm {
 namespace g3 {
-// x fp32 [rows][W] -> hi / lo bf16 [S][rows][W], copy s shifted along the row: out[s][r][w] = x[r][w + s - pad] (0 outside)
+// x fp32 [rows][W] -> hi / lo bf16 [S][rows][W], copy s shifted along the row: out[s][r][w] = x[r][w + s - pad] (0 outside).
+// A thread owns 8 consecutive pixels of a row: its window x[w0 - pad .. w0 + 7 + S - 1 - pad] is loaded once (two 16-byte loads + the
+// edge values), every shifted copy leaves as one 16-byte store of hi and one of lo.  Generic (scalar) form for other shapes.
+template <int S_MAX>
+__global__ void __launch_bounds__(256)
+split_shift_bf16_vec_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long rows,
+                            int W, int S, int pad) {
+  const long long groups = rows * (W >> 3), total = rows * W;
+  for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < groups; gidx += (long long)gridDim.x * blockDim.x) {
+    const long long r = gidx / (W >> 3);
+    const int w0 = (int)(gidx - r * (W >> 3)) << 3;
+    const float* xr = x + r * W;
+    float win[8 + S_MAX - 1];
+    const float4 a = __ldg(reinterpret_cast<const float4*>(xr + w0)), b = __ldg(reinterpret_cast<const float4*>(xr + w0 + 4));
+    const float core[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 8 + S_MAX - 1; ++k) {
+      const int w = w0 + k - pad;
+      win[k] = (k >= pad && k < pad + 8) ? core[k - pad] : ((w >= 0 && w < W && k < 8 + S - 1) ? __ldg(xr + w) : 0.f);
+    }
+#pragma unroll
+    for (int sft = 0; sft < S_MAX; ++sft) {
+      if (sft < S) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float v0 = win[2 * k + sft], v1 = win[2 * k + 1 + sft];
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+          const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+          h[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          l[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        const long long o = (long long)sft * total + r * W + w0;
+        *reinterpret_cast<uint4*>(hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 split_shift_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long rows, int W,
                         int S, int pad) {
@@ -631,6 +675,12 @@ split_shift_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__
 extern "C" int edadm_split_shift_bf16(const float* x, void* hi, void* lo, int64_t rows, int W, int S, int pad, void* stream) {
   if (!x || !hi || !lo || rows < 1 || W < 1 || S < 1 || pad < 0) return fail(EDADM_ERR_ARG, "split_shift_bf16: bad arguments");
   const long long total = rows * W;
+  const bool vec = (W % 8) == 0 && S <= 3 && pad <= 1 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0;
+  if (vec) {
+    const int blocks = (int)std::min<long long>((total / 8 + 255) / 256, (long long)sm_count() * 16);
+    g3::split_shift_bf16_vec_kernel<3><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, rows, W, S, pad);
+    return check_launch("split_shift_bf16");
+  }
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 16);
   g3::split_shift_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, rows, W, S, pad);
   return check_launch("split_shift_bf16");
@@ -657,6 +707,7 @@ extern "C" int edadm_conv_wgrad_bf16x3(const void* dy_hi, const void* dy_lo, con
   p.m_tiles = (N + BM - 1) / BM;
   p.block_n = C >= 128 ? 128 : ((C + 31) / 32) * 32;
   if (C > 128 && C % 128 && C % 96 == 0) p.block_n = 96;
+  if (const char* e = getenv("EDADM_WGRAD_BN")) { const int v = atoi(e); if (v >= 32 && v <= 128 && v % 32 == 0) p.block_n = v; }   // experiments
   p.n_tiles = (C + p.block_n - 1) / p.block_n;
   p.splits = splits; p.k_steps = k_total / splits; p.reduce_add = splits > 1;
   p.conv = 2; p.taps = R * S; p.S = S; p.wg_cpi = cpi; p.wg_W = W; p.wg_pad = pad; p.wg_B = B;
