@@ -586,12 +586,15 @@ extern "C" int edadm_qattn_fwd(const uint8_t* qc, const uint8_t* kc, const uint8
     int rc = encode_map(&map_v, vc, 3, dims, strides, box, "attention v codes");
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set_dev[64] = {false};       // the opt-in is per device
+  int attr_dev = 0;
+  cudaGetDevice(&attr_dev);
+  attr_dev = attr_dev < 64 ? attr_dev : 63;
+  if (!attr_set_dev[attr_dev]) {
     cudaError_t e = cudaFuncSetAttribute(qattn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(qattn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
     if (e != cudaSuccess) return fail(EDADM_ERR_CUDA, "qattn_fwd: cannot opt in to %d B shared memory: %s", ATT_SMEM_BYTES, cudaGetErrorString(e));
-    attr_set = true;
+    attr_set_dev[attr_dev] = true;
   }
   dim3 grid((Tq + ATT_M - 1) / ATT_M, d_chunks, BH);
   // |raw - zq*rk| <= 255*255*max(d, dp): the magic-number int->float conversion is exact below 2^22

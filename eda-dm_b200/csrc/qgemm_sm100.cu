@@ -655,12 +655,15 @@ static int launch_qgemm(const uint8_t* q, int B, int Hp, int Wp, int Cp_act, int
   p.debug = 0;
   if (const char* e = getenv("EDADM_GEMM_DEBUG")) p.debug = atoi(e);
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set_dev[64] = {false};       // the opt-in is per device
+  int attr_dev = 0;
+  cudaGetDevice(&attr_dev);
+  attr_dev = attr_dev < 64 ? attr_dev : 63;
+  if (!attr_set_dev[attr_dev]) {
     cudaError_t e = cudaFuncSetAttribute(qgemm_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(qgemm_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return fail(EDADM_ERR_CUDA, "qgemm_i8: cannot opt in to %d B shared memory: %s", SMEM_LIMIT, cudaGetErrorString(e));
-    attr_set = true;
+    attr_set_dev[attr_dev] = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
