@@ -1,0 +1,11 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT"
+timeout 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_parity_full.py -x -q -m gpu --tb=short 2>&1 | tail -3
+timeout 600 python scratch/r02/gemm_table.py imagenet 2>&1 | grep -v Warn | grep "eager step\|  1728 \|  5184 \|  8640 \| 17280 \| 13824 "
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-recon > gpurun_out/bench_p12.json 2> gpurun_out/bench_p12.err; tail -2 gpurun_out/bench_p12.err
+python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/bench_p12.json').read().strip().splitlines() if l.startswith('{')][-1])
+print('imagenet', d['ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['share_of_eager_step'], d['gpu_launches'])
+s=d['secondary']; print('church', s['ms_per_step'], s['value'], s['e2e']['value'], s['roofline']['frac'])
+PY
