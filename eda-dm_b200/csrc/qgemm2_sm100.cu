@@ -69,7 +69,7 @@ struct __align__(8) Barriers {
 
 __device__ __forceinline__ float gelu_erf(float x) {
   // ATen's CUDA GELU (approximate='none'): x * 0.5 * (1 + erf(x * M_SQRT1_2))
-  return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  return x * 0.5f * (1.0f + erff_two_poly(x * 0.70710678118654752440f));
 }
 
 // same bits as clamp(round(x / d) + z, 0, qmax) (see pack.cu quant_code_fast)
