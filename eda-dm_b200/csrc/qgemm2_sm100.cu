@@ -41,6 +41,10 @@ struct Params {
   // split shortcut (two quantizer pairs along K, quant_layer.py:415-432): a second K range with its own weights / scales, summed
   // into a second TMEM accumulator (columns + block_n) and combined in the epilogue -- one launch, no fp32 round trip between them
   int dual, k_chunks1, k_last_mmas1, a_c_offset1;
+  // short-K linears (K <= 4 chunks, single CTAs): the weight tile of the CTA's N block stays in smem for the whole launch (b_res) and
+  // the stage ring carries activation tiles only -- with 3 K steps per tile an A+B ring is one tile deep and every tile pays the
+  // full TMA latency (measured: 370 us of the 475 us GEGLU projection remain with the whole epilogue switched off)
+  int b_res;
   const float* delta_a1; const float* zp_a1; const float* delta_w1; const int32_t* wsum_eff1;
   int Wo, HoWo;
   int block_n, n_tiles, m_units;            // m_units = ceil(m_tiles / CTAS): scheduling units along M
@@ -64,6 +68,7 @@ struct __align__(8) Barriers {
   uint64_t tmem_full[ACC_STAGES];
   uint64_t tmem_empty[ACC_STAGES];
   uint64_t res_full[MAX_RES_BUFS];
+  uint64_t b_full;
   uint32_t tmem_base;
 };
 
@@ -108,7 +113,7 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + p.stages * p.a_stage_bytes;
-  uint8_t* out_buf = smem_b + p.stages * p.b_stage_bytes;
+  uint8_t* out_buf = smem_b + (p.b_res ? p.k_chunks : p.stages) * p.b_stage_bytes;
   uint8_t* res_buf = out_buf + 2 * OUT_BUF_BYTES;
   float* epi_scale = reinterpret_cast<float*>(res_buf + p.res_bufs * OUT_BUF_BYTES);
   int* epi_zterm = reinterpret_cast<int*>(epi_scale + MAX_BN);
@@ -119,14 +124,15 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
-  const int unit0 = CTAS == 2 ? (int)cluster_id_x() : (int)blockIdx.x;
-  const int unit_step = CTAS == 2 ? (int)num_clusters_x() : (int)gridDim.x;
+  // b_res: CTA c owns N block c % n_tiles and every (gridDim / n_tiles)-th M tile; otherwise units are dealt round robin
+  const int unit0 = CTAS == 2 ? (int)cluster_id_x() : (p.b_res ? ((int)blockIdx.x / p.n_tiles) * p.n_tiles + (int)blockIdx.x % p.n_tiles : (int)blockIdx.x);
+  const int unit_step = CTAS == 2 ? (int)num_clusters_x() : (p.b_res ? ((int)gridDim.x / p.n_tiles) * p.n_tiles : (int)gridDim.x);
   const int num_units = p.m_units * p.n_tiles;
   const int k_iters0 = p.taps * p.k_chunks;
   const int k_iters = k_iters0 + (p.dual ? p.taps * p.k_chunks1 : 0);
   const int stages = p.stages;
   const int bn_cta = p.block_n / CTAS;                        // weight rows staged by this CTA
-  const uint32_t stage_tx = (uint32_t)p.a_stage_bytes + (uint32_t)bn_cta * p.kbytes;
+  const uint32_t stage_tx = (uint32_t)p.a_stage_bytes + (p.b_res ? 0u : (uint32_t)bn_cta * p.kbytes);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -136,6 +142,7 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     if (p.res_mode == 1) tma_prefetch_desc(&map_res);
     for (int i = 0; i < stages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&bars->tmem_full[i], 1); mbar_init(&bars->tmem_empty[i], EPI_WARPS * CTAS); }
+    mbar_init(&bars->b_full, 1);
     for (int i = 0; i < MAX_RES_BUFS; ++i) mbar_init(&bars->res_full[i], 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -158,6 +165,19 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     // ===================== TMA producer (both CTAs of a pair: own A rows, own half of B) =====================
     int stage = 0;
     uint32_t phase = 0;
+    if (CTAS == 1 && p.b_res && unit0 < num_units) {      // the CTA's weight rows, all K chunks, once
+      const bool geglu = p.out_mode == OUT_U8_GEGLU;
+      const int n_blk = unit0 % p.n_tiles;
+      const int nrow0 = geglu ? n_blk * (p.block_n / 2) : n_blk * p.block_n;
+      if (elect_one()) {
+        mbar_expect_tx(&bars->b_full, (uint32_t)p.k_chunks * (uint32_t)p.block_n * p.kbytes);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          tma_load_3d(smem_b + kc * p.b_stage_bytes, &map_b, &bars->b_full, kc * p.kbytes, 0, nrow0);
+          if (geglu) tma_load_3d(smem_b + kc * p.b_stage_bytes + (p.block_n / 2) * p.kbytes, &map_b, &bars->b_full, kc * p.kbytes, 0, nrow0 + p.geglu_half);
+        }
+      }
+      __syncwarp();
+    }
     for (int unit = unit0; unit < num_units; unit += unit_step) {
       const int n_blk = unit % p.n_tiles, m_unit = unit / p.n_tiles;
       const int m0 = (m_unit * CTAS + (int)rank) * BM;
@@ -187,8 +207,8 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
               } else {
                 mbar_expect_tx(&bars->full[stage], stage_tx);
                 tma_load_4d(smem_a + stage * p.a_stage_bytes, &map_a, &bars->full[stage], c_off + kc * p.kbytes, ow0 + kw, oh0 + kh, b0);
-                tma_load_3d(smem_b + stage * p.b_stage_bytes, mb, &bars->full[stage], kc * p.kbytes, tap, nrow0);
-                if (geglu) tma_load_3d(smem_b + stage * p.b_stage_bytes + b_half_bytes, mb, &bars->full[stage], kc * p.kbytes, tap, nrow1);
+                if (!p.b_res) tma_load_3d(smem_b + stage * p.b_stage_bytes, mb, &bars->full[stage], kc * p.kbytes, tap, nrow0);
+                if (geglu && !p.b_res) tma_load_3d(smem_b + stage * p.b_stage_bytes + b_half_bytes, mb, &bars->full[stage], kc * p.kbytes, tap, nrow1);
               }
             }
             __syncwarp();
@@ -207,6 +227,7 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (CTAS == 1 && p.b_res && unit0 < num_units) { mbar_wait(&bars->b_full, 0); tc_fence_after(); }
       for (int unit = unit0; unit < num_units; unit += unit_step) {
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -220,7 +241,7 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           if (++kc == kcs) kc = 0;
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
-          const uint32_t aaddr = a_base + stage * p.a_stage_bytes, baddr = b_base + stage * p.b_stage_bytes;
+          const uint32_t aaddr = a_base + stage * p.a_stage_bytes, baddr = b_base + (p.b_res ? (kc == 0 ? kcs - 1 : kc - 1) : stage) * p.b_stage_bytes;
           const uint64_t adesc = sw64 ? make_smem_desc_sw64(aaddr) : make_smem_desc(aaddr);
           const uint64_t bdesc = sw64 ? make_smem_desc_sw64(baddr) : make_smem_desc(baddr);
           if (elect_one()) {
@@ -282,11 +303,14 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     uint32_t tile_par = 0;                        // code outputs: staging buffer of the current tile
     uint32_t rchunk = 0;                          // running residual chunk counter: buffer = rchunk % res_bufs
     uint32_t rphase_bits = 0;                     // phase bit per residual buffer
+    int last_n_blk = -1;
     for (int unit = unit0; unit < num_units; unit += unit_step) {
       const int n_blk = unit % p.n_tiles, m_unit = unit / p.n_tiles;
       const int n0 = n_blk * p.block_n;
       const int m0 = (m_unit * CTAS + (int)rank) * BM;
-      // per-column epilogue constants of this tile (the previous tile's readers are past their last barrier)
+      // per-column epilogue constants of this tile (the previous tile's readers are past their last barrier); a CTA that keeps
+      // its N block for the whole launch (b_res) loads them once instead of paying their global-load latency on every tile
+      if (n_blk != last_n_blk)
       for (int j = et; j < p.block_n; j += EPI_WARPS * 32) {
         int n = n0 + j;
         if (mode == OUT_U8_GEGLU) n = (j < p.block_n / 2) ? n_blk * (p.block_n / 2) + j : p.geglu_half + n_blk * (p.block_n / 2) + (j - p.block_n / 2);
@@ -301,6 +325,7 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           epi_bias[MAX_BN / 2 + j] = 0.f;
         }
       }
+      last_n_blk = n_blk;
       // coordinates of this tile in the output / residual maps
       int co0, co1, co2;                          // NCHW: (pixel, channel, image); rows: (column, row)
       if (mode == OUT_F32_NCHW) {
@@ -634,7 +659,18 @@ int launch_qgemm2(const Gemm2Args& a, void* stream) {
   p.stages = (SMEM_LIMIT - fixed) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   if (p.stages < 2) return 1;
-  const int smem_bytes = fixed + p.stages * stage_bytes;
+  int smem_bytes = fixed + p.stages * stage_bytes;
+  // weight-resident schedule for the short-K linears: every CTA keeps the K chunks of ONE N block and streams activation tiles
+  int grid_res = 0;
+  if (ctas == 1 && !dual && a.R * a.S == 1 && p.k_chunks <= 4 && n_tiles <= sms && m_units >= 4 * (sms / n_tiles) && getenv("EDADM_GEMM_NO_BRES") == nullptr) {
+    const int a_stages = std::min(MAX_STAGES, (SMEM_LIMIT - fixed - p.k_chunks * p.b_stage_bytes) / p.a_stage_bytes);
+    if (a_stages >= p.k_chunks + 2) {               // more than one tile of activations in flight
+      p.b_res = 1;
+      p.stages = a_stages;
+      smem_bytes = fixed + p.k_chunks * p.b_stage_bytes + p.stages * p.a_stage_bytes;
+      grid_res = n_tiles * (sms / n_tiles);
+    }
+  }
 
   static int attr_dev_mask[64] = {0};
   int dev = 0;
@@ -658,7 +694,7 @@ int launch_qgemm2(const Gemm2Args& a, void* stream) {
     cudaError_t e = cudaLaunchKernelEx(&cfg, qgemm2_kernel<2>, map_a, map_b, map_out, map_res, map_b1, p);
     if (e != cudaSuccess) return fail(EDADM_ERR_CUDA, "qgemm2 (pairs): %s", cudaGetErrorString(e));
   } else {
-    const int grid = units < sms ? units : sms;
+    const int grid = grid_res ? grid_res : (units < sms ? units : sms);
     qgemm2_kernel<1><<<grid, THREADS, smem_bytes, (cudaStream_t)stream>>>(map_a, map_b, map_out, map_res, map_b1, p);
   }
   return check_launch("qgemm2");
