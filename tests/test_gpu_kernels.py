@@ -705,7 +705,9 @@ def test_qgemm2_conv_pairs_and_tma_store(cuda, monkeypatch, ctas, B, C, H, N, k,
 
 
 @pytest.mark.parametrize("M,K,N,geglu,w_bits", [(300, 384, 384, False, 4), (4096, 384, 3072, True, 4), (1000, 96, 192, True, 4),
-                                                (77, 320, 80, False, 8), (513, 128, 64, True, 8)])
+                                                (77, 320, 80, False, 8), (513, 128, 64, True, 8),
+                                                # large M: the weight-resident schedule (N block fixed per CTA, activation-only ring)
+                                                (32768, 384, 384, False, 4), (16384, 384, 3072, True, 4), (32900, 512, 256, False, 4)])
 def test_qgemm_codes_epilogue_bit_exact(cuda, M, K, N, geglu, w_bits):
     """the code-emitting epilogue (plain / GEGLU-gated) == fp32 GEMM output followed by the standalone quantizer producers"""
     from edadm import ops
