@@ -1,3 +1,3 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-timeout 600 python scratch/r02/gemm_table.py imagenet 2>&1 | grep -v Warn | head -30
+timeout 600 python scratch/r02/gemm_table.py imagenet 2>&1 | grep -v Warn | head -26
