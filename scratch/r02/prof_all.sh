@@ -25,4 +25,5 @@ run qattn_imagenet qattn_kernel 2 attn_in
 run qattn_church qattn_kernel 2 attn_church
 run gemm_bf16x3_conv gemm_bf16x3_kernel 2 bf16x3_conv
 run gemm_bf16x3_linear gemm_bf16x3_kernel 2 bf16x3_lin
+run gemm_bf16x3_wgrad gemm_bf16x3_kernel 2 bf16x3_wgrad
 ls -la gpurun_out/r02/ncu/*.ncu-rep | wc -l; du -sh gpurun_out/r02/ncu

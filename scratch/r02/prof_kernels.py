@@ -52,6 +52,8 @@ for rep in range(4):
         ops.qattn_bnd(q_,k_,v_,heads,aqn,dd**-0.5)
     elif which=='bf16x3_conv':            # reconstruction-loop conv on the bf16 x 3 kernel: ImageNet 16x16 ResBlock conv 576->576, batch 32
         x=R(32,576,16,16); w=R(576,576,3,3)*0.03; ops.conv_bf16x3(x,w,R(576))
+    elif which=='bf16x3_wgrad':           # convolution wgrad of the same ResBlock conv (pixels = reduction dimension, split-K)
+        x=R(32,576,16,16); gy=R(32,576,16,16); ops.conv_wgrad_bf16x3(gy,x,3)
     elif which=='bf16x3_lin':             # transformer-block linear of the reconstruction loop: 32 x 1024 tokens, 384 -> 3072
         x=R(32*1024,384); w=R(3072,384)*0.05; ops.linear_bf16x3(x,w,R(3072))
     torch.cuda.synchronize()

@@ -28,6 +28,7 @@ CASES={
  "qgemm_i8_lin_res": ("first-generation int8 GEMM, ff.net[2] linear with residual epilogue, M=131072, N=384, K=1536 (fp32 row-major out)", None, 2*131072*384*1536),
  "qattn_imagenet": ("fused quantized attention, ImageNet self-attention T=1024, d=384, 128 (batch x head): single S accumulator, one pass per CTA", None, 4*128*1024*1024*384),
  "gemm_bf16x3_conv": ("reconstruction-loop convolution on the bf16 x 3 tcgen05 kernel (implicit GEMM, NHWC split operands, NCHW TMA store): 3x3 576->576 at 16x16, batch 32 (M=8192, N=576, K=5184); flops counted 3x (hi.hi + hi.lo + lo.hi)", None, 3*2*8192*576*5184),
+ "gemm_bf16x3_wgrad": ("reconstruction-loop convolution WGRAD on the bf16 x 3 tcgen05 kernel: dW of the 3x3 576->576 conv at 16x16, batch 32 (pixels are the reduction: M=576, N=576 per tap, K=8192, 9 taps, split-K 4 with TMA reduce-add); flops counted 3x", None, 3*2*8192*576*5184),
  "gemm_bf16x3_linear": ("reconstruction-loop linear on the bf16 x 3 tcgen05 kernel: M=32768, N=3072, K=384; flops counted 3x", None, 3*2*32768*3072*384),
  "qattn_church": ("fused quantized attention, church T=1024, d=24, 800 (batch x head)", None, 4*800*1024*1024*24),
 }
