@@ -45,6 +45,7 @@ struct Params {
   // the stage ring carries activation tiles only -- with 3 K steps per tile an A+B ring is one tile deep and every tile pays the
   // full TMA latency (measured: 370 us of the 475 us GEGLU projection remain with the whole epilogue switched off)
   int b_res;
+  long long* trace;                         // debug (edadm_debug_set_gemm_trace): per CTA, per tile (first 16) role timestamps; null in production
   const float* delta_a1; const float* zp_a1; const float* delta_w1; const int32_t* wsum_eff1;
   int Wo, HoWo;
   int block_n, n_tiles, m_units;            // m_units = ceil(m_tiles / CTAS): scheduling units along M
@@ -178,10 +179,12 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       }
       __syncwarp();
     }
-    for (int unit = unit0; unit < num_units; unit += unit_step) {
+    int ti_p = 0;
+    for (int unit = unit0; unit < num_units; unit += unit_step, ++ti_p) {
       const int n_blk = unit % p.n_tiles, m_unit = unit / p.n_tiles;
       const int m0 = (m_unit * CTAS + (int)rank) * BM;
       const int b0 = m0 / p.HoWo;
+      if (p.trace && lane == 0 && ti_p < 16) p.trace[((size_t)blockIdx.x * 16 + ti_p) * 8 + 5] = clock64();
       const int rem = m0 - b0 * p.HoWo;
       const int oh0 = rem / p.Wo, ow0 = rem - oh0 * p.Wo;
       // weight rows of this CTA: a plain tile takes block_n consecutive rows (each CTA of a pair its half); a GEGLU tile is
@@ -216,6 +219,7 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           }
         }
       }
+      if (p.trace && lane == 0 && ti_p < 16) p.trace[((size_t)blockIdx.x * 16 + ti_p) * 8 + 6] = clock64();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
@@ -228,9 +232,11 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
       int acc = 0;
       uint32_t acc_phase = 0;
       if (CTAS == 1 && p.b_res && unit0 < num_units) { mbar_wait(&bars->b_full, 0); tc_fence_after(); }
-      for (int unit = unit0; unit < num_units; unit += unit_step) {
+      int ti_m = 0;
+      for (int unit = unit0; unit < num_units; unit += unit_step, ++ti_m) {
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (p.trace && lane == 0 && ti_m < 16) p.trace[((size_t)blockIdx.x * 16 + ti_m) * 8 + 0] = clock64();
         uint32_t tmem_d = tmem_base + (uint32_t)acc * MAX_BN;
         int kc = 0, kcs = p.k_chunks, klast = p.k_last_mmas, it_r = 0;
         for (int it = 0; it < k_iters; ++it, ++it_r) {
@@ -241,6 +247,7 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           if (++kc == kcs) kc = 0;
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
+          if (p.trace && lane == 0 && it == 0 && ti_m < 16) p.trace[((size_t)blockIdx.x * 16 + ti_m) * 8 + 1] = clock64();
           const uint32_t aaddr = a_base + stage * p.a_stage_bytes, baddr = b_base + (p.b_res ? (kc == 0 ? kcs - 1 : kc - 1) : stage) * p.b_stage_bytes;
           const uint64_t adesc = sw64 ? make_smem_desc_sw64(aaddr) : make_smem_desc(aaddr);
           const uint64_t bdesc = sw64 ? make_smem_desc_sw64(baddr) : make_smem_desc(baddr);
@@ -267,6 +274,7 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           else umma_commit(&bars->tmem_full[acc]);
         }
         __syncwarp();
+        if (p.trace && lane == 0 && ti_m < 16) p.trace[((size_t)blockIdx.x * 16 + ti_m) * 8 + 2] = clock64();
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -304,6 +312,7 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     uint32_t rchunk = 0;                          // running residual chunk counter: buffer = rchunk % res_bufs
     uint32_t rphase_bits = 0;                     // phase bit per residual buffer
     int last_n_blk = -1;
+    int ti_e = 0;
     for (int unit = unit0; unit < num_units; unit += unit_step) {
       const int n_blk = unit % p.n_tiles, m_unit = unit / p.n_tiles;
       const int n0 = n_blk * p.block_n;
@@ -357,6 +366,9 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (p.trace && et == 0 && ti_e < 16) p.trace[((size_t)blockIdx.x * 16 + ti_e) * 8 + 3] = clock64();
+      // (software-pipelining these TMEM loads against the conversion of the previous chunk was measured and is slower: the epilogue
+      // is bound by its instruction count, not by the TMEM latency -- profiles/gemm2_timeline_r02.txt)
       for (int ci = 0; ci < n_chunks; ++ci, ++gchunk) {
         const int c0 = ci * CHUNK + 16 * half;    // first of this thread's 16 columns inside the tile
         uint32_t a[16];
@@ -373,6 +385,7 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             if (CTAS == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->tmem_empty[acc]), 0));
             else mbar_arrive(&bars->tmem_empty[acc]);
           }
+          if (p.trace && et == 0 && ti_e < 16) p.trace[((size_t)blockIdx.x * 16 + ti_e) * 8 + 7] = clock64();
         }
         // dequantise: exact int32 zero-point fold, one fp32 FMA; the per-column constants come as 128-bit broadcast loads
         dequant16(a, v, epi_zterm + c0, epi_scale + c0, epi_bias + c0, has_cw ? epi_cw + c0 : nullptr, rs);
@@ -459,6 +472,8 @@ qgemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         // the two warps of a quarter hold the two 16-column halves of every chunk of this row
         if (m < p.M && rowsum_codes) atomicAdd(p.q_rowsum + m, rowsum_codes);
       }
+      if (p.trace && et == 0 && ti_e < 16) p.trace[((size_t)blockIdx.x * 16 + ti_e) * 8 + 4] = clock64();
+      ++ti_e;
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
     if (issuer) bulk_wait<0>();                   // all stores complete before the CTA (and its shared memory) goes away
@@ -502,6 +517,8 @@ struct Gemm2Args {
   const void* wq1 = nullptr; int Cp_w1 = 0; int a_c_offset1 = 0;
   const float* delta_a1 = nullptr; const float* zp_a1 = nullptr; const float* delta_w1 = nullptr; const int32_t* wsum_eff1 = nullptr;
 };
+
+long long* gemm_trace_buffer();                   // qgemm_sm100.cu (edadm_debug_set_gemm_trace)
 
 // returns EDADM_OK, an error, or +1 when this kernel does not cover the case (the caller falls back to the first-generation kernel)
 int launch_qgemm2(const Gemm2Args& a, void* stream) {
@@ -649,6 +666,7 @@ int launch_qgemm2(const Gemm2Args& a, void* stream) {
   p.bias_img = a.bias_img;
   p.delta_a = a.delta_a; p.zp_a = a.zp_a; p.delta_w = a.delta_w; p.wsum_eff = a.wsum_eff; p.cw = a.cw; p.rowsum = a.rowsum; p.bias = a.bias;
   p.q_delta = a.q_delta; p.q_zp = a.q_zp; p.q_max = (float)(a.q_levels - 1); p.q_rowsum = a.q_rowsum;
+  p.trace = gemm_trace_buffer();
   const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   const int fixed_no_res = 1024 + 2 * OUT_BUF_BYTES + EPI_VEC_BYTES + 1024;
   p.res_bufs = 0;

@@ -543,6 +543,7 @@ using namespace edadm;
 static long long* g_gemm_trace = nullptr;
 // debug hook (scratch/ timeline experiments only): per-CTA [16 tiles][8] clock64 stamps of the warp roles
 extern "C" int edadm_debug_set_gemm_trace(long long* buf) { g_gemm_trace = buf; return 0; }
+namespace edadm { long long* gemm_trace_buffer() { return g_gemm_trace; } }
 
 // Activation codes q: [B][Hp][Wp][Cp_act] u8 (halo included), filter R x S, stride 1:  Ho = Hp-R+1, Wo = Wp-S+1.
 // A 2-D GEMM ([M][Kp] rows) is the special case B=1, Hp=1, Wp=M, R=S=1.
