@@ -120,6 +120,29 @@ def test_quant_model_rewrite_ldm(name):
         assert isinstance(mods[qname], UniformAffineQuantizer), qname
 
 
+def test_lazy_concatenation_host_logic():
+    """CatPair quacks like the concatenated tensor and materialises on demand; a QuantResBlock only takes the two-source route on
+    the integer path (CUDA, no hooks, no gradients): on CPU / in FP state the UNet forward falls back to th.cat and stays exact"""
+    from edadm import ops
+    from qdiff.quant_block import QuantResBlock
+    a, b = torch.randn(2, 32, 4, 4), torch.randn(2, 16, 4, 4)
+    pair = ops.CatPair(a, b)
+    assert tuple(pair.shape) == (2, 48, 4, 4) and pair.dim() == 4 and pair.numel() == a.numel() + b.numel()
+    assert pair.dtype == a.dtype and pair.device == a.device and not pair.is_cuda
+    full = pair.materialize()
+    assert torch.equal(full, torch.cat([a, b], 1)) and pair.materialize() is full          # cached
+    assert not ops.cat_slices_ok(pair, 0)                                                   # CPU tensors never take the slice kernels
+    g = H.load("ldm_tiny.npz")
+    model = H.ldm_model("ldm_tiny.npz")
+    model.load_state_dict(H.state_dict(g))
+    qnn = _qmodel(model)
+    blocks = [m for m in qnn.modules() if isinstance(m, QuantResBlock)]
+    assert blocks and all(m.lazy_cat(a, b) is None for m in blocks)                         # CPU: always the materialised path
+    args = [torch.from_numpy(g["x"])[:4], torch.from_numpy(g["t"])[:4]]
+    with torch.no_grad():
+        assert H.rel_l2(qnn(*args), torch.from_numpy(g["y_fp"])) < 1e-6
+
+
 def test_scale_search_equals_oracle_on_cpu():
     """The product's range search (pure tensor ops, device independent) == the oracle's restatement == the reference."""
     from qdiff.quant_layer import UniformAffineQuantizer
