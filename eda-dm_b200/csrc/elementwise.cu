@@ -328,6 +328,7 @@ extern "C" int edadm_uaq_fwd(const float* x, float* y, uint8_t* codes, const flo
                              const float* zero_point, int64_t n, int64_t channels, int64_t inner,
                              int n_levels, const uint8_t* keep_mask, const float* keep_rand, float qdrop_prob,
                              uint64_t seed, uint64_t offset, void* stream) {
+  if (n == 0) return EDADM_OK;   // empty tensor (torch hands out a null data pointer for it): nothing to do
   if (!x || !y || !delta || !zero_point) return fail(EDADM_ERR_ARG, "uaq_fwd: null pointer");
   if (n < 0 || channels < 1 || inner < 1 || n_levels < 2 || n_levels > 256)
     return fail(EDADM_ERR_ARG, "uaq_fwd: bad sizes n=%lld channels=%lld inner=%lld levels=%d",

@@ -120,6 +120,8 @@ class UAQFunction(torch.autograd.Function):
 
 
 def uaq_fake_quant(x, delta, zero_point, n_levels, keep_mask=None, prob=1.0, seed=0, offset=0, keep_rand=None):
+    if x.numel() == 0:          # empty batch: the element-wise quantizer of nothing
+        return x.clone()
     return UAQFunction.apply(x, delta, zero_point, n_levels, keep_mask, prob, seed, offset, keep_rand)
 
 
@@ -740,7 +742,7 @@ def qgemm_i8_codes(q, pw: PackedWeight, delta_a, zp_a, consumer, bias=None, rows
 
 def conv3x3_small_n_ok(x, weight, kwargs):
     """True when `F.conv2d(x, weight, **kwargs)` is the narrow output-layer case edadm_conv3x3_small_n covers."""
-    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and weight.dim() == 4):
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and weight.dim() == 4) or x.numel() == 0:
         return False
     if weight.shape[0] > 4 or tuple(weight.shape[2:]) != (3, 3) or x.shape[0] > 65535 or weight.shape[1] * weight.shape[0] > 3600:
         return False

@@ -39,6 +39,8 @@ def _fusable(tensors, quantizers, n_keys=0, bh=0):
     for t in tensors:
         if not t.is_cuda or t.dtype != th.float32 or (th.is_grad_enabled() and t.requires_grad):
             return False
+        if t.numel() == 0:          # empty batch: nothing to launch, torch's batched matmul returns the empty result
+            return False
     for q in quantizers:
         if q.inited is False or q.delta is None or q.channel_wise or (q.is_training and q.prob < 1.0):
             return False
@@ -94,10 +96,10 @@ def legacy_attention_forward(self, qkv):
             _fusable((qkv,), (qk.act_quantizer_q, qk.act_quantizer_k, sv.act_quantizer_v, sv.act_quantizer_w), n_keys=length,
                      bh=bs * self.n_heads):
         aq = _aquant(qk.act_quantizer_q, qk.act_quantizer_k, sv.act_quantizer_v, sv.act_quantizer_w)
-        return ops.qattn_bct(q, k, v, aq, scale, 1.0).reshape(bs, -1, length)
+        return ops.qattn_bct(q, k, v, aq, scale, 1.0).reshape(bs, self.n_heads * ch, length)
     weight = qk(q, k)
     weight = th.softmax(weight.float(), dim=-1).type(weight.dtype)
-    return sv(weight, v).reshape(bs, -1, length)
+    return sv(weight, v).reshape(bs, self.n_heads * ch, length)
 
 
 def patch_legacy_attention(module):

@@ -261,7 +261,7 @@ class QuantAttentionBlock(BaseQuantBlock):
 
     def _forward(self, x):
         b, c, *spatial = x.shape
-        x = x.reshape(b, c, -1)
+        x = x.flatten(2)
         if isinstance(self.qkv, QuantModule):
             qkv = self.qkv.forward_prenorm(x, self.norm, silu=False)     # GroupNorm folded into the qkv producer
         else:

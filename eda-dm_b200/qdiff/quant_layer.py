@@ -379,6 +379,8 @@ class QuantModule(nn.Module):
     def _integer_path_ok(self, input):
         if not input.is_cuda or input.dtype != torch.float32 or torch.is_grad_enabled() and input.requires_grad:
             return False
+        if input.numel() == 0:      # empty batch (a ragged last shard): no tile to launch; the elementwise + library route returns
+            return False            # the empty result F.conv2d / F.linear give in the reference
         return self._integer_state_ok(input)
 
     def _integer_state_ok(self, input=None):
@@ -528,7 +530,7 @@ class QuantModule(nn.Module):
         fold = bias_img is not None and residual is None and not tokens_out and self._epilogue_residual(bias_img) is not None
         out = self._finish(self._forward_int8(x, affine=(a, s, silu), residual=self._epilogue_residual(residual),
                                               tokens_out=tokens_out, bias_img=bias_img if fold else None, codes=codes), residual)
-        return out if bias_img is None or fold else out + bias_img.reshape(out.shape[0], -1, *([1] * (out.dim() - 2)))
+        return out if bias_img is None or fold else out + bias_img.reshape(out.shape[0], out.shape[1], *([1] * (out.dim() - 2)))
 
     def forward_upsample2x(self, x):
         """`self(F.interpolate(x, scale_factor=2, mode="nearest"))` -- the conv of a resampling `Upsample` (openaimodel.py Upsample,
@@ -748,7 +750,7 @@ class QuantModule(nn.Module):
                     and self._epilogue_residual(bias_img) is not None)
             if not fold:
                 out = self.forward(input, split=split, residual=residual)
-                return out + bias_img.reshape(out.shape[0], -1, *([1] * (out.dim() - 2)))
+                return out + bias_img.reshape(out.shape[0], out.shape[1], *([1] * (out.dim() - 2)))
         if split != 0 and self.split != 0:
             assert split == self.split
         elif split != 0:
@@ -820,6 +822,8 @@ def _implicit_tiling_ok(B, Ho, Wo):
 def _library_fwd(fn, input, weight, bias, kwargs):
     """fp32 conv / linear of the calibration + FP paths (cuDNN / cuBLAS), TF32 off unless opted in.  The narrow output
     layer (<= 4 channels, its input is never quantized) takes the dedicated stencil kernel when no gradient is needed."""
+    if input.numel() == 0:          # empty batch: the library's own empty result, no kernel of ours has a tile to run
+        return fn(input, weight, bias, **kwargs)
     if fn is F.conv2d and ops.conv3x3_small_n_ok(input, weight, kwargs):
         return ops.conv3x3_small_n(input, weight, bias)
     if (fn is F.linear and backend.calib_gemm_bf16x3 and ops.linear_bf16x3_ok(input, weight) and

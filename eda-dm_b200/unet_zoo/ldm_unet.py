@@ -142,7 +142,7 @@ class QKVAttentionLegacy(nn.Module):
         self.qkv_matmul.scale = 1 / math.sqrt(math.sqrt(ch))
         weight = self.qkv_matmul(q, k)
         weight = torch.softmax(weight.float(), dim=-1).type(weight.dtype)
-        return self.smv_matmul(weight, v).reshape(bs, -1, length)
+        return self.smv_matmul(weight, v).reshape(bs, self.n_heads * ch, length)
 
 
 class AttentionBlock(nn.Module):
@@ -158,7 +158,7 @@ class AttentionBlock(nn.Module):
 
     def forward(self, x):
         b, c, *spatial = x.shape
-        x = x.reshape(b, c, -1)
+        x = x.flatten(2)
         # quantized modules (qdiff.QuantModule) take GroupNorm into their activation producer and the residual into
         # their epilogue; plain nn.Conv1d runs module by module
         if hasattr(self.qkv, 'forward_prenorm'):
@@ -253,12 +253,12 @@ class SpatialTransformer(nn.Module):
         if hasattr(self.proj_in, 'forward_prenorm'):
             y = self.proj_in.forward_prenorm(x, self.norm, silu=False, tokens_out=True)
         else:
-            y = self.proj_in(self.norm(x)).reshape(b, -1, h * w).permute(0, 2, 1)
+            y = self.proj_in(self.norm(x)).flatten(2).permute(0, 2, 1)
         for blk in self.transformer_blocks:
             y = blk(y, context)
         if hasattr(self.proj_out, 'forward_from_tokens') and not self.proj_out._forward_hooks:
             return self.proj_out.forward_from_tokens(y, (h, w), residual=x)
-        y = y.permute(0, 2, 1).reshape(b, -1, h, w)
+        y = y.permute(0, 2, 1).reshape(b, y.shape[2], h, w)
         return self.proj_out(y) + x
 
 

@@ -453,6 +453,27 @@ def test_qattn_cross_layout(cuda, B, heads, d, Tq, Tk):
     assert _rel_l2(out.cpu(), ref) < 1e-3
 
 
+def test_qattn_sd_self_attention_max_keys(cuda):
+    """Stable-Diffusion self-attention at the 64x64 level (quant_block.py:204-235: T = 4096 tokens, d = 40) -- exactly the
+    kernel's key limit (csrc/qattn.cu ATT_MAX_KEYS), two of the eight heads.  Ranges are set by hand (max-abs for q/k/v, a
+    clipping range for the probabilities as the mse search picks) so that the CPU oracle finishes in seconds."""
+    from edadm import ops
+    heads, d, T = 2, 40, 4096
+    g = torch.Generator().manual_seed(29)
+    q, k, v = (torch.randn(1, T, heads * d, generator=g) for _ in range(3))
+    scale = d ** -0.5
+
+    def sp(t):
+        return t.reshape(1, T, heads, d).permute(0, 2, 1, 3).reshape(heads, T, d)
+    qp = {n: dict(delta=t.abs().max() / 127.5, zero_point=torch.tensor(128.), n_levels=256) for n, t in (("q", q), ("k", k), ("v", v))}
+    p_max = float((torch.einsum("bid,bjd->bij", sp(q), sp(k)) * scale).softmax(-1).max())
+    qp["w"] = dict(delta=torch.tensor(0.25 * p_max / 255), zero_point=torch.tensor(0.), n_levels=256)
+    ref = O.attn_core_cross(q, k, v, heads, scale, qp)
+    out = ops.qattn_bnd(sp(q).contiguous().to(cuda), sp(k).contiguous().to(cuda), sp(v).contiguous().to(cuda), heads,
+                        _to_aquant(cuda, qp), scale)
+    assert _rel_l2(out.cpu(), ref) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,C,H,N", [(2, 192, 32, 3), (3, 64, 13, 4), (1, 30, 40, 1), (2, 128, 8, 2)])
 def test_conv3x3_small_n(cuda, B, C, H, N):

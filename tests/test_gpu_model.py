@@ -126,6 +126,41 @@ def test_unet_end_to_end_within_reference_platform_noise(cuda, name, make, split
     assert H.rel_l2(y, y_same_device) <= max(2.0 * noise, 1e-3)
 
 
+@pytest.mark.parametrize("name,make,split_attr", [CASES[0], CASES[3]], ids=["ddim_tiny", "ldm_xattn_tiny"])
+def test_empty_and_ragged_batches(cuda, name, make, split_attr):
+    """Edge cases of the data-parallel sampler: an EMPTY shard (batch 0: the reference's F.conv2d / F.linear / einsum return
+    empty tensors; the integer kernels have no tile to launch, so every layer must step aside) and a ragged shard of ONE
+    image (M = H*W rows, far below one 128-row tile at the inner levels), layer by layer against the same layer fed the
+    full batch: the integer GEMM is exact, so a row's result may not depend on what else is in the batch."""
+    from qdiff.quant_layer import QuantModule
+    g = H.load(name)
+    qnn = _product(g, make(), cuda, split_attr)
+    args = _args(g, cuda)
+    with torch.no_grad():
+        y_fp = qnn(*args)
+        H.install_qparams(qnn, H.qtable(g))
+        qnn.set_quant_state(True, True)
+        empty = qnn(*[a[:0] for a in args])
+        assert empty.shape == (0,) + tuple(y_fp.shape[1:]) and empty.dtype == y_fp.dtype
+        full = {}
+        hooks = _capture([(n, m) for n, m in qnn.named_modules() if isinstance(m, QuantModule)], full)
+        qnn(*args)
+        for h in hooks:
+            h.remove()
+        worst = 0.0
+        for lname, layer in qnn.named_modules():
+            if not isinstance(layer, QuantModule):
+                continue
+            xin, yfull = full[lname]
+            y1 = layer(xin[:1].contiguous())
+            assert y1.shape == yfull[:1].shape
+            worst = max(worst, H.rel_l2(y1.cpu(), yfull[:1].cpu()))
+            e = layer(xin[:0])
+            assert e.shape == (0,) + tuple(yfull.shape[1:]), (lname, e.shape)
+        print(f"{name}: one-image shard vs the same rows of the full batch, worst layer rel-L2 {worst:.2e}")
+        assert worst < 1e-6
+
+
 def test_ddim_tiny_scale_search_on_gpu(cuda):
     """The product's own set_weight/act_quantize_params (search on the GPU) lands on the reference's scales."""
     from qdiff import set_weight_quantize_params, set_act_quantize_params
