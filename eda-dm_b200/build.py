@@ -11,8 +11,8 @@ LIB = os.path.join(LIBDIR, "libedadm.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 # per-file extras: the quantizer files must reproduce torch's separate mul/add roundings
-EXTRA = {"elementwise.cu": ["-fmad=false"], "pack.cu": ["-fmad=false"], "qgemm2_sm100.cu": ["-fmad=false"], "gemm_bf16x3_sm100.cu": ["-fmad=false"]}
-SOURCES = ["common.cu", "elementwise.cu", "pack.cu", "qgemm_sm100.cu", "qgemm2_sm100.cu", "gemm_bf16x3_sm100.cu", "qattn.cu", "conv_small.cu"]
+EXTRA = {"elementwise.cu": ["-fmad=false"], "optim.cu": ["-fmad=false"], "pack.cu": ["-fmad=false"], "qgemm2_sm100.cu": ["-fmad=false"], "gemm_bf16x3_sm100.cu": ["-fmad=false"]}
+SOURCES = ["common.cu", "elementwise.cu", "optim.cu", "pack.cu", "qgemm_sm100.cu", "qgemm2_sm100.cu", "gemm_bf16x3_sm100.cu", "qattn.cu", "conv_small.cu"]
 
 
 def _newest(paths):

@@ -28,6 +28,7 @@ _SIGNATURES = {
     "edadm_round_reg": (c_int, [P, c_int64, c_float, c_float, P, P, c_int, P, P]),
     "edadm_lp_loss_fwd": (c_int, [P, P, c_int64, c_float, c_float, P, P, P]),
     "edadm_lp_loss_bwd": (c_int, [P, P, c_int64, c_float, c_float, P, P, P]),
+    "edadm_fused_adam": (c_int, [P, c_int, P, P, P, P, P, c_double, c_double, c_float, c_int, P]),
     "edadm_mse_search_scores": (c_int, [P, c_int64, c_int64, P, P, c_int, c_int, c_float, P, P]),
     "edadm_act_quant_nhwc": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P, c_int, c_float, c_int64, P]),
     "edadm_act_quant_rows": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, c_int, c_int, P, P, c_int, c_float, c_int, c_int64, P]),

@@ -261,6 +261,17 @@ def lp_loss(pred, tgt, p=2.0, reduction="none"):
     return LpLossFunction.apply(pred, tgt, p, reduction == "none")
 
 
+def fused_adam(segments, n_segments, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, zero_grad=True):
+    """One Adam step over every parameter segment (torch.optim.Adam semantics; reference qdiff/block_recon.py:113-117, 199-206).
+    segments: int64 [n, 3] device table (qdiff._fused_adam.segment_table); grad / exp_avg / exp_avg_sq: flat fp32 buffers;
+    lr: two device floats; step: device int64 step count (>= 1).  Parameters are updated in place through raw pointers."""
+    _need_cuda(segments, grad, exp_avg, exp_avg_sq, lr, step)
+    assert segments.dtype == torch.int64 and segments.is_contiguous() and step.dtype == torch.int64
+    assert all(t.dtype == torch.float32 and t.is_contiguous() for t in (grad, exp_avg, exp_avg_sq, lr))
+    lib.fused_adam(segments.data_ptr(), int(n_segments), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                   lr.data_ptr(), step.data_ptr(), float(beta1), float(beta2), float(eps), int(bool(zero_grad)), _stream())
+
+
 # ------------------------------------------------------------------------------------------------
 # K1  integer path
 # ------------------------------------------------------------------------------------------------

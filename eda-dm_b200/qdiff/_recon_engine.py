@@ -26,6 +26,7 @@ from .adaptive_rounding import AdaRoundQuantizer
 from .utils import AttentionMap
 from edadm import ops
 from . import dist as qdist
+from ._fused_adam import FusedAdam
 
 logger = logging.getLogger(__name__)
 
@@ -235,12 +236,13 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
     use_graph = _graph_capturable(unit, device) and bool(w_para or a_para)
     w_opt = a_opt = w_sched = a_sched = None
     w_lr = a_lr = None
+    fused_adam = use_graph and backend.recon_fused_adam
     if use_graph:   # learning rates live on the device so the captured Adam steps see the schedule
-        w_lr = torch.tensor(float(lr_w), device=device)
-        a_lr = torch.tensor(float(lr_a), device=device)
-        if w_para:
+        lrs = torch.tensor([float(lr_w), float(lr_a)], device=device)
+        w_lr, a_lr = lrs[0], lrs[1]
+        if w_para and not fused_adam:
             w_opt = torch.optim.Adam(w_para, lr=w_lr, capturable=True)
-        if a_para:
+        if a_para and not fused_adam:
             a_opt = torch.optim.Adam(a_para, lr=a_lr, capturable=True)
     else:
         if w_para:
@@ -257,6 +259,8 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
     sz = cached_outs.size(0)
     model.block_count = model.block_count + 1
     bucket = qdist.GradBucket(w_para + a_para) if (w_para or a_para) else None
+    # both Adam updates as ONE pass over the flat gradient bucket (edadm_fused_adam), which also clears the consumed gradients
+    adam = FusedAdam(bucket, len(w_para), lrs) if (fused_adam and bucket is not None) else None
     rng = random if not qdist.is_active() else random.Random(random.getrandbits(48) + 7919 * qdist.rank())
     losses = []
     fbr = (not is_layer) and len(hooks) != 0 and add_loss != 0.0
@@ -320,7 +324,7 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
         elif not is_layer:
             cur_inp = cur_sym
         if bucket is not None:
-            bucket.zero()
+            bucket.zero(memset=adam is None)
         args_q = (cur_inp, emb_inp) if resblock else (cur_inp,)
         args_fp = (cur_sym, emb_sym) if resblock else (cur_sym,)
         m_loss = 0.0
@@ -367,6 +371,8 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
             bucket.all_reduce_mean()
             if timing is not None and 'grad_norms' in timing:
                 gnorm_out[0].copy_(bucket.flat[:n_w].norm()); gnorm_out[1].copy_(bucket.flat[n_w:].norm())
+        if adam is not None:
+            adam.step()
         for opt in (w_opt, a_opt):
             if opt is not None:
                 opt.step()
@@ -447,6 +453,8 @@ def reconstruct(model, unit, cali_data, *, batch_size, iters, weight, opt_mode, 
         timing['cuda_graph'] = bool(graph)
         timing['fp_taps_memoised'] = memo
     finish_unit(unit, trained, hooks, attn_only)
+    if adam is not None:
+        adam.finish()
     if bucket is not None:
         bucket.release()
         for prm in bucket.params:

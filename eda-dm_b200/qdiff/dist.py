@@ -58,8 +58,10 @@ class GradBucket:
 
         self._works, self._done, self._hooks = [], set(), []
 
-    def zero(self):
-        self.flat.zero_()
+    def zero(self, memset: bool = True):
+        """start of an iteration; memset=False when the previous optimiser pass already cleared the buffer (FusedAdam)"""
+        if memset:
+            self.flat.zero_()
         self._works, self._done = [], set()
 
     def overlap_backward(self, min_numel: int = 1 << 16, stream=None):

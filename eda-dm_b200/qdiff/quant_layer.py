@@ -42,6 +42,7 @@ class _Backend:
     recon_overlap_allreduce = True    # data parallel: all-reduce each alpha gradient as soon as its backward has produced it
     recon_memoise_fp_taps = True      # FP-model taps of the per-layer loss: computed once per unit for all cached samples (HBM), not per iteration
     recon_memoise_bytes = 32 << 30    #   ... as long as they fit in this many bytes
+    recon_fused_adam = True           # both Adam updates of an iteration as one pass over the flat gradient bucket (edadm_fused_adam)
     calib_gemm_bf16x3 = True          # linears of the reconstruction loop (fwd / dgrad / wgrad) on edadm_gemm_bf16x3 instead of cuBLAS fp32
     calib_conv_wgrad_bf16x3 = True    # ... including the convolution wgrad (False: cuDNN's, TF32 by torch's default -- 6-10 % faster on the
                                       # 576-channel ImageNet ResBlocks, 10-18 % slower on church's, 50x less accurate)

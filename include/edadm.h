@@ -73,6 +73,17 @@ int edadm_lp_loss_fwd(const float* pred, const float* tgt, int64_t n, float p, f
 int edadm_lp_loss_bwd(const float* pred, const float* tgt, int64_t n, float p, float inv_rest, const float* gloss,
                       float* gpred, void* stream);
 
+/* ---- K6: optimiser step of the reconstruction loop --------------------------------------------------
+ * Replaces the two torch.optim.Adam(...).step() calls per iteration (qdiff/block_recon.py:113-117 construct them,
+ * :199-206 step them; layer_recon.py:82-86, attn_layer_recon.py:68-72) with ONE pass over the flat gradient bucket
+ * of the unit (SURVEY.md section 8b "edadm_fused_adam").  segments: device table of n_segments records
+ * {float* param, int64 flat_offset, int32 count, int32 group}; lr: two device floats (group 0 = AdaRound alphas,
+ * group 1 = activation step sizes); step: device int64, the 1-based step count.  Arithmetic of torch's
+ * _single_tensor_adam (amsgrad off, no weight decay).  zero_grad != 0 also clears the consumed gradients.          */
+int edadm_fused_adam(const void* segments, int n_segments, float* grad, float* exp_avg, float* exp_avg_sq,
+                     const float* lr, const int64_t* step, double beta1, double beta2, float eps, int zero_grad,
+                     void* stream);
+
 /* ---- K1 prologue: integer-code producers ----------------------------------------------------------
  * Activation codes are exactly clamp(rint(x/delta)+zp, 0, L-1) (quant_layer.py:267-268) stored as u8.
  * act_quant_nhwc: x fp32 [B][C][H][W] -> q [B][H+2pad][W+2pad][Cp]; halo pixels hold the zero-point

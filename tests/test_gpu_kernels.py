@@ -1067,3 +1067,59 @@ def test_bmm_nt_bf16x3_forward_and_gradients(cuda, G, M, N, K):
     assert _rel_l2(c.detach().double(), cd.detach()) < 2e-5
     assert _rel_l2(a.grad.double(), ad.grad) < 2e-5
     assert _rel_l2(b.grad.double(), bd.grad) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------
+def test_fused_adam_matches_torch_optim(cuda):
+    """edadm_fused_adam (both optimisers of a reconstruction unit in one pass over the flat gradient bucket) against the
+    reference's optimiser, torch.optim.Adam (qdiff/block_recon.py:113-117), run in fp64 on the CPU: two parameter groups
+    with their own (changing) learning rates, tensors whose sizes / flat offsets break 16-byte alignment, scalars (the
+    activation step sizes), a tensor spanning several 8192-element segments; consumed gradients are cleared; version
+    counters move so that packed-weight caches notice."""
+    from qdiff.dist import GradBucket
+    from qdiff._fused_adam import FusedAdam
+    g = torch.Generator().manual_seed(71)
+    shapes_w, shapes_a = [(40, 32, 3, 3), (7, 3), (20000,), (5, 5, 5)], [(), (), (1,), ()]
+    init = [torch.randn(s, generator=g) for s in shapes_w] + [torch.rand(s, generator=g) * 0.1 + 0.01 for s in shapes_a]
+    ours = [torch.nn.Parameter(t.clone().to(cuda)) for t in init]
+    ref = [torch.nn.Parameter(t.clone().double()) for t in init]
+    nw = len(shapes_w)
+    bucket = GradBucket(ours)
+    lrs = torch.zeros(2, device=cuda)
+    adam = FusedAdam(bucket, nw, lrs)
+    opt_w, opt_a = torch.optim.Adam(ref[:nw], lr=1e-2, foreach=False), torch.optim.Adam(ref[nw:], lr=4e-4, foreach=False)
+    versions = [p._version for p in ours]
+    for it in range(6):
+        lr_w, lr_a = 1e-2 * (1 - it / 8), 4e-4 * (1 - it / 8)
+        lrs.copy_(torch.tensor([lr_w, lr_a]))
+        for grp, lr in ((opt_w, lr_w), (opt_a, lr_a)):
+            grp.param_groups[0]['lr'] = lr
+        grads = [torch.randn(t.shape, generator=g) * (10.0 ** (-(i % 4))) for i, t in enumerate(init)]
+        grads[2][:100] = 0.0                                   # exact zeros: update is 0 / (0 + eps)
+        for p, r, gr in zip(ours, ref, grads):
+            p.grad.copy_(gr.to(cuda))                          # views into bucket.flat
+            r.grad = gr.double()
+        adam.step()
+        opt_w.step(); opt_a.step()
+        assert float(bucket.flat.abs().max()) == 0.0           # consumed gradients cleared for the next backward
+    adam.finish()
+    assert all(p._version > v for p, v in zip(ours, versions))
+    assert int(adam.step_count) == 6
+    worst = 0.0
+    for p, r, t0 in zip(ours, ref, init):
+        moved = float((r.detach() - t0.double()).abs().max())
+        err = float((p.detach().cpu().double() - r.detach()).abs().max())
+        worst = max(worst, err / max(moved, 1e-30))
+        assert err <= 1e-4 * moved + 1e-6 * float(t0.abs().max()), (tuple(t0.shape), err, moved)   # fp32 storage of p: ~1 ulp per step
+    # moments against the fp64 optimiser state
+    states = [opt.state[r] for r, opt in zip(ref, [opt_w] * nw + [opt_a] * (len(ref) - nw))]
+    for key, buf in (('exp_avg', adam.exp_avg), ('exp_avg_sq', adam.exp_avg_sq)):
+        want = torch.cat([st[key].reshape(-1) for st in states])
+        got = buf.cpu().double()
+        assert _rel_l2(got, want) < 1e-6
+        off = 0
+        for i, st in enumerate(states):         # per tensor, absolute: a scalar's first moment is a cancelling sum of its gradients
+            n, scale = st[key].numel(), (10.0 ** (-(i % 4))) ** (1 if key == 'exp_avg' else 2)
+            assert float((got[off:off + n] - want[off:off + n]).abs().max()) <= 1e-6 * scale, (key, i)
+            off += n
+    print(f"fused Adam vs fp64 torch.optim.Adam after 6 steps: worst |dp| / |total update| {worst:.2e}")

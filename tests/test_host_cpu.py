@@ -191,6 +191,28 @@ def test_walker_visits_units_in_reference_order():
     assert kinds["model.down.0.downsample.conv"] == "layer"
 
 
+def test_fused_adam_segment_table():
+    """host side of edadm_fused_adam: every parameter element belongs to exactly one segment, segments never straddle two
+    tensors, flat offsets follow the GradBucket order, the group bit separates alphas from step sizes"""
+    from qdiff._fused_adam import segment_table, SEGMENT
+    params = [torch.zeros(3, 5), torch.zeros(2 * SEGMENT + 17), torch.zeros(()), torch.zeros(SEGMENT), torch.zeros(1)]
+    table, total = segment_table(params, n_group0=2)
+    assert total == sum(p.numel() for p in params) and table.dtype.name == "int64" and table.shape[1] == 3
+    flat_cover, off = [], 0
+    for i, p in enumerate(params):
+        rows = [r for r in table if p.data_ptr() <= r[0] < p.data_ptr() + 4 * max(1, p.numel())]
+        assert sum(int(r[2]) & 0xFFFFFFFF for r in rows) == p.numel()
+        for r in rows:
+            cnt, grp = int(r[2]) & 0xFFFFFFFF, int(r[2]) >> 32
+            assert 1 <= cnt <= SEGMENT and grp == (0 if i < 2 else 1)
+            assert (int(r[0]) - p.data_ptr()) // 4 == int(r[1]) - off          # same element in the tensor and in the flat buffer
+            flat_cover.append((int(r[1]), cnt))
+        off += p.numel()
+    flat_cover.sort()
+    assert flat_cover[0][0] == 0 and all(a + n == b for (a, n), (b, _) in zip(flat_cover, flat_cover[1:]))
+    assert flat_cover[-1][0] + flat_cover[-1][1] == total
+
+
 def test_grad_bucket_views_and_sharding():
     from qdiff import dist as qdist
     a = torch.nn.Parameter(torch.zeros(3, 4))
