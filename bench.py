@@ -259,9 +259,12 @@ def bench_recon(qnn, kind, shape, ctx, dev, world, iters, modes):
     from qdiff.quant_layer import backend
     # the headline blocks run the reference loop literally (FP forward inside every iteration); "weak_memoised_fp_taps" is the
     # product default, which computes the FP taps once per unit for all cached samples and gathers them per iteration
-    runs = [(m, m, False) for m in modes] + ([("weak_memoised_fp_taps", "weak", True)] if "weak" in modes else [])
-    for key, mode, memo in runs:
+    # "weak_torch_optim_adam": the literal loop with the two torch.optim.Adam (capturable) steps instead of edadm_fused_adam
+    runs = [(m, m, False, True) for m in modes] + ([("weak_memoised_fp_taps", "weak", True, True),
+                                                     ("weak_torch_optim_adam", "weak", False, False)] if "weak" in modes else [])
+    for key, mode, memo, fused_adam in runs:
         backend.recon_memoise_fp_taps = memo
+        backend.recon_fused_adam = fused_adam
         rb = 32 if mode == "weak" else max(1, 32 // world)
         per_unit = {}
         for label, (unit, is_layer) in units.items():
@@ -289,8 +292,10 @@ def bench_recon(qnn, kind, shape, ctx, dev, world, iters, modes):
         out[key] = {"batch_per_gpu": rb, "global_batch": rb * world, "units": per_unit, "geomean_iters_per_s": gm,
                      "geomean_samples_per_s": gm * rb * world}
     backend.recon_memoise_fp_taps = True
-    out["semantics"] = ("weak / strong: reference loop, quant fwd + FP fwd + quant fwd (FBR) + backward + 2 Adam steps, QDrop 0.5; "
-                        "weak_memoised_fp_taps: same losses and updates, the FP-model taps read from a per-unit table filled before the loop")
+    backend.recon_fused_adam = True
+    out["semantics"] = ("weak / strong: reference loop, quant fwd + FP fwd + quant fwd (FBR) + backward + 2 Adam steps (one fused pass), "
+                        "QDrop 0.5; weak_memoised_fp_taps: same losses and updates, the FP-model taps read from a per-unit table filled "
+                        "before the loop; weak_torch_optim_adam: the weak run with torch.optim.Adam stepping instead of edadm_fused_adam")
     return out
 
 
