@@ -30,6 +30,7 @@ CASES={
  "gemm_bf16x3_conv": ("reconstruction-loop convolution on the bf16 x 3 tcgen05 kernel (implicit GEMM, NHWC split operands, NCHW TMA store): 3x3 576->576 at 16x16, batch 32 (M=8192, N=576, K=5184); flops counted 3x (hi.hi + hi.lo + lo.hi)", None, 3*2*8192*576*5184),
  "gemm_bf16x3_wgrad": ("reconstruction-loop convolution WGRAD on the bf16 x 3 tcgen05 kernel: dW of the 3x3 576->576 conv at 16x16, batch 32 (pixels are the reduction: M=576, N=576 per tap, K=8192, 9 taps, split-K 4 with TMA reduce-add); flops counted 3x", None, 3*2*8192*576*5184),
  "gemm_bf16x3_linear": ("reconstruction-loop linear on the bf16 x 3 tcgen05 kernel: M=32768, N=3072, K=384; flops counted 3x", None, 3*2*32768*3072*384),
+ "fused_adam": ("both Adam updates of a reconstruction iteration in one pass (edadm_fused_adam), ImageNet transformer-block unit: 17.5 M alphas + 20 step sizes; read g, p, m, v, write p, m, v and the cleared g", 17547284*32, None),
  "qattn_church": ("fused quantized attention, church T=1024, d=24, 800 (batch x head)", None, 4*800*1024*1024*24),
 }
 for name,(note,nbytes,nops) in CASES.items():
