@@ -120,6 +120,36 @@ def unit_vectors():
     print("unit.npz", len(out))
 
 
+def unit_max_vectors():
+    """scale_method 'max' / 'max_scale' (init_quantization_scale_2, reference quant_layer.py:278-345): the constructor default of
+    UniformAffineQuantizer, unused by the scripts; (delta, zero_point) and the fake-quantized tensor for every branch."""
+    g = torch.Generator().manual_seed(21)
+    xs = {"act4d": torch.randn(4, 12, 6, 6, generator=g) * 1.7 + 0.3,
+          "pos3d": torch.softmax(torch.randn(3, 16, 16, generator=g), -1),
+          "w4d": torch.randn(10, 6, 3, 3, generator=g) * 0.07,
+          "w2d": torch.randn(9, 20, generator=g) * 0.2,
+          "tiny": torch.randn(5, 7, generator=g) * 1e-10}
+    cases = [("act4d", 8, False, False, False, "max"), ("act4d", 8, True, False, False, "max"), ("act4d", 6, False, False, False, "max_scale"),
+             ("pos3d", 8, False, False, True, "max"), ("pos3d", 8, False, False, False, "max"),
+             ("w4d", 4, True, True, False, "max"), ("w4d", 4, False, True, False, "max"), ("w4d", 8, True, True, False, "max_scale"),
+             ("w2d", 4, False, True, False, "max"), ("w2d", 3, True, True, False, "max"), ("tiny", 8, False, False, False, "max")]
+    out = {k: npy(v) for k, v in xs.items()}
+    out["cases"] = np.array(["|".join(map(str, c)) for c in cases])
+    for i, (name, bits, sym, cw, az, method) in enumerate(cases):
+        q = UniformAffineQuantizer(n_bits=bits, symmetric=sym, channel_wise=cw, scale_method=method, always_zero=az)
+        delta, zp = q.init_quantization_scale_2(xs[name], cw)
+        q.delta, q.zero_point = delta, zp
+        q.set_inited(True)
+        y = q(xs[name])
+        zp_t = zp if torch.is_tensor(zp) else torch.tensor(float(zp))
+        out.update({f"c{i}_delta": npy(delta), f"c{i}_zp": npy(zp_t.float()), f"c{i}_y": npy(y)})
+    # forward() of an un-inited quantizer with the constructor default takes the same route (:251, :260)
+    q = UniformAffineQuantizer(n_bits=8)
+    out["default_y"] = npy(q(xs["act4d"]))
+    np.savez_compressed(os.path.join(OUT, "unit_max.npz"), **out)
+    print("unit_max.npz", len(out))
+
+
 def _init_all(qnn, cali, bs):
     set_weight_quantize_params(qnn, cali)
     # the generic driver does not reset the LDM matmul quantizers: do it by hand (set_quantize_params_LDM.py:31-36)
@@ -395,9 +425,11 @@ def api_goldens():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["unit", "ddim", "ldm", "xattn", "cfg", "api"]
+    which = sys.argv[1:] or ["unit", "unit_max", "ddim", "ldm", "xattn", "cfg", "api"]
     if "unit" in which:
         unit_vectors()
+    if "unit_max" in which:
+        unit_max_vectors()
     if "ddim" in which:
         ddim_tiny()
     if "ldm" in which:

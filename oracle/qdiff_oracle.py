@@ -132,6 +132,30 @@ def init_scale(x, n_bits, channel_wise, sym=True, running=None):
     return delta, zp, one_side
 
 
+# ---- qdiff/quant_layer.py:278-345 (scale_method 'max' / 'max_scale': the tensor's extrema, no search) ----------
+def init_scale_max(x, n_bits, channel_wise, sym=False, always_zero=False, scale_method="max"):
+    """(delta, zero_point) of init_quantization_scale_2.  Per tensor (:303-327): Python-float (double) arithmetic on
+    `.item()` extrema -- x_min = min(min, 0), x_max = max(max, 0), both times (n_bits + 2) / 8 for 'max_scale';
+    delta = max(|x_min|, x_max) / n_levels when symmetric, else (max - min) / (n_levels - 1) from the RAW extrema
+    (:318, unscaled and not clamped to 0); floor 1e-8; zero_point = round(-x_min / delta) (Python round == half to even)
+    unless symmetric / always_zero (0); delta is cast to x's dtype at the end.  Channel-wise (:280-302): the same per
+    slice x[c], written into fp32 vectors shaped [C, 1, ...]."""
+    n_levels = 2 ** n_bits
+    if channel_wise:
+        pairs = [init_scale_max(x[c], n_bits, False, sym, always_zero, scale_method) for c in range(x.shape[0])]
+        shape = [x.shape[0]] + [1] * (x.dim() - 1)
+        return (torch.stack([d for d, _ in pairs]).reshape(shape), torch.stack([z for _, z in pairs]).reshape(shape))
+    lo, hi = x.min().item(), x.max().item()
+    x_min, x_max = min(lo, 0), max(hi, 0)
+    if "scale" in scale_method:
+        x_min, x_max = x_min * (n_bits + 2) / 8, x_max * (n_bits + 2) / 8
+    delta = max(abs(x_min), x_max) / n_levels if sym else float(hi - lo) / (n_levels - 1)
+    if delta < 1e-8:
+        delta = 1e-8
+    zp = round(-x_min / delta) if not (sym or always_zero) else 0
+    return torch.tensor(delta).type_as(x), torch.tensor(float(zp)).type_as(x)
+
+
 # ---- qdiff/adaptive_rounding.py -------------------------------------------------------------------
 GAMMA, ZETA = -0.1, 1.1
 
