@@ -146,6 +146,14 @@ def unit_max_vectors():
     # forward() of an un-inited quantizer with the constructor default takes the same route (:251, :260)
     q = UniformAffineQuantizer(n_bits=8)
     out["default_y"] = npy(q(xs["act4d"]))
+    # asymmetric, two-sided 'mse' ranges: perform_2D_search (:120-147), 100 clipping widths x n_levels zero-points
+    s2d = {"t4": (torch.randn(6, 40, generator=g) * 0.8 + 0.4, 4, False), "t8": (torch.randn(64, generator=g) * 1.5 - 0.2, 8, False),
+           "c3": (torch.randn(5, 4, 3, 3, generator=g) * 0.3 + 0.05, 3, True)}
+    for key, (x, bits, cw) in s2d.items():
+        q = UniformAffineQuantizer(n_bits=bits, symmetric=False, channel_wise=cw, scale_method='mse')
+        y = q(x)
+        assert q.one_side_dist == 'no'
+        out.update({f"s2d_{key}_x": npy(x), f"s2d_{key}_y": npy(y), f"s2d_{key}_delta": npy(q.delta), f"s2d_{key}_zp": npy(q.zero_point)})
     np.savez_compressed(os.path.join(OUT, "unit_max.npz"), **out)
     print("unit_max.npz", len(out))
 

@@ -109,15 +109,44 @@ def search_1d(x, n_levels, channel_wise, one_side_dist, num=100):
     return best_min, best_max
 
 
+# ---- qdiff/quant_layer.py:120-147 -----------------------------------------------------------------
+def search_2d(x, n_bits, channel_wise, num=100):
+    """asymmetric two-sided range: every clipping width xrange * i / num (i = 1..num) with every zero-point 0..n_levels-1"""
+    n_levels = 2 ** n_bits
+    if channel_wise:
+        y = torch.flatten(x, 1)
+        x_min, x_max = y.amin(1), y.amax(1)
+        x_max = torch.max(x_max, torch.zeros_like(x_max))   # :124-126 one-sided channels
+        x_min = torch.min(x_min, torch.zeros_like(x_min))
+    else:
+        x_min, x_max = x.amin(), x.amax()
+    xrange = x_max - x_min
+    best_score = torch.zeros_like(x_min) + 1e10
+    best_min, best_max = x_min.clone(), x_max.clone()
+    for i in range(1, num + 1):
+        tmp_min = torch.zeros_like(x_min)
+        tmp_max = xrange / num * i
+        tmp_delta = (tmp_max - tmp_min) / (2 ** n_bits - 1)
+        for zp in range(0, n_levels):
+            new_min, new_max = tmp_min - zp * tmp_delta, tmp_max - zp * tmp_delta
+            x_q = _quantize_minmax(x, new_max, new_min, n_levels, channel_wise)
+            score = _search_score(x, x_q, channel_wise)
+            best_min = torch.where(score < best_score, new_min, best_min)
+            best_max = torch.where(score < best_score, new_max, best_max)
+            best_score = torch.min(best_score, score)
+    return best_min, best_max
+
+
 # ---- qdiff/quant_layer.py:215-244 (init path for scale_method='mse', sym or one-sided) --------------
 def init_scale(x, n_bits, channel_wise, sym=True, running=None):
     """Returns (delta, zero_point, one_side_dist, running) following get_x_min_x_max +
     update_quantize_range (:79-85, only when `running` is a dict == leaf_param) + calculate_qparams."""
     n_levels = 2 ** n_bits
     one_side = "pos" if x.min() >= 0.0 else "neg" if x.max() <= 0.0 else "no"
-    if not (one_side != "no" or sym):
-        raise NotImplementedError("2-D search (asymmetric, two-sided) is not restated")
-    best_min, best_max = search_1d(x, n_levels, channel_wise, one_side)
+    if one_side != "no" or sym:          # :227-231
+        best_min, best_max = search_1d(x, n_levels, channel_wise, one_side)
+    else:
+        best_min, best_max = search_2d(x, n_bits, channel_wise)
     if running is not None:
         if running.get("min") is None:
             running["min"], running["max"] = best_min, best_max
