@@ -213,6 +213,25 @@ def test_fused_adam_segment_table():
     assert flat_cover[-1][0] + flat_cover[-1][1] == total
 
 
+def test_device_learning_rate_table_equals_torch_scheduler():
+    """the captured reconstruction step reads its learning rates from a table indexed by a device counter (`_cosine_lr`); the
+    reference steps torch's CosineAnnealingLR(T_max=iters, eta_min=0) (block_recon.py:114-117, 203-206): same schedule"""
+    from qdiff._recon_engine import _cosine_lr, LinearTempDecay
+    for lr0, iters in ((1e-2, 40), (4e-4, 1000), (1e-2, 7)):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.Adam([p], lr=lr0)
+        sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=iters, eta_min=0.)
+        for t in range(iters):
+            lr = opt.param_groups[0]['lr']
+            assert abs(lr - _cosine_lr(lr0, t, iters)) <= 1e-12 * lr0, (lr0, iters, t)
+            p.grad = torch.ones(1)
+            opt.step()
+            sched.step()
+    # temperature of the (disabled by every caller) rounding regulariser, block_recon.py:305-323: linear from start_b to end_b
+    td = LinearTempDecay(100, rel_start_decay=0.2, start_b=20, end_b=2)
+    assert td(1) == 20 and td(19) == 20 and td(20) == 20 and abs(td(60) - 11.0) < 1e-12 and td(100) == 2 and td(150) == 2
+
+
 def test_grad_bucket_views_and_sharding():
     from qdiff import dist as qdist
     a = torch.nn.Parameter(torch.zeros(3, 4))
